@@ -1,0 +1,81 @@
+"""ctypes binding of libwc_b200.so (include/wc_b200.h).  There is no CPU fallback: if the
+library is missing it is built with nvcc, and if that fails importing this module raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+import torch  # noqa: F401  (loads the CUDA runtime the library links against)
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+WC_DECOMP = {'cholesky': 0, 'zca': 1}
+INFO_SLOTS = 4
+INFO_NOT_PD, INFO_BAD_CLASS, INFO_JACOBI = 0, 1, 2
+
+
+class WcError(RuntimeError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    path = _build.LIB
+    if not os.path.exists(path) or os.environ.get('WC_B200_REBUILD'):
+        path = _build.build()
+    try:
+        return ctypes.CDLL(path)
+    except OSError as e:  # fail loudly: the product has no other implementation
+        raise WcError(f'cannot load {path}: {e}') from e
+
+
+lib = _load()
+
+_P = c_void_p
+_SIGS = {
+    'wc_version': (c_int, []),
+    'wc_path_for': (c_int, [c_int64, c_int, c_int, c_int]),
+    'wc_stats_workspace_bytes': (c_size_t, [c_int64, c_int, c_int]),
+    'wc_stats_fwd': (c_int, [_P, c_int64, c_int, c_int, _P, c_size_t, _P, _P, _P]),
+    'wc_stats_merge': (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    'wc_factor_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'wc_factor_fwd': (c_int, [_P, _P, _P, c_double, c_int, c_int, c_float, c_float, c_int, c_int, c_int,
+                              _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    'wc_compose_fwd': (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, c_int, _P,
+                               _P, _P, _P, _P, _P]),
+    'wc_apply_fwd': (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P, _P]),
+    'wc_reduce_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    'wc_reduce_bwd': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
+    'wc_color_bwd_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    'wc_color_bwd': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int,
+                             _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    'wc_factor_bwd_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'wc_factor_bwd': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_double, c_int, c_int, c_float, c_int, c_int,
+                              _P, _P, _P, c_size_t, _P]),
+    'wc_apply_bwd': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, c_int, _P, _P]),
+}
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+EXPORTS = tuple(_SIGS.keys())
+
+_ERRS = {-1: 'invalid argument', -2: 'workspace too small', -3: 'unsupported shape', -4: 'misaligned pointer'}
+
+
+def check(rc: int, what: str) -> None:
+    """Negative codes are argument errors (the reference raises ValueError / assert there,
+    gan/conditional_layers.py:615,628-632,768-770); positive codes are cudaError_t."""
+    if rc == 0:
+        return
+    if rc < 0:
+        raise ValueError(f'{what}: {_ERRS.get(rc, rc)}')
+    raise WcError(f'{what}: CUDA error {rc}')
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

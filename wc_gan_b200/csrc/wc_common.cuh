@@ -1,0 +1,55 @@
+// Shared helpers for the libwc_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/wc_b200.h"
+
+#define WC_CHECK_LAUNCH()                                   \
+  do {                                                      \
+    cudaError_t e__ = cudaGetLastError();                   \
+    if (e__ != cudaSuccess) return (int)e__;                \
+  } while (0)
+
+#define WC_CUDA(call)                                       \
+  do {                                                      \
+    cudaError_t e__ = (call);                               \
+    if (e__ != cudaSuccess) return (int)e__;                \
+  } while (0)
+
+static inline bool wc_aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+static inline size_t wc_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int wc_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+constexpr int WC_NUM_SMS = 148;  // B200: 2 dies x 74 SMs
+
+__device__ __forceinline__ float wc_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming 128-bit load that does not allocate in L1 (activations are read once per kernel)
+__device__ __forceinline__ float4 wc_ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// ---- internal launchers shared between translation units ---------------------------------
+// generic batched small matmul:  Cm[b1,b2] = alpha * sum_{q<nsum} opA opB + beta * Cm
+struct WcSmm {
+  const float* A; const float* B; float* C;
+  int M, N, K;                 // C is M x N, inner dimension K
+  long long rsA, csA;          // element (i,k) of op(A) at A[i*rsA + k*csA]
+  long long rsB, csB;          // element (k,j) of op(B) at B[k*rsB + j*csB]
+  long long rsC, csC;
+  int nb1, nb2;                // two batch dimensions (grid.z = nb1*nb2)
+  long long bA1, bA2, bB1, bB2, bC1, bC2;
+  int nsum;                    // extra summed dimension
+  long long sA, sB;
+  float alpha, beta;
+  int tri;                     // 0 none, 1 keep lower (incl. diag) of C, 2 keep upper (incl. diag); others zeroed
+};
+int wc_smm_launch(const WcSmm& p, cudaStream_t st);

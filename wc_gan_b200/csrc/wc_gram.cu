@@ -1,0 +1,416 @@
+// K1 (batch statistics) and K4 (backward reduction): "gram"-shaped reductions over rows,
+//   Out[slot][i][j] += sum_r (A[r,i] - ma[i]) * (B[r,j] - mb[j]),
+// FP32 FFMA path (any C, any g).  The tcgen05 path for C in {128,256} lives in wc_tc.cu.
+//
+// Reference segments replaced: gan/conditional_layers.py:652-660,:683 (K1) and TF autodiff of
+// :707,:824,:1010 / generator.py:50 w.r.t. the matrices (K4).
+#include "wc_common.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int TI = 64, TJ = 64, RK = 16, NT = 256;
+constexpr int UNIT_ROWS = 256;  // a work unit never crosses a sample boundary
+
+struct GramParams {
+  const float* A; const float* B;   // [rows][lda], [rows][ldb]
+  int lda, ldb;
+  const float* ma; const float* mb; // per-column shifts (nullable)
+  int nI, nJ;                       // columns of A / B taking part
+  int grouped;                      // 1: only tiles on the block diagonal (A == B, nI == nJ)
+  int g, tw, tpg;                   // group size, tile width along the diagonal (g < 64), tiles per group side (g >= 64)
+  int ntiles;
+  int N, HW;                        // samples, rows per sample
+  int ups;                          // units per sample
+  int units_per_chunk, nchunks;
+  const int32_t* order;             // processing order of samples (nullable = identity)
+  const int32_t* slot_of;           // slot (class) per sample, already clamped (nullable = 0)
+  float* out; long long out_slot_stride; int ldo;  // Out[slot][i][j]
+  float* asum; float* bsum; long long sum_slot_stride; // column sums per slot (nullable)
+  int atomic;                       // 1: atomicAdd into out[slot]; 0: store into out[chunk] (slot ignored)
+};
+
+__device__ __forceinline__ void tile_bounds(const GramParams& p, int tile, int& i0, int& iend, int& j0, int& jend,
+                                            bool& want_a, bool& want_b) {
+  if (p.grouped) {
+    if (p.g >= TI) {
+      int per = p.tpg * p.tpg;
+      int grp = tile / per, t = tile % per;
+      int ti = t / p.tpg, tj = t % p.tpg;
+      i0 = grp * p.g + ti * TI; iend = min(grp * p.g + p.g, i0 + TI);
+      j0 = grp * p.g + tj * TJ; jend = min(grp * p.g + p.g, j0 + TJ);
+      want_a = (tj == 0); want_b = false;
+    } else {
+      i0 = tile * p.tw; iend = min(p.nI, i0 + p.tw);
+      j0 = i0; jend = iend;
+      want_a = true; want_b = false;
+    }
+  } else {
+    int tjn = (p.nJ + TJ - 1) / TJ;
+    int ti = tile / tjn, tj = tile % tjn;
+    i0 = ti * TI; iend = min(p.nI, i0 + TI);
+    j0 = tj * TJ; jend = min(p.nJ, j0 + TJ);
+    want_a = (tj == 0); want_b = (ti == 0);
+  }
+}
+
+template <bool kVec>
+__device__ __forceinline__ float4 load4(const float* base, long long row_off, int col, int cend, const float* shift, bool row_ok) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!row_ok) return v;
+  if (kVec) {
+    if (col + 3 < cend) {
+      v = wc_ldg_stream(reinterpret_cast<const float4*>(base + row_off + col));
+      if (shift) { float4 s = *reinterpret_cast<const float4*>(shift + col); v.x -= s.x; v.y -= s.y; v.z -= s.z; v.w -= s.w; }
+      return v;
+    }
+  }
+  float t[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int c = col + q;
+    t[q] = (c < cend) ? (__ldg(base + row_off + c) - (shift ? shift[c] : 0.f)) : 0.f;
+  }
+  return make_float4(t[0], t[1], t[2], t[3]);
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(NT) gram_kernel(GramParams p) {
+  __shared__ __align__(16) float As[2][RK][TI];
+  __shared__ __align__(16) float Bs[2][RK][TJ];
+  __shared__ float red[RK][TI];
+
+  const int tile = blockIdx.x, chunk = blockIdx.y;
+  int i0, iend, j0, jend; bool want_a, want_b;
+  tile_bounds(p, tile, i0, iend, j0, jend, want_a, want_b);
+  want_a = want_a && (p.asum != nullptr);
+  want_b = want_b && (p.bsum != nullptr);
+
+  const int t = threadIdx.x;
+  const int lrow = t >> 4, lcol = (t & 15) * 4;   // loader mapping: row in step, first column
+  const int tx = t & 15, ty = t >> 4;             // compute mapping: 4x4 micro tile
+
+  const long long total_units = (long long)p.N * p.ups;
+  long long u_begin = (long long)chunk * p.units_per_chunk;
+  long long u_end = min(total_units, u_begin + p.units_per_chunk);
+
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  float4 asum4 = make_float4(0, 0, 0, 0), bsum4 = make_float4(0, 0, 0, 0);
+
+  // step iterator state
+  long long unit = u_begin;
+  int r_in_unit = 0;
+  auto unit_info = [&](long long u, int& sample, int& row0, int& nrows) {
+    int sidx = (int)(u / p.ups), sub = (int)(u % p.ups);
+    sample = p.order ? p.order[sidx] : sidx;
+    row0 = sub * UNIT_ROWS;
+    nrows = min(UNIT_ROWS, p.HW - row0);
+  };
+
+  int cur_slot = -1;
+  float4 ra, rb;
+  int next_slot = 0;
+  bool have = unit < u_end;
+  auto fetch = [&]() {
+    int sample, row0, nrows;
+    unit_info(unit, sample, row0, nrows);
+    next_slot = p.slot_of ? p.slot_of[sample] : 0;
+    int r = r_in_unit + lrow;
+    bool ok = r < nrows;
+    long long grow = (long long)sample * p.HW + row0 + r;
+    ra = load4<kVec>(p.A, grow * p.lda, i0 + lcol, iend, p.ma, ok);
+    rb = load4<kVec>(p.B, grow * p.ldb, j0 + lcol, jend, p.mb, ok);
+    r_in_unit += RK;
+    if (r_in_unit >= nrows) { r_in_unit = 0; ++unit; }
+  };
+  auto flush = [&](int slot) {
+    float* o = p.atomic ? p.out + (long long)slot * p.out_slot_stride
+                        : p.out + (long long)chunk * p.out_slot_stride;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      int i = i0 + ty * 4 + a;
+      if (i >= iend) continue;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        int j = j0 + tx * 4 + b;
+        if (j >= jend) continue;
+        if (p.atomic) atomicAdd(o + (long long)i * p.ldo + j, acc[a][b]);
+        else o[(long long)i * p.ldo + j] = acc[a][b];
+        acc[a][b] = 0.f;
+      }
+    }
+    if (want_a || want_b) {
+      for (int pass = 0; pass < 2; ++pass) {
+        bool want = pass == 0 ? want_a : want_b;
+        if (!want) continue;
+        float4 v = pass == 0 ? asum4 : bsum4;
+        __syncthreads();
+        red[lrow][lcol + 0] = v.x; red[lrow][lcol + 1] = v.y; red[lrow][lcol + 2] = v.z; red[lrow][lcol + 3] = v.w;
+        __syncthreads();
+        if (t < TI) {
+          float sacc = 0.f;
+#pragma unroll
+          for (int q = 0; q < RK; ++q) sacc += red[q][t];
+          int c0 = pass == 0 ? i0 : j0, cend = pass == 0 ? iend : jend;
+          float* so = (pass == 0 ? p.asum : p.bsum) +
+                      (p.atomic ? (long long)slot : (long long)chunk) * p.sum_slot_stride;
+          if (c0 + t < cend) { if (p.atomic) atomicAdd(so + c0 + t, sacc); else so[c0 + t] = sacc; }
+        }
+      }
+      asum4 = make_float4(0, 0, 0, 0); bsum4 = make_float4(0, 0, 0, 0);
+      __syncthreads();
+    }
+  };
+
+  if (have) {
+    fetch();
+    *reinterpret_cast<float4*>(&As[0][lrow][lcol]) = ra;
+    *reinterpret_cast<float4*>(&Bs[0][lrow][lcol]) = rb;
+    if (want_a) { asum4.x += ra.x; asum4.y += ra.y; asum4.z += ra.z; asum4.w += ra.w; }
+    if (want_b) { bsum4.x += rb.x; bsum4.y += rb.y; bsum4.z += rb.z; bsum4.w += rb.w; }
+    cur_slot = next_slot;
+  }
+  __syncthreads();
+  int buf = 0;
+  while (have) {
+    bool more = unit < u_end;
+    int slot_after = cur_slot;
+    if (more) { fetch(); slot_after = next_slot; }
+    // compute current step
+#pragma unroll
+    for (int k = 0; k < RK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(av[x], bv[y], acc[x][y]);
+    }
+    if (!more) break;
+    if (slot_after != cur_slot) {  // block-uniform: all threads read the same unit
+      flush(cur_slot);
+      cur_slot = slot_after;
+    }
+    *reinterpret_cast<float4*>(&As[buf ^ 1][lrow][lcol]) = ra;
+    *reinterpret_cast<float4*>(&Bs[buf ^ 1][lrow][lcol]) = rb;
+    if (want_a) { asum4.x += ra.x; asum4.y += ra.y; asum4.z += ra.z; asum4.w += ra.w; }
+    if (want_b) { bsum4.x += rb.x; bsum4.y += rb.y; bsum4.z += rb.z; bsum4.w += rb.w; }
+    __syncthreads();
+    buf ^= 1;
+  }
+  if (cur_slot >= 0) flush(cur_slot);
+  else if (!p.atomic) {  // empty chunk in store mode: partials must still be defined
+    cur_slot = 0; flush(0);
+  }
+}
+
+// ---- K1 helpers ---------------------------------------------------------------------------
+// pivot[c] = mean of the first `rows` rows: a cheap shift that removes the E[xx^T]-mu mu^T cancellation
+__global__ void pivot_kernel(const float* __restrict__ x, int rows, int C, float* __restrict__ pivot) {
+  int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  int w = threadIdx.x >> 5;  // 8 warps stride over rows
+  __shared__ float part[8][32];
+  float s = 0.f;
+  if (c < C) for (int r = w; r < rows; r += 8) s += x[(long long)r * C + c];
+  part[w][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (w == 0 && c < C) {
+    float a = 0.f;
+    for (int q = 0; q < 8; ++q) a += part[q][threadIdx.x];
+    pivot[c] = a / (float)rows;
+  }
+}
+
+// reduce chunk partials (fixed order => deterministic), correct for the pivot:
+//   d = sum(x-p)/M, mean = p + d, S = S_p - M d d^T   (diagonal blocks only)
+__global__ void stats_finalize_kernel(const float* __restrict__ partS, const float* __restrict__ partSum,
+                                      int nchunks, long long strideS, int C, int g, double M,
+                                      const float* __restrict__ pivot, float* __restrict__ mean, float* __restrict__ S) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)C * g;
+  if (idx >= total) return;
+  int grp = (int)(idx / ((long long)g * g));
+  int rem = (int)(idx % ((long long)g * g));
+  int i = grp * g + rem / g, j = grp * g + rem % g;
+  float s = 0.f, di = 0.f, dj = 0.f;
+  for (int q = 0; q < nchunks; ++q) {
+    s += partS[(long long)q * strideS + (long long)i * C + j];
+    di += partSum[(long long)q * C + i];
+    dj += partSum[(long long)q * C + j];
+  }
+  double ddi = (double)di / M, ddj = (double)dj / M;
+  S[idx] = (float)((double)s - M * ddi * ddj);
+  if (rem % g == rem / g) mean[i] = (float)((double)pivot[i] + ddi);
+}
+
+// Chan merge of R shard records {count, mean[C], S[G g g]}
+__global__ void stats_merge_kernel(const float* __restrict__ rec, int R, int C, int g,
+                                   float* __restrict__ mean, float* __restrict__ S, float* __restrict__ count_total) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)C * g;
+  if (idx >= total) return;
+  long long stride = 1 + C + total;
+  int grp = (int)(idx / ((long long)g * g));
+  int rem = (int)(idx % ((long long)g * g));
+  int i = grp * g + rem / g, j = grp * g + rem % g;
+  double n = 0, mi = 0, mj = 0;
+  for (int r = 0; r < R; ++r) {
+    double nr = rec[r * stride];
+    n += nr; mi += nr * rec[r * stride + 1 + i]; mj += nr * rec[r * stride + 1 + j];
+  }
+  mi /= n; mj /= n;
+  double s = 0;
+  for (int r = 0; r < R; ++r) {
+    double nr = rec[r * stride];
+    double di = rec[r * stride + 1 + i] - mi, dj = rec[r * stride + 1 + j] - mj;
+    s += rec[r * stride + 1 + C + idx] + nr * di * dj;
+  }
+  S[idx] = (float)s;
+  if (rem % g == rem / g) mean[i] = (float)mi;
+  if (idx == 0) count_total[0] = (float)n;
+}
+
+// ---- K4 helper: stable counting sort of samples by class (one CTA) -----------------------------
+__global__ void class_order_kernel(const int32_t* __restrict__ cls, int N, int K,
+                                   int32_t* __restrict__ order, int32_t* __restrict__ slot_of) {
+  extern __shared__ int sh[];  // [K] starts
+  int* start = sh;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) start[k] = 0;
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    int c = cls[n]; c = c < 0 ? 0 : (c >= K ? K - 1 : c);
+    slot_of[n] = c;
+    atomicAdd(&start[c], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int k = 0; k < K; ++k) { int c = start[k]; start[k] = run; run += c; }
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    int c = slot_of[n], rank = 0;
+    for (int m = 0; m < n; ++m) rank += (slot_of[m] == c);   // written above by this or another thread, after the barrier
+    order[start[c] + rank] = n;
+  }
+}
+
+struct StatsPlan { int ntiles, nchunks, units_per_chunk, ups, tw, tpg; size_t off_pivot, off_sum, off_S, bytes; };
+
+StatsPlan plan_stats(int64_t M, int C, int g) {
+  StatsPlan pl{};
+  if (g >= TI) { pl.tpg = wc_cdiv(g, TI); pl.ntiles = (C / g) * pl.tpg * pl.tpg; pl.tw = TI; }
+  else { pl.tw = (TI / g) * g; pl.tpg = 1; pl.ntiles = wc_cdiv(C, pl.tw); }
+  pl.ups = wc_cdiv(M, UNIT_ROWS);
+  int want = std::max(1, (4 * WC_NUM_SMS) / pl.ntiles);
+  int by_rows = (int)(M / 512 > 0 ? M / 512 : 1);
+  pl.nchunks = std::min(std::min(want, by_rows), pl.ups);
+  pl.units_per_chunk = wc_cdiv(pl.ups, pl.nchunks);
+  pl.nchunks = wc_cdiv(pl.ups, pl.units_per_chunk);
+  pl.off_pivot = 0;
+  pl.off_sum = wc_align_up((size_t)C * 4, 256);
+  pl.off_S = pl.off_sum + wc_align_up((size_t)pl.nchunks * C * 4, 256);
+  pl.bytes = pl.off_S + (size_t)pl.nchunks * C * C * 4;
+  return pl;
+}
+
+}  // namespace
+
+extern "C" size_t wc_stats_workspace_bytes(int64_t M, int C, int g) {
+  if (M <= 0 || C <= 0 || g <= 0 || C % g) return 0;
+  return plan_stats(M, C, g).bytes;
+}
+
+extern "C" int wc_stats_fwd(const float* x, int64_t M, int C, int g, float* workspace, size_t workspace_bytes,
+                            float* mean, float* S, wc_stream_t stream) {
+  if (!x || !workspace || !mean || !S || M <= 0 || C <= 0 || g <= 0 || C % g) return WC_E_ARG;
+  if (M > (int64_t)INT32_MAX) return WC_E_UNSUPPORTED;
+  StatsPlan pl = plan_stats(M, C, g);
+  if (workspace_bytes < pl.bytes) return WC_E_WORKSPACE;
+  if (!wc_aligned16(workspace)) return WC_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* pivot = reinterpret_cast<float*>(ws + pl.off_pivot);
+  float* psum = reinterpret_cast<float*>(ws + pl.off_sum);
+  float* pS = reinterpret_cast<float*>(ws + pl.off_S);
+  int prow = (int)(M < 1024 ? M : 1024);
+  pivot_kernel<<<wc_cdiv(C, 32), 256, 0, st>>>(x, prow, C, pivot);
+  WC_CHECK_LAUNCH();
+  GramParams p{};
+  p.A = x; p.B = x; p.lda = C; p.ldb = C; p.ma = pivot; p.mb = pivot; p.nI = C; p.nJ = C;
+  p.grouped = 1; p.g = g; p.tw = pl.tw; p.tpg = pl.tpg; p.ntiles = pl.ntiles;
+  p.N = 1; p.HW = (int)M; p.ups = pl.ups; p.units_per_chunk = pl.units_per_chunk; p.nchunks = pl.nchunks;
+  p.order = nullptr; p.slot_of = nullptr;
+  p.out = pS; p.out_slot_stride = (long long)C * C; p.ldo = C;
+  p.asum = psum; p.bsum = nullptr; p.sum_slot_stride = C; p.atomic = 0;
+  dim3 grid(pl.ntiles, pl.nchunks);
+  bool vec = (C % 4 == 0) && (g % 4 == 0) && wc_aligned16(x);
+  if (vec) gram_kernel<true><<<grid, NT, 0, st>>>(p); else gram_kernel<false><<<grid, NT, 0, st>>>(p);
+  WC_CHECK_LAUNCH();
+  long long total = (long long)C * g;
+  stats_finalize_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(pS, psum, pl.nchunks, (long long)C * C, C, g, (double)M, pivot, mean, S);
+  WC_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int wc_stats_merge(const float* records, int R, int C, int g, float* mean, float* S, float* count_total,
+                              wc_stream_t stream) {
+  if (!records || !mean || !S || !count_total || R <= 0 || C <= 0 || g <= 0 || C % g) return WC_E_ARG;
+  long long total = (long long)C * g;
+  stats_merge_kernel<<<wc_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(records, R, C, g, mean, S, count_total);
+  WC_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" size_t wc_reduce_workspace_bytes(int N, int HW, int Cin, int Cout, int K) {
+  if (N <= 0 || HW <= 0 || Cin <= 0 || Cout <= 0 || K <= 0) return 0;
+  return wc_align_up((size_t)N * 4, 256) * 2;
+}
+
+extern "C" int wc_reduce_bwd(const float* x, const float* dy, int N, int HW, int Cin, int Cout,
+                             const float* mean, const int32_t* cls, int K,
+                             float* P, float* s, float* workspace, size_t workspace_bytes, wc_stream_t stream) {
+  if (!x || !dy || !P || !s || N <= 0 || HW <= 0 || Cin <= 0 || Cout <= 0 || K <= 0) return WC_E_ARG;
+  if ((int64_t)N * HW > (int64_t)INT32_MAX) return WC_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool cond = (cls != nullptr) && K > 1;
+  int32_t *order = nullptr, *slot_of = nullptr;
+  if (cond) {
+    size_t need = wc_reduce_workspace_bytes(N, HW, Cin, Cout, K);
+    if (!workspace || workspace_bytes < need) return WC_E_WORKSPACE;
+    if (K > 8192) return WC_E_UNSUPPORTED;
+    order = reinterpret_cast<int32_t*>(workspace);
+    slot_of = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + need / 2);
+    class_order_kernel<<<1, 1024, K * sizeof(int), st>>>(cls, N, K, order, slot_of);
+    WC_CHECK_LAUNCH();
+  }
+  WC_CUDA(cudaMemsetAsync(P, 0, (size_t)K * Cin * Cout * 4, st));
+  WC_CUDA(cudaMemsetAsync(s, 0, (size_t)K * Cout * 4, st));
+  GramParams p{};
+  p.A = x; p.B = dy; p.lda = Cin; p.ldb = Cout; p.ma = mean; p.mb = nullptr; p.nI = Cin; p.nJ = Cout;
+  p.grouped = 0; p.g = Cin; p.tw = TI; p.tpg = 1;
+  p.ntiles = wc_cdiv(Cin, TI) * wc_cdiv(Cout, TJ);
+  // unconditional: one virtual sample of all rows so that units are full
+  if (cond) { p.N = N; p.HW = HW; } else { p.N = 1; p.HW = N * HW; }
+  p.ups = wc_cdiv(p.HW, UNIT_ROWS);
+  long long units = (long long)p.N * p.ups;
+  long long rows = (long long)N * HW;
+  long long want = std::max(1, (4 * WC_NUM_SMS) / p.ntiles);
+  long long by_rows = rows / 512 > 0 ? rows / 512 : 1;
+  long long nch = std::min(std::min(want, by_rows), units);
+  p.units_per_chunk = (int)((units + nch - 1) / nch);
+  p.nchunks = (int)((units + p.units_per_chunk - 1) / p.units_per_chunk);
+  p.order = order; p.slot_of = slot_of;
+  p.out = P; p.out_slot_stride = (long long)Cin * Cout; p.ldo = Cout;
+  p.asum = nullptr; p.bsum = s; p.sum_slot_stride = Cout; p.atomic = 1;
+  dim3 grid(p.ntiles, p.nchunks);
+  bool vec = (Cin % 4 == 0) && (Cout % 4 == 0) && wc_aligned16(x) && wc_aligned16(dy) && (!mean || wc_aligned16(mean));
+  if (vec) gram_kernel<true><<<grid, NT, 0, st>>>(p); else gram_kernel<false><<<grid, NT, 0, st>>>(p);
+  WC_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,706 @@
+// K2 / K2b / K5a / K5b: the small-matrix stages of the WC layer (everything that is C x C,
+// never M x C).  These are latency-bound; see DESIGN.md for the launch list.
+//
+// Reference segments replaced: gan/conditional_layers.py:662-704 (factorisation, moving
+// averages, shrinkage, renorm, test path), generator.py:41-78 + conditional_layers.py:811-819,
+// :993-1005 (per-class kernels), and TF autodiff of all of them.
+#include "wc_common.cuh"
+#include <math.h>
+
+// =============================================================================================
+// generic batched small matmul
+// =============================================================================================
+namespace {
+
+struct SmmExtra { const float* count_dev; float count_host; int count_mode; float diag_scale; };
+
+__global__ void __launch_bounds__(256) smm_kernel(WcSmm p, SmmExtra ex) {
+  __shared__ float As[32][33];
+  __shared__ float Bs[32][33];
+  const int z = blockIdx.z, b1 = z / p.nb2, b2 = z % p.nb2;
+  const float* A = p.A + b1 * p.bA1 + b2 * p.bA2;
+  const float* B = p.B + b1 * p.bB1 + b2 * p.bB2;
+  float* C = p.C + b1 * p.bC1 + b2 * p.bC2;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const bool a_kfast = (p.csA == 1) || (p.rsA != 1);   // which index varies fastest across threads when loading
+  const bool b_jfast = (p.csB == 1) || (p.rsB != 1);
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int q = 0; q < p.nsum; ++q) {
+    const float* Aq = A + (long long)q * p.sA;
+    const float* Bq = B + (long long)q * p.sB;
+    for (int k0 = 0; k0 < p.K; k0 += 32) {
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        int idx = threadIdx.x + e * 256;
+        int lo = idx & 31, hi = idx >> 5;
+        int ii = a_kfast ? hi : lo, kk = a_kfast ? lo : hi;
+        float v = 0.f;
+        if (i0 + ii < p.M && k0 + kk < p.K) v = Aq[(long long)(i0 + ii) * p.rsA + (long long)(k0 + kk) * p.csA];
+        As[ii][kk] = v;
+        int jj = b_jfast ? lo : hi, kb = b_jfast ? hi : lo;
+        float w = 0.f;
+        if (j0 + jj < p.N && k0 + kb < p.K) w = Bq[(long long)(k0 + kb) * p.rsB + (long long)(j0 + jj) * p.csB];
+        Bs[kb][jj] = w;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) {
+        float a0 = As[ty * 2][kk], a1 = As[ty * 2 + 1][kk];
+        float c0 = Bs[kk][tx * 2], c1 = Bs[kk][tx * 2 + 1];
+        acc[0][0] = fmaf(a0, c0, acc[0][0]); acc[0][1] = fmaf(a0, c1, acc[0][1]);
+        acc[1][0] = fmaf(a1, c0, acc[1][0]); acc[1][1] = fmaf(a1, c1, acc[1][1]);
+      }
+    }
+  }
+  float alpha = p.alpha;
+  if (ex.count_mode) {
+    float cnt = ex.count_dev ? ex.count_dev[0] : ex.count_host;
+    alpha /= (ex.count_mode == 1 ? cnt : (cnt - 1.f));
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      int i = i0 + ty * 2 + a, j = j0 + tx * 2 + b;
+      if (i >= p.M || j >= p.N) continue;
+      float* cp = C + (long long)i * p.rsC + (long long)j * p.csC;
+      float v = alpha * acc[a][b];
+      if (i == j) v *= ex.diag_scale;
+      if ((p.tri == 1 && j > i) || (p.tri == 2 && j < i)) v = 0.f;
+      else if (p.beta != 0.f) v += p.beta * (*cp);
+      *cp = v;
+    }
+}
+
+int smm(const WcSmm& p, cudaStream_t st, const float* count_dev = nullptr, float count_host = 0.f,
+        int count_mode = 0, float diag_scale = 1.f) {
+  if (p.M <= 0 || p.N <= 0 || p.nb1 <= 0 || p.nb2 <= 0) return 0;
+  dim3 grid(wc_cdiv(p.N, 32), wc_cdiv(p.M, 32), p.nb1 * p.nb2);
+  SmmExtra ex{count_dev, count_host, count_mode, diag_scale};
+  smm_kernel<<<grid, 256, 0, st>>>(p, ex);
+  WC_CHECK_LAUNCH();
+  return 0;
+}
+
+WcSmm smm_init() {
+  WcSmm p{};
+  p.nb1 = p.nb2 = 1; p.nsum = 1; p.alpha = 1.f; p.beta = 0.f; p.tri = 0;
+  return p;
+}
+
+// C[grp] (g x n, row stride ldc) = alpha * op(W[grp]) (g x g) * B[grp rows] ; batched over (outer nb1, groups)
+// W is (G,g,g).  transW: use W^T.
+WcSmm smm_blockdiag_left(const float* W, bool transW, const float* B, float* C, int g, int G, int ncols, int ld,
+                         int nouter, long long outer_stride) {
+  WcSmm p = smm_init();
+  p.A = W; p.B = B; p.C = C; p.M = g; p.N = ncols; p.K = g;
+  p.rsA = transW ? 1 : g; p.csA = transW ? g : 1;
+  p.rsB = ld; p.csB = 1; p.rsC = ld; p.csC = 1;
+  p.nb1 = nouter; p.nb2 = G;
+  p.bA1 = 0; p.bA2 = (long long)g * g;
+  p.bB1 = outer_stride; p.bB2 = (long long)g * ld;
+  p.bC1 = outer_stride; p.bC2 = (long long)g * ld;
+  return p;
+}
+
+// (G,g,g) x (G,g,g) -> (G,g,g) with optional transposes
+WcSmm smm_gg(const float* A, bool tA, const float* B, bool tB, float* C, int g, int G) {
+  WcSmm p = smm_init();
+  p.A = A; p.B = B; p.C = C; p.M = p.N = p.K = g;
+  p.rsA = tA ? 1 : g; p.csA = tA ? g : 1;
+  p.rsB = tB ? 1 : g; p.csB = tB ? g : 1;
+  p.rsC = g; p.csC = 1;
+  p.nb1 = 1; p.nb2 = G;
+  p.bA2 = p.bB2 = p.bC2 = (long long)g * g;
+  return p;
+}
+
+// =============================================================================================
+// K2: prep (scale, EMA, shrink), Cholesky + triangular inverse, Jacobi eigensolver
+// =============================================================================================
+__global__ void factor_prep_kernel(const float* __restrict__ mean, const float* __restrict__ S,
+                                   const float* count_dev, float count_host, int C, int g, float eps, float extra_eps,
+                                   float momentum, int training, float* moving_mean, float* moving_cov,
+                                   float* __restrict__ Ashr) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)C * g;
+  if (idx >= total) return;
+  int rem = (int)(idx % ((long long)g * g));
+  int r = rem / g, c = rem % g;
+  float cov;
+  if (training) {
+    float cnt = count_dev ? count_dev[0] : count_host;
+    // symmetrise on read: the two triangles of S may differ in the last bit (different summation order)
+    long long base = idx - rem;
+    cov = 0.5f * (S[base + (long long)r * g + c] + S[base + (long long)c * g + r]) / (cnt - 1.f);
+    moving_cov[idx] = moving_cov[idx] * momentum + cov * (1.f - momentum);        // conditional_layers.py:687-689
+    if (r == c) {
+      int ch = (int)(idx / ((long long)g * g)) * g + r;
+      moving_mean[ch] = moving_mean[ch] * momentum + mean[ch] * (1.f - momentum);  // :684-686
+    }
+  } else {
+    cov = moving_cov[idx];
+  }
+  Ashr[idx] = (1.f - eps) * cov + (r == c ? eps + extra_eps : 0.f);                // :691 (+ :671 for ZCA)
+}
+
+__device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }   // packed lower, j <= i
+
+// One CTA per group.  Packed lower-triangular matrix in shared memory:
+// right-looking Cholesky (one column per step), then row-by-row in-place inverse.
+__global__ void __launch_bounds__(1024) chol_inv_kernel(const float* __restrict__ Ain, int g,
+                                                        float* __restrict__ Lout, float* __restrict__ Linv_out,
+                                                        int32_t* info) {
+  extern __shared__ float sm[];
+  float* a = sm;                       // g(g+1)/2
+  float* col = a + g * (g + 1) / 2;    // g
+  float* piv = col + g;                // g
+  const int grp = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
+  const float* Ag = Ain + (long long)grp * g * g;
+  for (int idx = t; idx < g * g; idx += nt) {
+    int i = idx / g, j = idx % g;
+    if (j <= i) a[pk(i, j)] = Ag[idx];
+  }
+  const int warp = t >> 5, lane = t & 31, nw = nt >> 5;
+  for (int k = 0; k < g; ++k) {
+    __syncthreads();
+    float p = a[pk(k, k)];
+    if (!(p > 0.f)) {  // also catches NaN
+      if (t == 0 && info) atomicCAS(&info[WC_INFO_NOT_PD], 0, grp * g + k + 1);
+      p = 1e-30f;
+    }
+    for (int i = k + 1 + t; i < g; i += nt) col[i] = a[pk(i, k)];
+    if (t == 0) piv[k] = p;
+    __syncthreads();
+    float inv = 1.f / p;
+    for (int i = k + 1 + warp; i < g; i += nw) {
+      float lik = col[i] * inv;
+      float* row = a + pk(i, 0);
+      for (int j = k + 1 + lane; j <= i; j += 32) row[j] = fmaf(-lik, col[j], row[j]);
+    }
+  }
+  __syncthreads();
+  // scale columns: L_ij = a_ij / sqrt(piv_j), L_jj = sqrt(piv_j)
+  for (int idx = t; idx < g * g; idx += nt) {
+    int i = idx / g, j = idx % g;
+    if (j < i) a[pk(i, j)] *= rsqrtf(piv[j]);
+    else if (j == i) a[pk(i, i)] = sqrtf(piv[i]);
+  }
+  __syncthreads();
+  if (Lout) {
+    float* Lg = Lout + (long long)grp * g * g;
+    for (int idx = t; idx < g * g; idx += nt) {
+      int i = idx / g, j = idx % g;
+      Lg[idx] = (j <= i) ? a[pk(i, j)] : 0.f;
+    }
+  }
+  if (!Linv_out) return;
+  __syncthreads();
+  // in-place inverse, row by row: X[i,j] = (delta_ij - sum_{k=j}^{i-1} L[i,k] X[k,j]) / L[i,i]
+  // thread (j, part): 4 threads share one column j and split the k range
+  const int part = t & 3, jcol = t >> 2;
+  for (int i = 0; i < g; ++i) {
+    float lii = a[pk(i, i)];
+    float v = 0.f;
+    bool active = jcol <= i && jcol < g;   // blockDim.x >= 4 g is required by the launcher
+    if (active) {
+      const float* row = a + pk(i, 0);
+      float sacc = 0.f;
+      for (int k = jcol + part; k < i; k += 4) sacc = fmaf(row[k], a[pk(k, jcol)], sacc);
+      v = sacc;
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    __syncthreads();   // all reads of row i (as L) done before it is overwritten with X
+    if (active && part == 0) a[pk(i, jcol)] = ((jcol == i ? 1.f : 0.f) - v) / lii;
+    __syncthreads();
+  }
+  float* Xg = Linv_out + (long long)grp * g * g;
+  for (int idx = t; idx < g * g; idx += nt) {
+    int i = idx / g, j = idx % g;
+    Xg[idx] = (j <= i) ? a[pk(i, j)] : 0.f;
+  }
+}
+
+// One-sided (Hestenes) Jacobi SVD of the Cholesky factor L (A = L L^T = U diag(sigma^2) U^T).
+// One CTA per group; Bm is a (G,g,g) COLUMN-major scratch (column j contiguous) in global memory (L1/L2
+// resident, only this CTA touches its slice).  A warp owns one column pair per step.
+__global__ void __launch_bounds__(1024) jacobi_kernel(const float* __restrict__ L, int g, float* __restrict__ Bm,
+                                                      float* __restrict__ U, float* __restrict__ lam, int32_t* info) {
+  __shared__ int pairs[2][256];      // round-robin tournament positions (g <= 512)
+  __shared__ int rotated;
+  const int grp = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
+  const int warp = t >> 5, lane = t & 31, nw = nt >> 5;
+  const float* Lg = L + (long long)grp * g * g;
+  float* B = Bm + (long long)grp * g * g;
+  for (int idx = t; idx < g * g; idx += nt) {
+    int i = idx / g, j = idx % g;
+    B[(long long)j * g + i] = Lg[idx];     // column-major copy
+  }
+  const int n = (g + 1) & ~1;              // even number of players (one dummy when g is odd)
+  const int half = n / 2;
+  int sweep = 0;
+  for (; sweep < 20; ++sweep) {
+    if (t == 0) rotated = 0;
+    for (int i = t; i < half; i += nt) { pairs[0][i] = i; pairs[1][i] = n - 1 - i; }
+    __syncthreads();
+    for (int round = 0; round < n - 1; ++round) {
+      for (int pi = warp; pi < half; pi += nw) {
+        int p = pairs[0][pi], q = pairs[1][pi];
+        if (p >= g || q >= g) continue;
+        float* bp = B + (long long)p * g;
+        float* bq = B + (long long)q * g;
+        float al = 0.f, be = 0.f, ga = 0.f;
+        for (int i = lane; i < g; i += 32) { float x = bp[i], y = bq[i]; al = fmaf(x, x, al); be = fmaf(y, y, be); ga = fmaf(x, y, ga); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          al += __shfl_xor_sync(0xffffffffu, al, o);
+          be += __shfl_xor_sync(0xffffffffu, be, o);
+          ga += __shfl_xor_sync(0xffffffffu, ga, o);
+        }
+        if (fabsf(ga) > 1e-6f * sqrtf(al * be) && ga != 0.f) {
+          float zeta = (be - al) / (2.f * ga);
+          float tt = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
+          float c = rsqrtf(1.f + tt * tt), s = c * tt;
+          for (int i = lane; i < g; i += 32) {
+            float x = bp[i], y = bq[i];
+            bp[i] = c * x - s * y;
+            bq[i] = s * x + c * y;
+          }
+          if (lane == 0) rotated = 1;
+        }
+      }
+      __syncthreads();
+      // rotate the tournament: position 0 of row 0 is fixed
+      int np0 = -1, np1 = -1;
+      if (t < half) {
+        np0 = (t == 0) ? pairs[0][0] : (t == 1 ? pairs[1][0] : pairs[0][t - 1]);
+        np1 = (t == half - 1) ? pairs[0][half - 1] : pairs[1][t + 1];
+      }
+      __syncthreads();
+      if (t < half) { pairs[0][t] = np0; pairs[1][t] = np1; }
+      __syncthreads();
+    }
+    int again = rotated;
+    __syncthreads();
+    if (!again) break;
+  }
+  if (t == 0 && info) atomicMax(&info[WC_INFO_JACOBI], sweep + 1);
+  // columns of B are U * sigma; lam = sigma^2 (eigenvalue of A).  U written row-major (G,g,g).
+  float* Ug = U + (long long)grp * g * g;
+  for (int j = warp; j < g; j += nw) {
+    const float* bj = B + (long long)j * g;
+    float nn = 0.f;
+    for (int i = lane; i < g; i += 32) nn = fmaf(bj[i], bj[i], nn);
+    nn = wc_warp_sum(nn);
+    float inv = rsqrtf(fmaxf(nn, 1e-38f));
+    for (int i = lane; i < g; i += 32) Ug[(long long)i * g + j] = bj[i] * inv;
+    if (lane == 0) lam[grp * g + j] = nn;
+  }
+}
+
+// Us = U * diag(lam^power)  (row-major (G,g,g))
+__global__ void scale_cols_kernel(const float* __restrict__ U, const float* __restrict__ lam, int C, int g, float power,
+                                  float* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)C * g) return;
+  int grp = (int)(idx / ((long long)g * g));
+  int j = (int)(idx % g);
+  out[idx] = U[idx] * powf(lam[grp * g + j], power);
+}
+
+// Y[i,j] *= -1 / (r_i r_j (r_i + r_j)),  r = sqrt(lam)      (Daleckii-Krein for lam^-1/2)
+__global__ void zca_mulF_kernel(float* __restrict__ Y, const float* __restrict__ lam, int C, int g) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)C * g) return;
+  int grp = (int)(idx / ((long long)g * g));
+  int rem = (int)(idx % ((long long)g * g));
+  float ri = sqrtf(lam[grp * g + rem / g]), rj = sqrtf(lam[grp * g + rem % g]);
+  Y[idx] *= -1.f / (ri * rj * (ri + rj));
+}
+
+// out = alpha * (X + X^T) per group; alpha optionally divided by (count - 1)
+__global__ void sym_scale_kernel(const float* __restrict__ X, float alpha, const float* count_dev, float count_host,
+                                 int use_count, int C, int g, float* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)C * g) return;
+  long long base = idx - idx % ((long long)g * g);
+  int rem = (int)(idx - base);
+  int r = rem / g, c = rem % g;
+  if (use_count) alpha /= ((count_dev ? count_dev[0] : count_host) - 1.f);
+  out[idx] = alpha * (X[idx] + X[base + (long long)c * g + r]);
+}
+
+// =============================================================================================
+// K2b: per-class matrices
+// =============================================================================================
+__global__ void build_wk_kernel(int Cin, int Cout, int K, const float* __restrict__ Wu, const float* __restrict__ bu,
+                                const float* __restrict__ Wc, const float* __restrict__ bc, int triangular,
+                                const float* __restrict__ cm, const float* __restrict__ D, int E,
+                                const float* __restrict__ bf, float* __restrict__ ehat, float* __restrict__ Wk,
+                                float* __restrict__ b) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long per = (long long)Cin * Cout;
+  if (idx >= per * K) return;
+  int k = (int)(idx / per);
+  long long ij = idx % per;
+  int i = (int)(ij / Cout), j = (int)(ij % Cout);
+  float w = Wu ? Wu[ij] : 0.f;
+  if (Wc && !(triangular && j < i)) w += Wc[idx];              // matrix_band_part(kernel, 0, -1): upper triangle
+  if (cm) {
+    float sq = 0.f;
+    for (int e = 0; e < E; ++e) { float v = cm[k * E + e]; sq = fmaf(v, v, sq); }
+    float rho = rsqrtf(fmaxf(sq, 1e-12f));                     // tf.nn.l2_normalize
+    for (int e = 0; e < E; ++e) {
+      float eh = cm[k * E + e] * rho;
+      w = fmaf(eh, D[(long long)e * per + ij], w);
+      if (ij == 0) ehat[k * E + e] = eh;
+    }
+  }
+  Wk[idx] = w;
+  if (i == 0 && b) b[(long long)k * Cout + j] = (bu ? bu[j] : 0.f) + (bc ? bc[(long long)k * Cout + j] : 0.f) +
+                                                (bf ? bf[(long long)k * Cout + j] : 0.f);
+}
+
+// =============================================================================================
+// K5a helpers
+// =============================================================================================
+__global__ void sum_over_k_kernel(const float* __restrict__ X, long long per, int K, float* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per) return;
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) s += X[(long long)k * per + idx];
+  out[idx] = s;
+}
+
+__global__ void triu_copy_kernel(const float* __restrict__ X, int Cin, int Cout, long long total, float* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  long long ij = idx % ((long long)Cin * Cout);
+  int i = (int)(ij / Cout), j = (int)(ij % Cout);
+  out[idx] = (j < i) ? 0.f : X[idx];
+}
+
+// de[k,e] = <Q_k, D_e>, one CTA per (k,e)
+__global__ void __launch_bounds__(256) class_dot_kernel(const float* __restrict__ Q, const float* __restrict__ D, long long per, int E,
+                                                        float* __restrict__ de) {
+  __shared__ float part[8];
+  int k = blockIdx.x / E, e = blockIdx.x % E;
+  const float* q = Q + (long long)k * per;
+  const float* d = D + (long long)e * per;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < per; i += 256) s = fmaf(q[i], d[i], s);
+  s = wc_warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += part[w];
+    de[blockIdx.x] = a;
+  }
+}
+
+// backward of tf.nn.l2_normalize (conditional_layers.py:994): one thread per class
+__global__ void l2norm_bwd_kernel(const float* __restrict__ cm, const float* __restrict__ ehat, const float* __restrict__ de,
+                                  int K, int E, float* __restrict__ dcm) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float sq = 0.f, dot = 0.f;
+  for (int e = 0; e < E; ++e) { float v = cm[k * E + e]; sq = fmaf(v, v, sq); dot = fmaf(de[k * E + e], ehat[k * E + e], dot); }
+  float rho = rsqrtf(fmaxf(sq, 1e-12f));
+  bool clamped = !(sq > 1e-12f);
+  for (int e = 0; e < E; ++e)
+    dcm[k * E + e] = clamped ? rho * de[k * E + e] : rho * (de[k * E + e] - ehat[k * E + e] * dot);
+}
+
+size_t gg_bytes(int C, int g) { return wc_align_up((size_t)C * g * 4, 256); }
+
+}  // namespace
+
+int wc_smm_launch(const WcSmm& p, cudaStream_t st) { return smm(p, st); }
+
+// =============================================================================================
+// K2 entry points
+// =============================================================================================
+extern "C" size_t wc_factor_workspace_bytes(int C, int g, int decomposition, int renorm) {
+  if (C <= 0 || g <= 0 || C % g) return 0;
+  // Ashr, L, (zca: Bm, Us) ; renorm: Amov, Wmov, Lmov-scratch
+  size_t n = 2;
+  if (decomposition == WC_DECOMP_ZCA) n += 2;
+  if (renorm) n += 4;
+  return n * gg_bytes(C, g);
+}
+
+namespace {
+// factor one (G,g,g) SPD matrix `Ashr` -> Wm (inverse square root), optional sqrt factor, optional U/lam
+int factor_matrix(const float* Ashr, int C, int g, int decomposition, float* Wm, float* sqrt_out, float* U, float* lam,
+                  float* L /*scratch or output*/, float* Bm, float* Us, int32_t* info, cudaStream_t st) {
+  const int G = C / g;
+  size_t smem = ((size_t)g * (g + 1) / 2 + 2 * (size_t)g) * 4;
+  int threads = min(1024, max(128, ((4 * g + 31) / 32) * 32));
+  if (4 * g > 1024) return WC_E_UNSUPPORTED;   // g <= 256
+  if (smem > 227 * 1024) return WC_E_UNSUPPORTED;
+  if (smem > 48 * 1024) WC_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long total = (long long)C * g;
+  if (decomposition == WC_DECOMP_CHOLESKY) {
+    chol_inv_kernel<<<G, threads, smem, st>>>(Ashr, g, sqrt_out, Wm, info);
+    WC_CHECK_LAUNCH();
+    return 0;
+  }
+  chol_inv_kernel<<<G, threads, smem, st>>>(Ashr, g, L, nullptr, info);
+  WC_CHECK_LAUNCH();
+  jacobi_kernel<<<G, 1024, 0, st>>>(L, g, Bm, U, lam, info);
+  WC_CHECK_LAUNCH();
+  scale_cols_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(U, lam, C, g, -0.25f, Us);
+  WC_CHECK_LAUNCH();
+  int rc = smm(smm_gg(Us, false, Us, true, Wm, g, G), st);
+  if (rc) return rc;
+  if (sqrt_out) {
+    scale_cols_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(U, lam, C, g, 0.25f, Us);
+    WC_CHECK_LAUNCH();
+    rc = smm(smm_gg(Us, false, Us, true, sqrt_out, g, G), st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+}  // namespace
+
+extern "C" int wc_factor_fwd(const float* mean, const float* S, const float* count_dev, double count_host, int C, int g,
+                             float eps, float momentum, int decomposition, int renorm, int training,
+                             float* moving_mean, float* moving_cov, float* Weff, float* Wm, float* R, float* U,
+                             float* lam, int32_t* info, float* workspace, size_t workspace_bytes, wc_stream_t stream) {
+  if (C <= 0 || g <= 0 || C % g || !moving_cov || !Weff || !workspace) return WC_E_ARG;
+  if (training && (!mean || !S || !moving_mean || !Wm)) return WC_E_ARG;
+  if (decomposition != WC_DECOMP_CHOLESKY && decomposition != WC_DECOMP_ZCA) return WC_E_ARG;
+  if (decomposition == WC_DECOMP_ZCA && training && (!U || !lam)) return WC_E_ARG;
+  if (training && renorm && !R) return WC_E_ARG;
+  if (g > 512) return WC_E_UNSUPPORTED;
+  if (workspace_bytes < wc_factor_workspace_bytes(C, g, decomposition, renorm && training)) return WC_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int G = C / g;
+  const size_t gb = gg_bytes(C, g);
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* Ashr = reinterpret_cast<float*>(ws);
+  float* L = reinterpret_cast<float*>(ws + gb);
+  float *Bm = nullptr, *Us = nullptr;
+  size_t off = 2 * gb;
+  const bool zca = decomposition == WC_DECOMP_ZCA;
+  if (zca) { Bm = reinterpret_cast<float*>(ws + off); Us = reinterpret_cast<float*>(ws + off + gb); off += 2 * gb; }
+  const float extra = zca ? eps : 0.f;   // conditional_layers.py:671 adds eps*I again on top of :691
+  long long total = (long long)C * g;
+  int rc;
+  if (!training) {
+    // test phase (:702-704): factor the moving covariance; U/lam scratch if the caller gave none
+    factor_prep_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(nullptr, nullptr, nullptr, 0.f, C, g, eps, extra, momentum, 0,
+                                                            moving_mean, moving_cov, Ashr);
+    WC_CHECK_LAUNCH();
+    if (zca && (!U || !lam)) return WC_E_ARG;   // eigenvector / eigenvalue scratch is required in every phase
+    return factor_matrix(Ashr, C, g, decomposition, Weff, nullptr, U, lam, L, Bm, Us, info, st);
+  }
+  float *Amov = nullptr, *Wmov = nullptr, *Lb = nullptr, *Umov = nullptr;
+  if (renorm) {
+    Amov = reinterpret_cast<float*>(ws + off); Wmov = reinterpret_cast<float*>(ws + off + gb);
+    Lb = reinterpret_cast<float*>(ws + off + 2 * gb); Umov = reinterpret_cast<float*>(ws + off + 3 * gb);
+    // moving covariance as it is BEFORE this step's update (:695-696)
+    factor_prep_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(nullptr, nullptr, nullptr, 0.f, C, g, eps, extra, momentum, 0,
+                                                            moving_mean, moving_cov, Amov);
+    WC_CHECK_LAUNCH();
+    // lam scratch for the moving factor: reuse R's first C floats (R is written afterwards)
+    rc = factor_matrix(Amov, C, g, decomposition, Wmov, nullptr, Umov, R, L, Bm, Us, info, st);
+    if (rc) return rc;
+  }
+  factor_prep_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(mean, S, count_dev, (float)count_host, C, g, eps, extra, momentum, 1,
+                                                          moving_mean, moving_cov, Ashr);
+  WC_CHECK_LAUNCH();
+  rc = factor_matrix(Ashr, C, g, decomposition, Wm, renorm ? Lb : nullptr, U, lam, L, Bm, Us, info, st);
+  if (rc) return rc;
+  if (renorm) {
+    rc = smm(smm_gg(Wmov, false, Lb, false, R, g, G), st);           // R = l_mov_inverse . stop_gradient(l)   (:697-698)
+    if (rc) return rc;
+    rc = smm(smm_gg(R, false, Wm, false, Weff, g, G), st);           // Weff = R . l_inv
+    if (rc) return rc;
+  } else if (Weff != Wm) {
+    WC_CUDA(cudaMemcpyAsync(Weff, Wm, (size_t)total * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+// =============================================================================================
+// K2b entry point
+// =============================================================================================
+extern "C" int wc_compose_fwd(const float* Weff, int Cin, int Cout, int g, int K, const float* Wu, const float* bu,
+                              const float* Wc, const float* bc, int triangular, const float* class_matrix,
+                              const float* D, int E, const float* bf, float* ehat, float* Wk, float* T, float* b,
+                              wc_stream_t stream) {
+  if (Cin <= 0 || Cout <= 0 || K <= 0 || !Wk || !T) return WC_E_ARG;
+  if (Weff && (g <= 0 || Cin % g)) return WC_E_ARG;
+  if (class_matrix && (!D || E <= 0 || !ehat)) return WC_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long per = (long long)Cin * Cout;
+  build_wk_kernel<<<wc_cdiv(per * K, 256), 256, 0, st>>>(Cin, Cout, K, Wu, bu, Wc, bc, triangular, class_matrix, D, E, bf,
+                                                         ehat, Wk, b);
+  WC_CHECK_LAUNCH();
+  if (!Weff) {
+    if (T != Wk) WC_CUDA(cudaMemcpyAsync(T, Wk, (size_t)per * K * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  return smm(smm_blockdiag_left(Weff, true, Wk, T, g, Cin / g, Cout, Cout, K, per), st);
+}
+
+// =============================================================================================
+// K5a entry points
+// =============================================================================================
+extern "C" size_t wc_color_bwd_workspace_bytes(int Cin, int Cout, int g, int K, int E) {
+  if (Cin <= 0 || Cout <= 0 || K <= 0) return 0;
+  return wc_align_up((size_t)K * Cin * Cout * 4, 256) + wc_align_up((size_t)K * (E > 0 ? E : 1) * 4, 256);
+}
+
+extern "C" int wc_color_bwd(const float* P, const float* s, const float* Weff, const float* Wk, int Cin, int Cout, int g,
+                            int K, float* dWu, float* dbu, float* dWc, float* dbc, int triangular,
+                            const float* class_matrix, const float* ehat, const float* D, int E, float* dD,
+                            float* dclass_matrix, float* dbf, float* dWeff, float* gbar, float* workspace,
+                            size_t workspace_bytes, wc_stream_t stream) {
+  if (!P || !s || !Wk || Cin <= 0 || Cout <= 0 || K <= 0) return WC_E_ARG;
+  if (Weff && (g <= 0 || Cin % g)) return WC_E_ARG;
+  if ((dD || dclass_matrix) && (!class_matrix || !ehat || !D || E <= 0)) return WC_E_ARG;
+  if (!workspace || workspace_bytes < wc_color_bwd_workspace_bytes(Cin, Cout, g, K, E)) return WC_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long per = (long long)Cin * Cout;
+  float* Qws = workspace;
+  float* de = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + wc_align_up((size_t)K * per * 4, 256));
+  int rc;
+  const bool need_q = dWu || dWc || dD || dclass_matrix;
+  const float* Q = P;
+  if (need_q && Weff) {
+    // Q_k = Weff P_k  ( = x_hat^T dy per class )
+    float* Qdst = Qws;
+    if (dWc && !triangular) Qdst = dWc;
+    else if (K == 1 && dWu) Qdst = dWu;
+    rc = smm(smm_blockdiag_left(Weff, false, P, Qdst, g, Cin / g, Cout, Cout, K, per), st);
+    if (rc) return rc;
+    Q = Qdst;
+  }
+  if (dWu && Q != dWu) {
+    if (K == 1) WC_CUDA(cudaMemcpyAsync(dWu, Q, (size_t)per * 4, cudaMemcpyDeviceToDevice, st));
+    else { sum_over_k_kernel<<<wc_cdiv(per, 256), 256, 0, st>>>(Q, per, K, dWu); WC_CHECK_LAUNCH(); }
+  }
+  if (dbu) { sum_over_k_kernel<<<wc_cdiv(Cout, 256), 256, 0, st>>>(s, Cout, K, dbu); WC_CHECK_LAUNCH(); }
+  if (dWc && Q != dWc) {
+    if (triangular) { triu_copy_kernel<<<wc_cdiv(per * K, 256), 256, 0, st>>>(Q, Cin, Cout, per * K, dWc); WC_CHECK_LAUNCH(); }
+    else WC_CUDA(cudaMemcpyAsync(dWc, Q, (size_t)per * K * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (dbc) WC_CUDA(cudaMemcpyAsync(dbc, s, (size_t)K * Cout * 4, cudaMemcpyDeviceToDevice, st));
+  if (dbf) WC_CUDA(cudaMemcpyAsync(dbf, s, (size_t)K * Cout * 4, cudaMemcpyDeviceToDevice, st));
+  if (dD) {
+    // dD[e] = sum_k ehat[k,e] Q_k  : (E x K) . (K x per)
+    WcSmm p = smm_init();
+    p.A = ehat; p.B = Q; p.C = dD; p.M = E; p.N = (int)per; p.K = K;
+    p.rsA = 1; p.csA = E; p.rsB = per; p.csB = 1; p.rsC = per; p.csC = 1;
+    rc = smm(p, st);
+    if (rc) return rc;
+  }
+  if (dclass_matrix) {
+    class_dot_kernel<<<K * E, 256, 0, st>>>(Q, D, per, E, de);
+    WC_CHECK_LAUNCH();
+    l2norm_bwd_kernel<<<wc_cdiv(K, 128), 128, 0, st>>>(class_matrix, ehat, de, K, E, dclass_matrix);
+    WC_CHECK_LAUNCH();
+  }
+  if (dWeff) {
+    if (!Weff) return WC_E_ARG;
+    // dWeff[grp] = sum_k Wk[k][grp rows,:] . P[k][grp rows,:]^T
+    WcSmm p = smm_init();
+    p.A = Wk; p.B = P; p.C = dWeff; p.M = g; p.N = g; p.K = Cout;
+    p.rsA = Cout; p.csA = 1; p.rsB = 1; p.csB = Cout; p.rsC = g; p.csC = 1;
+    p.nb1 = 1; p.nb2 = Cin / g;
+    p.bA2 = (long long)g * Cout; p.bB2 = (long long)g * Cout; p.bC2 = (long long)g * g;
+    p.nsum = K; p.sA = per; p.sB = per;
+    rc = smm(p, st);
+    if (rc) return rc;
+  }
+  if (gbar) {
+    // gbar = sum_k Wk[k] s[k]
+    WcSmm p = smm_init();
+    p.A = Wk; p.B = s; p.C = gbar; p.M = Cin; p.N = 1; p.K = Cout;
+    p.rsA = Cout; p.csA = 1; p.rsB = 1; p.csB = 0; p.rsC = 1; p.csC = 1;
+    p.nsum = K; p.sA = per; p.sB = Cout;
+    rc = smm(p, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// =============================================================================================
+// K5b entry points
+// =============================================================================================
+extern "C" size_t wc_factor_bwd_workspace_bytes(int C, int g, int decomposition, int renorm) {
+  if (C <= 0 || g <= 0 || C % g) return 0;
+  return 3 * gg_bytes(C, g);
+}
+
+extern "C" int wc_factor_bwd(const float* dWeff, const float* gbar, const float* Weff, const float* Wm, const float* R,
+                             const float* U, const float* lam, const float* count_dev, double count_host, int C, int g,
+                             float eps, int decomposition, int renorm, float* A, float* cvec, float* workspace,
+                             size_t workspace_bytes, wc_stream_t stream) {
+  if (!dWeff || !gbar || !Weff || !Wm || !A || !cvec || C <= 0 || g <= 0 || C % g) return WC_E_ARG;
+  if (renorm && !R) return WC_E_ARG;
+  if (decomposition == WC_DECOMP_ZCA && (!U || !lam)) return WC_E_ARG;
+  if (!workspace || workspace_bytes < wc_factor_bwd_workspace_bytes(C, g, decomposition, renorm)) return WC_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int G = C / g;
+  const size_t gb = gg_bytes(C, g);
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* W0 = reinterpret_cast<float*>(ws);
+  float* W1 = reinterpret_cast<float*>(ws + gb);
+  float* W2 = reinterpret_cast<float*>(ws + 2 * gb);
+  const float ch = (float)count_host;
+  long long total = (long long)C * g;
+  int rc;
+  const float* dWm = dWeff;
+  if (renorm) {  // Weff = R Wm with R constant  =>  dWm = R^T dWeff
+    rc = smm(smm_gg(R, true, dWeff, false, W2, g, G), st);
+    if (rc) return rc;
+    dWm = W2;
+  }
+  if (decomposition == WC_DECOMP_CHOLESKY) {
+    // Phi = -(tril(Z) - diag(Z)/2),  Z = dWm Wm^T
+    WcSmm p = smm_gg(dWm, false, Wm, true, W0, g, G);
+    p.alpha = -1.f; p.tri = 1;
+    rc = smm(p, st, nullptr, 0.f, 0, 0.5f);
+    if (rc) return rc;
+    rc = smm(smm_gg(W0, false, Wm, false, W1, g, G), st);     // Y = Phi Wm
+    if (rc) return rc;
+    rc = smm(smm_gg(Wm, true, W1, false, W0, g, G), st);      // Qs = Wm^T Y
+    if (rc) return rc;
+    // A = (1-eps) (Qs + Qs^T) / (count-1)
+    sym_scale_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(W0, 1.f - eps, count_dev, ch, 1, C, g, A);
+    WC_CHECK_LAUNCH();
+  } else {
+    sym_scale_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(dWm, 0.5f, nullptr, 0.f, 0, C, g, W0);   // sym(dWm)
+    WC_CHECK_LAUNCH();
+    rc = smm(smm_gg(U, true, W0, false, W1, g, G), st);       // U^T sym
+    if (rc) return rc;
+    rc = smm(smm_gg(W1, false, U, false, W0, g, G), st);      // (U^T sym) U
+    if (rc) return rc;
+    zca_mulF_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(W0, lam, C, g);
+    WC_CHECK_LAUNCH();
+    rc = smm(smm_gg(U, false, W0, false, W1, g, G), st);      // U (.)
+    if (rc) return rc;
+    WcSmm p = smm_gg(W1, false, U, true, A, g, G);            // (.) U^T, scaled: A = 2(1-eps) dSigma / (count-1)
+    p.alpha = 2.f * (1.f - eps);
+    rc = smm(p, st, count_dev, ch, 2, 1.f);
+    if (rc) return rc;
+  }
+  // cvec = Weff^T gbar / count
+  WcSmm p = smm_init();
+  p.A = Weff; p.B = gbar; p.C = cvec; p.M = g; p.N = 1; p.K = g;
+  p.rsA = 1; p.csA = g; p.rsB = 1; p.csB = 0; p.rsC = 1; p.csC = 1;
+  p.nb1 = 1; p.nb2 = G; p.bA2 = (long long)g * g; p.bB2 = g; p.bC2 = g;
+  return smm(p, st, count_dev, ch, 1, 1.f);
+}
+
+extern "C" int wc_version(void) { return WC_B200_VERSION; }
+
+// Dispatcher report (see include/wc_b200.h).  The tcgen05 kernels take over in wc_tc.cu when present.
+extern "C" __attribute__((weak)) int wc_path_for(int64_t M, int Cin, int Cout, int g) { return 0; }

@@ -50,6 +50,10 @@ typedef void* wc_stream_t;
 
 int wc_version(void);
 
+/* Statistics only: number of kernels this library has launched since it was loaded
+ * (a relaxed atomic counter; bench.py reports the per-step delta as gpu_launches).        */
+long long wc_launch_count(void);
+
 /* Which implementation the dispatcher would choose for a shape: bit0 = tcgen05 tensor-core
  * apply kernels, bit1 = tcgen05 gram kernels; 0 = FP32 FFMA kernels only.                 */
 int wc_path_for(int64_t M, int Cin, int Cout, int g);

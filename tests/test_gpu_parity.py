@@ -218,7 +218,7 @@ def test_ref_decorelation():
     for dec in ('cholesky', 'zca'):
         layer = W.DecorelationNormalization(renorm=False, decomposition=dec).to(DEV)
         layer.train()
-        out = layer(torch.from_numpy(x).to(DEV)).cpu().numpy()
+        out = layer(torch.from_numpy(x).to(DEV)).detach().cpu().numpy()
         out = np.reshape(out, [-1, out.shape[-1]])
         assert np.mean(np.abs(np.cov(out, rowvar=False) - np.eye(64))) < 1e-3
 
@@ -236,7 +236,7 @@ def test_ref_conditional_conv11():
     cls = np.expand_dims(np.arange(10) % 3, axis=-1).astype(np.int32)
     layer.build(10, None); layer.built = True
     layer.to(DEV)
-    out1 = layer([torch.from_numpy(x).to(DEV), torch.from_numpy(cls).to(DEV)]).cpu().numpy()
+    out1 = layer([torch.from_numpy(x).to(DEV), torch.from_numpy(cls).to(DEV)]).detach().cpu().numpy()
     k = kernel_init((3, 1, 1, 10, 20)); b = kernel_init((3, 20))
     out2 = np.stack([np.einsum('hwc,cf->hwf', x[i].astype(np.float64), k[int(cls[i, 0]), 0, 0]) + b[int(cls[i, 0])]
                      for i in range(10)])
@@ -254,7 +254,7 @@ def test_ref_triangular_conv11():
                                 bias_initializer='zeros')
     layer.build(2, None); layer.built = True
     layer.to(DEV)
-    out = layer([torch.ones(1, 2, 2, 2, device=DEV), torch.zeros(1, 1, dtype=torch.int32, device=DEV)]).cpu().numpy()
+    out = layer([torch.ones(1, 2, 2, 2, device=DEV), torch.zeros(1, 1, dtype=torch.int32, device=DEV)]).detach().cpu().numpy()
     assert np.all(out[0, ..., 0] == 1)
     assert np.all(out[0, ..., 1] == 4)
 
@@ -273,7 +273,7 @@ def test_ref_triangular_factorized_conv11():
     layer.build(2, None); layer.built = True
     layer.to(DEV)
     cls = torch.arange(2, dtype=torch.int32, device=DEV).reshape(2, 1)
-    out = layer([torch.ones(2, 2, 2, 2, device=DEV), cls]).cpu().numpy()
+    out = layer([torch.ones(2, 2, 2, 2, device=DEV), cls]).detach().cpu().numpy()
     assert np.all(out[0] == 2)
     assert np.all(out[1] == 2)
 

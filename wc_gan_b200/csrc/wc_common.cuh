@@ -5,8 +5,13 @@
 #include <stddef.h>
 #include "../../include/wc_b200.h"
 
+// statistics only (bench.py's gpu_launches): kernels launched by this library since load
+extern "C" long long wc_launch_count(void);
+void wc_count_launch();
+
 #define WC_CHECK_LAUNCH()                                   \
   do {                                                      \
+    wc_count_launch();                                      \
     cudaError_t e__ = cudaGetLastError();                   \
     if (e__ != cudaSuccess) return (int)e__;                \
   } while (0)

@@ -32,6 +32,23 @@ class WCSpec:
     number_of_classes: int = 1
 
 
+# When set to a dict, every C-ABI stage is bracketed by CUDA events on the launching stream:
+#   PROFILE[stage] = [(start_event, end_event), ...]      (bench.py reads the per-stage durations)
+PROFILE = None
+
+
+def _call(name: str, *args) -> None:
+    fn = getattr(lib, name)
+    if PROFILE is None:
+        check(fn(*args), name)
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    check(fn(*args), name)
+    e.record()
+    PROFILE.setdefault(name, []).append((s, e))
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -116,13 +133,13 @@ class WhiteningColoringFn(torch.autograd.Function):
                 mean_l, S_l = rec[1:1 + Cin], rec[1 + Cin:]
                 nb = lib.wc_stats_workspace_bytes(N * HW, Cin, g)
                 ws = _ws(nb, dev)
-                check(lib.wc_stats_fwd(ptr(x), N * HW, Cin, g, ptr(ws), nb, ptr(mean_l), ptr(S_l), st), 'wc_stats_fwd')
+                _call('wc_stats_fwd', ptr(x), N * HW, Cin, g, ptr(ws), nb, ptr(mean_l), ptr(S_l), st)
                 if sync:
                     rec[0:1].fill_(count)
                     recs = _f32(world, rec.numel(), device=dev)
                     dist.all_gather_into_tensor(recs, rec, group=group)
                     mean, S, count_dev = _f32(Cin, device=dev), _f32(G, g, g, device=dev), _f32(1, device=dev)
-                    check(lib.wc_stats_merge(ptr(recs), world, Cin, g, ptr(mean), ptr(S), ptr(count_dev), st), 'wc_stats_merge')
+                    _call('wc_stats_merge', ptr(recs), world, Cin, g, ptr(mean), ptr(S), ptr(count_dev), st)
                 else:
                     mean, S = mean_l, S_l
                 Wm = _f32(G, g, g, device=dev)
@@ -131,11 +148,11 @@ class WhiteningColoringFn(torch.autograd.Function):
                 mean, S = moving_mean.reshape(-1), None
             nb = lib.wc_factor_workspace_bytes(Cin, g, dec, int(spec.renorm and training))
             ws = _ws(nb, dev)
-            check(lib.wc_factor_fwd(ptr(mean) if training else None, ptr(S), ptr(count_dev), count, Cin, g,
+            _call('wc_factor_fwd', ptr(mean) if training else None, ptr(S), ptr(count_dev), count, Cin, g,
                                     spec.epsilon, spec.momentum, dec, int(spec.renorm), int(training),
                                     ptr(moving_mean), ptr(moving_cov), ptr(Weff),
                                     ptr(Wm if training else Weff), ptr(R), ptr(U), ptr(lam),
-                                    ptr(info), ptr(ws), nb, st), 'wc_factor_fwd')
+                                    ptr(info), ptr(ws), nb, st)
             if not training:
                 Wm = Weff
 
@@ -146,13 +163,13 @@ class WhiteningColoringFn(torch.autograd.Function):
         T = _f32(K, Cin, Cout, device=dev) if spec.whiten else Wk
         b = _f32(K, Cout, device=dev) if any(t is not None for t in (bu, bc, bf)) else None
         ehat = _f32(K, E, device=dev) if class_matrix is not None else None
-        check(lib.wc_compose_fwd(ptr(Weff), Cin, Cout, g, K, ptr(Wu_k), ptr(bu), ptr(Wc), ptr(bc),
+        _call('wc_compose_fwd', ptr(Weff), Cin, Cout, g, K, ptr(Wu_k), ptr(bu), ptr(Wc), ptr(bc),
                                  int(spec.triangular), ptr(class_matrix), ptr(D), E, ptr(bf),
-                                 ptr(ehat), ptr(Wk), ptr(T), ptr(b), st), 'wc_compose_fwd')
+                                 ptr(ehat), ptr(Wk), ptr(T), ptr(b), st)
         y = _f32(N, H, W_, Cout, device=dev)
         band = g if (spec.whiten and Wu is None and Wc is None and D is None and g < Cin) else 0
-        check(lib.wc_apply_fwd(ptr(x), N, HW, Cin, Cout, ptr(mean), ptr(T), ptr(b), ptr(cls), K, band,
-                               ptr(y), ptr(info), st), 'wc_apply_fwd')
+        _call('wc_apply_fwd', ptr(x), N, HW, Cin, Cout, ptr(mean), ptr(T), ptr(b), ptr(cls), K, band,
+                               ptr(y), ptr(info), st)
 
         ctx.spec, ctx.training, ctx.group, ctx.sync = spec, training, group, sync
         ctx.dims = (N, HW, Cin, Cout, g, K, E, count)
@@ -177,8 +194,8 @@ class WhiteningColoringFn(torch.autograd.Function):
         P, s = _f32(K, Cin, Cout, device=dev), _f32(K, Cout, device=dev)
         nb = lib.wc_reduce_workspace_bytes(N, HW, Cin, Cout, K)
         ws = _ws(nb, dev)
-        check(lib.wc_reduce_bwd(ptr(x), ptr(dy), N, HW, Cin, Cout, ptr(mean), ptr(cls), K, ptr(P), ptr(s),
-                                ptr(ws), nb, st), 'wc_reduce_bwd')
+        _call('wc_reduce_bwd', ptr(x), ptr(dy), N, HW, Cin, Cout, ptr(mean), ptr(cls), K, ptr(P), ptr(s),
+                                ptr(ws), nb, st)
 
         dWu = _f32(Cin, Cout, device=dev) if (has_Wu and need[1]) else None
         dbu = _f32(Cout, device=dev) if (has_bu and need[2]) else None
@@ -193,10 +210,10 @@ class WhiteningColoringFn(torch.autograd.Function):
         gbar = red[G * g * g:] if stats_grad else None
         nb = lib.wc_color_bwd_workspace_bytes(Cin, Cout, g, K, E)
         ws = _ws(nb, dev)
-        check(lib.wc_color_bwd(ptr(P), ptr(s), ptr(Weff), ptr(Wk), Cin, Cout, g, K,
+        _call('wc_color_bwd', ptr(P), ptr(s), ptr(Weff), ptr(Wk), Cin, Cout, g, K,
                                ptr(dWu), ptr(dbu), ptr(dWc), ptr(dbc), int(spec.triangular),
                                ptr(class_matrix), ptr(ehat), ptr(D), E, ptr(dD), ptr(dcm), ptr(dbf),
-                               ptr(dWeff), ptr(gbar), ptr(ws), nb, st), 'wc_color_bwd')
+                               ptr(dWeff), ptr(gbar), ptr(ws), nb, st)
         dx = None
         if need[0]:
             A = cvec = None
@@ -206,12 +223,12 @@ class WhiteningColoringFn(torch.autograd.Function):
                 A, cvec = _f32(G, g, g, device=dev), _f32(Cin, device=dev)
                 nb = lib.wc_factor_bwd_workspace_bytes(Cin, g, dec, int(spec.renorm))
                 ws = _ws(nb, dev)
-                check(lib.wc_factor_bwd(ptr(dWeff), ptr(gbar), ptr(Weff), ptr(Wm), ptr(R), ptr(U), ptr(lam),
+                _call('wc_factor_bwd', ptr(dWeff), ptr(gbar), ptr(Weff), ptr(Wm), ptr(R), ptr(U), ptr(lam),
                                         ptr(count_dev), count, Cin, g, spec.epsilon, dec, int(spec.renorm),
-                                        ptr(A), ptr(cvec), ptr(ws), nb, st), 'wc_factor_bwd')
+                                        ptr(A), ptr(cvec), ptr(ws), nb, st)
             dx = torch.empty_like(x)
-            check(lib.wc_apply_bwd(ptr(x), ptr(dy), N, HW, Cin, Cout, ptr(mean), ptr(T), ptr(A), ptr(cvec), g,
-                                   ptr(cls), K, ptr(dx), st), 'wc_apply_bwd')
+            _call('wc_apply_bwd', ptr(x), ptr(dy), N, HW, Cin, Cout, ptr(mean), ptr(T), ptr(A), ptr(cvec), g,
+                                   ptr(cls), K, ptr(dx), st)
 
         return (dx, dWu, dbu, dWc, dbc, dcm, dD, dbf, None, None, None, None, None, None, None)
 

@@ -270,16 +270,15 @@ def run_ours(args):
     dyh = [d.cpu().pin_memory() for d in dys[:2]]
     yh = torch.empty(SHAPE, dtype=torch.float32).pin_memory()
     dxh = torch.empty(SHAPE, dtype=torch.float32).pin_memory()
-    xd, dyd = torch.empty_like(xs[0]), torch.empty_like(dys[0])
+    xd, dyd = torch.empty(SHAPE, device=dev), torch.empty(SHAPE, device=dev)
 
     def e2e_step(i):
-        xd.requires_grad_(False)
         xd.copy_(xh[i % 2], non_blocking=True)
         dyd.copy_(dyh[i % 2], non_blocking=True)
-        xi = xd.requires_grad_(True)
+        xi = xd.detach().requires_grad_(True)
         y = stack(xi)
         gr = torch.autograd.grad(y, [xi] + params, dyd)
-        yh.copy_(y, non_blocking=True)
+        yh.copy_(y.detach(), non_blocking=True)
         dxh.copy_(gr[0], non_blocking=True)
 
     e_steps = max(3, min(args.steps, 10))

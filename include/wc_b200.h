@@ -67,7 +67,7 @@ int wc_stats_fwd(const float* x, int64_t M, int C, int g,
                  float* workspace, size_t workspace_bytes,
                  float* mean, float* S, wc_stream_t stream);
 
-/* Merge R shard records {count, mean[C], S[G*g*g]} (packed, stride 1+C+G*g*g floats), e.g.
+/* Merge R shard records {mean[C], S[G*g*g], count} (packed, stride C+G*g*g+1 floats), e.g.
  * the output of an all-gather, with Chan's parallel update.  New in this build (the
  * reference is single-GPU); equals :658,:683 on the concatenated batch.                   */
 int wc_stats_merge(const float* records, int R, int C, int g,

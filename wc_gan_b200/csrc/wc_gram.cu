@@ -248,27 +248,27 @@ __global__ void stats_finalize_kernel(const float* __restrict__ partS, const flo
   if (rem % g == rem / g) mean[i] = (float)((double)pivot[i] + ddi);
 }
 
-// Chan merge of R shard records {count, mean[C], S[G g g]}
+// Chan merge of R shard records {mean[C], S[G g g], count}
 __global__ void stats_merge_kernel(const float* __restrict__ rec, int R, int C, int g,
                                    float* __restrict__ mean, float* __restrict__ S, float* __restrict__ count_total) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)C * g;
   if (idx >= total) return;
-  long long stride = 1 + C + total;
+  long long stride = C + total + 1;
   int grp = (int)(idx / ((long long)g * g));
   int rem = (int)(idx % ((long long)g * g));
   int i = grp * g + rem / g, j = grp * g + rem % g;
   double n = 0, mi = 0, mj = 0;
   for (int r = 0; r < R; ++r) {
-    double nr = rec[r * stride];
-    n += nr; mi += nr * rec[r * stride + 1 + i]; mj += nr * rec[r * stride + 1 + j];
+    double nr = rec[r * stride + C + total];
+    n += nr; mi += nr * rec[r * stride + i]; mj += nr * rec[r * stride + j];
   }
   mi /= n; mj /= n;
   double s = 0;
   for (int r = 0; r < R; ++r) {
-    double nr = rec[r * stride];
-    double di = rec[r * stride + 1 + i] - mi, dj = rec[r * stride + 1 + j] - mj;
-    s += rec[r * stride + 1 + C + idx] + nr * di * dj;
+    double nr = rec[r * stride + C + total];
+    double di = rec[r * stride + i] - mi, dj = rec[r * stride + j] - mj;
+    s += rec[r * stride + C + idx] + nr * di * dj;
   }
   S[idx] = (float)s;
   if (rem % g == rem / g) mean[i] = (float)mi;

@@ -129,13 +129,13 @@ class WhiteningColoringFn(torch.autograd.Function):
             if dec == 1:
                 U, lam = _f32(G, g, g, device=dev), _f32(Cin, device=dev)
             if training:
-                rec = _f32(1 + Cin + G * g * g, device=dev)
-                mean_l, S_l = rec[1:1 + Cin], rec[1 + Cin:]
+                rec = _f32(Cin + G * g * g + 1, device=dev)      # {mean, S, count}: what a shard contributes
+                mean_l, S_l = rec[:Cin], rec[Cin:Cin + G * g * g]
                 nb = lib.wc_stats_workspace_bytes(N * HW, Cin, g)
                 ws = _ws(nb, dev)
                 _call('wc_stats_fwd', ptr(x), N * HW, Cin, g, ptr(ws), nb, ptr(mean_l), ptr(S_l), st)
                 if sync:
-                    rec[0:1].fill_(count)
+                    rec[-1:].fill_(count)
                     recs = _f32(world, rec.numel(), device=dev)
                     dist.all_gather_into_tensor(recs, rec, group=group)
                     mean, S, count_dev = _f32(Cin, device=dev), _f32(G, g, g, device=dev), _f32(1, device=dev)

@@ -112,9 +112,20 @@ int wc_compose_fwd(const float* Weff, int Cin, int Cout, int g, int K,
  * mean, b, cls may be NULL (no centring / no bias / class 0).  band > 0 promises T is block
  * diagonal with square blocks of `band` (whitening only).                                  */
 int wc_apply_fwd(const float* x, int N, int HW, int Cin, int Cout,
-                 const float* mean, const float* T, const float* b,
+                 const float* mean, const float* T, const void* T_packed, const float* b,
                  const int32_t* cls, int K, int band,
                  float* y, int32_t* info, wc_stream_t stream);
+
+/* ---- operand packing for the tcgen05 path (wc_path_for(...) & 1) --------------------------------
+ * The tensor-core K3/K6 kernels read the C x C matrices as pre-split bf16 hi/lo operand images
+ * (K-major, SWIZZLE_64B, one image per 32-channel K block) that cp.async.bulk drops straight into
+ * shared memory.  wc_pack_fwd packs T (K,C,C) for K3; wc_pack_bwd packs T for K6's dy.T^T term and,
+ * when A != NULL, the block-diagonal A (G,g,g) for its (x-mean).A term (nseg_shared = 1).
+ * Passing the packed buffer to wc_apply_fwd / wc_apply_bwd selects the tensor-core kernels; NULL
+ * selects the FP32 FFMA kernels (any shape).                                                      */
+size_t wc_pack_bytes(int C, int K, int nseg_shared);
+int wc_pack_fwd(const float* T, int C, int K, void* packed, wc_stream_t stream);
+int wc_pack_bwd(const float* T, const float* A, int C, int g, int K, void* packed, wc_stream_t stream);
 
 /* ---- K4  backward reduction ----------------------------------------------------------------
  * First half of TF autodiff through the segment K3 replaces:  per class
@@ -158,7 +169,8 @@ int wc_factor_bwd(const float* dWeff, const float* gbar,
  * Second half of autodiff through K3/K1:  dx[n] = dy[n] T[cls[n]]^T + (x[n]-mean) A - cvec.
  * A == NULL (inference phase or no whitening): dx[n] = dy[n] T[cls[n]]^T.                  */
 int wc_apply_bwd(const float* x, const float* dy, int N, int HW, int Cin, int Cout,
-                 const float* mean, const float* T, const float* A, const float* cvec, int g,
+                 const float* mean, const float* T, const float* A, const void* TA_packed,
+                 const float* cvec, int g,
                  const int32_t* cls, int K, float* dx, wc_stream_t stream);
 
 #ifdef __cplusplus

@@ -31,7 +31,9 @@ def test_argument_errors_without_device():
     assert L.wc_stats_fwd(None, 16, 8, 8, None, 0, None, None, None) == -1
     assert L.wc_stats_workspace_bytes(16, 8, 3) == 0          # C % g != 0
     assert L.wc_stats_workspace_bytes(65536, 256, 256) > 0
-    assert L.wc_apply_fwd(None, 1, 1, 1, 1, None, None, None, None, 1, 0, None, None, None) == -1
+    assert L.wc_apply_fwd(None, 1, 1, 1, 1, None, None, None, None, None, 1, 0, None, None, None) == -1
+    assert L.wc_pack_bytes(256, 1, 0) == 256 * 256 * 4 and L.wc_pack_bytes(100, 1, 0) == 0
+    assert L.wc_path_for(65536, 256, 256, 256) & 1 and L.wc_path_for(100, 24, 24, 24) == 0
     assert L.wc_reduce_bwd(None, None, 1, 1, 1, 1, None, None, 1, None, None, None, 0, None) == -1
     assert L.wc_factor_fwd(None, None, None, 1.0, 8, 3, 1e-3, 0.99, 0, 0, 1, None, None, None, None, None, None, None,
                            None, None, 0, None) == -1

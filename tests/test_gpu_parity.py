@@ -335,3 +335,29 @@ def test_create_norm_protocol():
                                            'repart_c.kernel', 'repart_u.kernel', 'repart_u.bias'}
     with pytest.raises(NotImplementedError):
         W.create_norm('b', 'ucs')
+
+
+# ---- both device paths stay covered: tcgen05 (default for C in {128,256}) and FP32 FFMA ------------
+@pytest.fixture
+def ffma_only():
+    from wc_gan_b200 import functional as F
+    old = F.USE_TENSOR_CORES
+    F.USE_TENSOR_CORES = False
+    yield
+    F.USE_TENSOR_CORES = old
+
+
+@pytest.mark.parametrize('shape,after_norm', [((64, 8, 8, 256), 'uconv'), ((64, 16, 16, 128), 'ucconv'),
+                                              ((64, 16, 16, 128), 'ufconv')])
+def test_ffma_path_on_tensor_core_shapes(ffma_only, shape, after_norm):
+    run_case('d', after_norm, shape, K=10, E=4)
+
+
+@pytest.mark.parametrize('shape', [(3, 5, 7, 128), (2, 16, 16, 256), (5, 4, 4, 128), (1, 1, 1, 256)])
+def test_tensor_core_ragged_tiles(shape):
+    """Row tiles that are partly empty (HW not a multiple of 128, tiny samples) on the tcgen05 path."""
+    from wc_gan_b200 import _lib
+    assert _lib.lib.wc_path_for(shape[0] * shape[1] * shape[2], shape[3], shape[3], shape[3]) & 1
+    run_case('n', 'ucconv', shape, K=3)
+    if shape[0] * shape[1] * shape[2] > shape[3] + 1:
+        run_case('d', 'ufconv', shape, K=3, E=2)

@@ -46,7 +46,10 @@ _SIGS = {
                               _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     'wc_compose_fwd': (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, c_int, _P,
                                _P, _P, _P, _P, _P]),
-    'wc_apply_fwd': (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P, _P]),
+    'wc_apply_fwd': (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P]),
+    'wc_pack_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'wc_pack_fwd': (c_int, [_P, c_int, c_int, _P, _P]),
+    'wc_pack_bwd': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
     'wc_reduce_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     'wc_reduce_bwd': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
     'wc_color_bwd_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
@@ -55,7 +58,7 @@ _SIGS = {
     'wc_factor_bwd_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'wc_factor_bwd': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_double, c_int, c_int, c_float, c_int, c_int,
                               _P, _P, _P, c_size_t, _P]),
-    'wc_apply_bwd': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, c_int, _P, _P]),
+    'wc_apply_bwd': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, c_int, _P, _P]),
 }
 for _name, (_res, _args) in _SIGS.items():
     _fn = getattr(lib, _name)

@@ -706,6 +706,3 @@ extern "C" int wc_version(void) { return WC_B200_VERSION; }
 static std::atomic<long long> g_launches{0};
 void wc_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" long long wc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
-
-// Dispatcher report (see include/wc_b200.h).  The tcgen05 kernels take over in wc_tc.cu when present.
-extern "C" __attribute__((weak)) int wc_path_for(int64_t M, int Cin, int Cout, int g) { return 0; }

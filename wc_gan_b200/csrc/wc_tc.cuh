@@ -1,0 +1,143 @@
+// tcgen05 / TMEM / mbarrier / bulk-copy primitives for the sm_100a tensor-core kernels (inline PTX).
+// Layout and descriptor conventions follow the PTX ISA "tcgen05 matrix descriptors" as restated in
+// CUTLASS cute/arch/mma_sm100_desc.hpp and cute/atom/mma_traits_sm100.hpp (canonical layouts).
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace wctc {
+
+// ---- shared-memory operand tiles -------------------------------------------------------------------
+// All operand tiles are made of 16-byte chunks (8 bf16).  Swizzle<B,4,3>: XOR byte-address bits [4,4+B)
+// with bits [7,7+B).  Tiles are 1024-byte aligned, so the XOR can be applied to the tile-relative offset.
+__host__ __device__ __forceinline__ uint32_t swz(uint32_t off, int B) {
+  return off ^ (((off >> 7) & ((1u << B) - 1u)) << 4);
+}
+
+// K-major tile [rows][KB bf16], row pitch = KB*2 bytes (KB = 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B).
+// Byte offset of the 16B chunk holding elements k = 8*chunk .. 8*chunk+7 of `row`.
+template <int KB>
+__host__ __device__ __forceinline__ uint32_t kmajor_chunk_off(int row, int chunk) {
+  constexpr int B = (KB == 64) ? 3 : (KB == 32) ? 2 : 1;
+  return swz((uint32_t)row * (KB * 2) + (uint32_t)chunk * 16, B);
+}
+
+// MN-major SWIZZLE_128B tile: [mn block of 64][k row][64 mn], k-row pitch 128 B, mn-block pitch = KROWS*128.
+// Byte offset of the 16B chunk holding mn = 64*blk + 8*chunk .. +7 at k-row `k`.
+template <int KROWS>
+__host__ __device__ __forceinline__ uint32_t mnmajor_chunk_off(int blk, int k, int chunk) {
+  return (uint32_t)blk * (KROWS * 128) + swz((uint32_t)k * 128 + (uint32_t)chunk * 16, 3);
+}
+
+enum : uint64_t { LAYOUT_SW128 = 2, LAYOUT_SW64 = 4, LAYOUT_SW32 = 6, LAYOUT_NONE = 0 };
+
+// 64-bit shared-memory matrix descriptor (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout type [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (layout << 61);
+}
+
+// 32-bit instruction descriptor for kind::f16, BF16 x BF16 -> F32 (InstrDescriptor):
+// c_format F32 = 1 at [4,6), a/b format BF16 = 1 at [7,10)/[10,13), a_major [15], b_major [16] (0 = K-major,
+// 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// generic-proxy writes (st.shared) -> visible to the async proxy (tcgen05.mma / bulk copies)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 1-D bulk copy global -> shared, completion counted on an mbarrier (bytes multiple of 16, 16B aligned)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]; one thread issues
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// TMEM -> registers: warp w reads lanes 32*(w%4)..+31 (thread t = lane), 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- fp32 -> bf16 splits ----------------------------------------------------------------------------
+// x = h + l (+ m) with each term a bf16 (round to nearest): 2 terms keep 16 mantissa bits, 3 terms all 24.
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {  // a -> low half, b -> high half
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float bf16lo_to_f32(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16hi_to_f32(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
+
+// split two floats into packed (hi, lo) bf16x2 words
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(a, b);
+  lo = pack_bf16x2(a - bf16lo_to_f32(hi), b - bf16hi_to_f32(hi));
+}
+__device__ __forceinline__ void split3(float a, float b, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+  hi = pack_bf16x2(a, b);
+  float ra = a - bf16lo_to_f32(hi), rb = b - bf16hi_to_f32(hi);
+  mid = pack_bf16x2(ra, rb);
+  lo = pack_bf16x2(ra - bf16lo_to_f32(mid), rb - bf16hi_to_f32(mid));
+}
+
+}  // namespace wctc

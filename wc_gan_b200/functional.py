@@ -36,6 +36,9 @@ class WCSpec:
 #   PROFILE[stage] = [(start_event, end_event), ...]      (bench.py reads the per-stage durations)
 PROFILE = None
 
+# False forces the FP32 FFMA kernels everywhere (tests compare the two device paths).
+USE_TENSOR_CORES = True
+
 
 def _call(name: str, *args) -> None:
     fn = getattr(lib, name)
@@ -168,7 +171,12 @@ class WhiteningColoringFn(torch.autograd.Function):
                                  ptr(ehat), ptr(Wk), ptr(T), ptr(b), st)
         y = _f32(N, H, W_, Cout, device=dev)
         band = g if (spec.whiten and Wu is None and Wc is None and D is None and g < Cin) else 0
-        _call('wc_apply_fwd', ptr(x), N, HW, Cin, Cout, ptr(mean), ptr(T), ptr(b), ptr(cls), K, band,
+        use_tc = bool(lib.wc_path_for(N * HW, Cin, Cout, g) & 1) and USE_TENSOR_CORES
+        Tp = None
+        if use_tc:
+            Tp = _ws(lib.wc_pack_bytes(Cin, K, 0), dev)
+            _call('wc_pack_fwd', ptr(T), Cin, K, ptr(Tp), st)
+        _call('wc_apply_fwd', ptr(x), N, HW, Cin, Cout, ptr(mean), ptr(T), ptr(Tp), ptr(b), ptr(cls), K, band,
                                ptr(y), ptr(info), st)
 
         ctx.spec, ctx.training, ctx.group, ctx.sync = spec, training, group, sync
@@ -227,7 +235,11 @@ class WhiteningColoringFn(torch.autograd.Function):
                                         ptr(count_dev), count, Cin, g, spec.epsilon, dec, int(spec.renorm),
                                         ptr(A), ptr(cvec), ptr(ws), nb, st)
             dx = torch.empty_like(x)
-            _call('wc_apply_bwd', ptr(x), ptr(dy), N, HW, Cin, Cout, ptr(mean), ptr(T), ptr(A), ptr(cvec), g,
+            TAp = None
+            if bool(lib.wc_path_for(N * HW, Cin, Cout, g) & 1) and USE_TENSOR_CORES:
+                TAp = _ws(lib.wc_pack_bytes(Cin, K, 1), dev)
+                _call('wc_pack_bwd', ptr(T), ptr(A), Cin, g, K, ptr(TAp), st)
+            _call('wc_apply_bwd', ptr(x), ptr(dy), N, HW, Cin, Cout, ptr(mean), ptr(T), ptr(A), ptr(TAp), ptr(cvec), g,
                                    ptr(cls), K, ptr(dx), st)
 
         return (dx, dWu, dbu, dWc, dbc, dcm, dD, dbf, None, None, None, None, None, None, None)

@@ -58,6 +58,10 @@ long long wc_launch_count(void);
  * apply kernels, bit1 = tcgen05 gram kernels; 0 = FP32 FFMA kernels only.                 */
 int wc_path_for(int64_t M, int Cin, int Cout, int g);
 
+/* Process-wide switch (default on): 0 makes K1/K4 use the FP32 FFMA gram kernels even for shapes the
+ * tcgen05 gram kernels support.  For A/B accuracy tests; not needed in normal use.               */
+void wc_set_tensor_core_gram(int enable);
+
 /* ---- K1  batch statistics ----------------------------------------------------------------
  * Replaces gan/conditional_layers.py:652-660 (transpose, reshape, reduce_mean, subtract) and
  * :683 (f f^T) for one shard.  Output: mean[C] and the CENTRED scatter S (G,g,g) =

@@ -341,10 +341,13 @@ def test_create_norm_protocol():
 @pytest.fixture
 def ffma_only():
     from wc_gan_b200 import functional as F
+    from wc_gan_b200._lib import lib
     old = F.USE_TENSOR_CORES
     F.USE_TENSOR_CORES = False
+    lib.wc_set_tensor_core_gram(0)
     yield
     F.USE_TENSOR_CORES = old
+    lib.wc_set_tensor_core_gram(1)
 
 
 @pytest.mark.parametrize('shape,after_norm', [((64, 8, 8, 256), 'uconv'), ((64, 16, 16, 128), 'ucconv'),

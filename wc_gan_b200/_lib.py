@@ -38,6 +38,7 @@ _SIGS = {
     'wc_version': (c_int, []),
     'wc_launch_count': (ctypes.c_longlong, []),
     'wc_path_for': (c_int, [c_int64, c_int, c_int, c_int]),
+    'wc_set_tensor_core_gram': (None, [c_int]),
     'wc_stats_workspace_bytes': (c_size_t, [c_int64, c_int, c_int]),
     'wc_stats_fwd': (c_int, [_P, c_int64, c_int, c_int, _P, c_size_t, _P, _P, _P]),
     'wc_stats_merge': (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),

@@ -321,6 +321,14 @@ StatsPlan plan_stats(int64_t M, int C, int g) {
 
 }  // namespace
 
+bool wc_tc_gram_ok(int Cin, int Cout);
+int wc_tc_gram_self(const float* x, long long M, int C, const float* pivot, float* Sp, float* sums, cudaStream_t st);
+int wc_tc_gram_cross(const float* x, const float* dy, int N, int HW, int C, const float* mean, const int32_t* order,
+                     const int32_t* slot_of, float* P, float* s, cudaStream_t st);
+
+static bool g_use_tc_gram = true;
+extern "C" void wc_set_tensor_core_gram(int enable) { g_use_tc_gram = enable != 0; }
+
 extern "C" size_t wc_stats_workspace_bytes(int64_t M, int C, int g) {
   if (M <= 0 || C <= 0 || g <= 0 || C % g) return 0;
   return plan_stats(M, C, g).bytes;
@@ -341,6 +349,18 @@ extern "C" int wc_stats_fwd(const float* x, int64_t M, int C, int g, float* work
   int prow = (int)(M < 1024 ? M : 1024);
   pivot_kernel<<<wc_cdiv(C, 32), 256, 0, st>>>(x, prow, C, pivot);
   WC_CHECK_LAUNCH();
+  if (g_use_tc_gram && wc_tc_gram_ok(C, C) && wc_aligned16(x)) {
+    // tensor-core path: the full C x C scatter is accumulated with vector reductions into one zeroed buffer
+    // (partial slot 0); the finalize kernel keeps the diagonal blocks when g < C.
+    WC_CUDA(cudaMemsetAsync(psum, 0, (size_t)C * 4, st));
+    WC_CUDA(cudaMemsetAsync(pS, 0, (size_t)C * C * 4, st));
+    int rc = wc_tc_gram_self(x, M, C, pivot, pS, psum, st);
+    if (rc) return rc;
+    long long tot = (long long)C * g;
+    stats_finalize_kernel<<<wc_cdiv(tot, 256), 256, 0, st>>>(pS, psum, 1, (long long)C * C, C, g, (double)M, pivot, mean, S);
+    WC_CHECK_LAUNCH();
+    return 0;
+  }
   GramParams p{};
   p.A = x; p.B = x; p.lda = C; p.ldb = C; p.ma = pivot; p.mb = pivot; p.nI = C; p.nJ = C;
   p.grouped = 1; p.g = g; p.tw = pl.tw; p.tpg = pl.tpg; p.ntiles = pl.ntiles;
@@ -391,6 +411,9 @@ extern "C" int wc_reduce_bwd(const float* x, const float* dy, int N, int HW, int
   }
   WC_CUDA(cudaMemsetAsync(P, 0, (size_t)K * Cin * Cout * 4, st));
   WC_CUDA(cudaMemsetAsync(s, 0, (size_t)K * Cout * 4, st));
+  if (g_use_tc_gram && wc_tc_gram_ok(Cin, Cout) && wc_aligned16(x) && wc_aligned16(dy) && wc_aligned16(P) &&
+      (!mean || wc_aligned16(mean)))
+    return wc_tc_gram_cross(x, dy, N, HW, Cin, mean, order, slot_of, P, s, st);
   GramParams p{};
   p.A = x; p.B = dy; p.lda = Cin; p.ldb = Cout; p.ma = mean; p.mb = nullptr; p.nI = Cin; p.nJ = Cout;
   p.grouped = 0; p.g = Cin; p.tw = TI; p.tpg = 1;

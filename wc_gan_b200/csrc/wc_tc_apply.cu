@@ -334,6 +334,6 @@ bool wc_tc_apply_ok(int Cin, int Cout) { return tc_shape_ok(Cin, Cout); }
 
 extern "C" int wc_path_for(int64_t M, int Cin, int Cout, int g) {
   int path = 0;
-  if (tc_shape_ok(Cin, Cout)) path |= 1;
+  if (tc_shape_ok(Cin, Cout)) path |= 3;   // bit0: tcgen05 apply kernels, bit1: tcgen05 gram kernels
   return path;
 }

@@ -1,0 +1,273 @@
+// K2 core: Cholesky factor L of a (g x g) SPD matrix and its inverse L^-1, one CTA per group matrix,
+// everything resident in shared memory as 32x32 tiles (g <= 256).
+//
+// Replaces tf.cholesky + tf.matrix_triangular_solve(L, I)  (gan/conditional_layers.py:665-666), which TF 1.5
+// runs as cuSOLVER potrf + cuBLAS trsm launches.
+//
+// Layout: lower tiles (I >= J) of the matrix, each stored column-major with pitch 36 floats
+// (element (r,c) at c*36 + r), so a tile is directly the "k-major" A operand of a warp-level 32x32x32 product
+// and rows of a tile column are contiguous for 128-bit loads.
+//
+// Cholesky (right-looking, per block column J):  warp-level potrf of the diagonal tile in registers (shuffles),
+// triangular solves of the panel tiles (lane = row, broadcast reads of L_JJ), rank-32 updates of the trailing tiles
+// (one warp per tile, 4x8 register blocking).  The diagonal-tile inverses are computed on the side.
+// Inverse (block forward substitution swept by diagonals): accumulators S_IJ = sum_K L_IK X_KJ stay in registers,
+// X_IJ = -inv(L_II) S_IJ is formed with warp shuffles and written to global memory, from where it is re-read as the
+// B operand of the following updates.  Dependency depth: 2 tile products per diagonal.
+#include "wc_common.cuh"
+
+namespace {
+
+constexpr int TB = 32, TP = 36, TS = TP * TB;   // tile edge, pitch, floats per tile
+constexpr int NW = 16;                          // warps per CTA
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float* tile_at(float* base, int I, int J) { return base + (I * (I + 1) / 2 + J) * TS; }
+
+// in-place lower Cholesky of a 32x32 tile; lane owns one row.  rdiag[c] = 1 / L[c][c].
+__device__ void warp_potrf32(float* T, float* rdiag, int lane, int& bad) {
+  float a[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) a[c] = T[c * TP + lane];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    float piv = __shfl_sync(FULL, a[k], k);
+    if (!(piv > 0.f)) { if (!bad) bad = k + 1; piv = 1e-30f; }
+    const float rs = rsqrtf(piv);
+    const float lk = a[k] * rs;
+    a[k] = lk;
+    if (lane == k) rdiag[k] = rs;
+#pragma unroll
+    for (int j = k + 1; j < 32; ++j) {
+      const float ljk = __shfl_sync(FULL, lk, j);
+      a[j] = fmaf(-lk, ljk, a[j]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c) T[c * TP + lane] = (c <= lane) ? a[c] : 0.f;
+}
+
+// solve X L^T = A for one 32x32 tile (lane = row of X).  x[] holds the row of A on entry, of X on exit.
+__device__ __forceinline__ void warp_trsm_row(float (&x)[32], const float* Ljj, const float* rdiag) {
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    float s0 = x[c], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int m = 0; m < c; ++m) {
+      const float l = Ljj[m * TP + c];               // L[c][m], same address for every lane (broadcast)
+      if ((m & 3) == 0) s0 = fmaf(-x[m], l, s0);
+      else if ((m & 3) == 1) s1 = fmaf(-x[m], l, s1);
+      else if ((m & 3) == 2) s2 = fmaf(-x[m], l, s2);
+      else s3 = fmaf(-x[m], l, s3);
+    }
+    x[c] = ((s0 + s1) + (s2 + s3)) * rdiag[c];
+  }
+}
+
+// acc(4x8 per lane) += A(32x32, k-major smem, pitch TP) * B(32x32, k-major, pitch pb; smem or global)
+__device__ __forceinline__ void warp_tile_fma(float (&acc)[4][8], const float* At, const float* Bt, int pb, int ly, int lx) {
+#pragma unroll 8
+  for (int kk = 0; kk < 32; ++kk) {
+    const float4 a = *reinterpret_cast<const float4*>(At + kk * TP + 4 * ly);
+    const float4 b0 = *reinterpret_cast<const float4*>(Bt + (long long)kk * pb + 8 * lx);
+    const float4 b1 = *reinterpret_cast<const float4*>(Bt + (long long)kk * pb + 8 * lx + 4);
+    const float av[4] = {a.x, a.y, a.z, a.w};
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+  }
+}
+
+// X = -Ad * S where S is held in the accumulator layout of this warp (B operand fetched with shuffles)
+__device__ __forceinline__ void warp_neg_mul_from_regs(float (&out)[4][8], const float* Ad, const float (&S)[4][8], int ly, int lx) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) out[r][c] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 32; ++kk) {
+    const float4 a = *reinterpret_cast<const float4*>(Ad + kk * TP + 4 * ly);
+    const float av[4] = {a.x, a.y, a.z, a.w};
+    const int src = (kk >> 2) * 4 + lx;
+    float bv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) bv[c] = __shfl_sync(FULL, S[kk & 3][c], src);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) out[r][c] = fmaf(-av[r], bv[c], out[r][c]);
+  }
+}
+
+__device__ __forceinline__ void tri_index(int t, int& a, int& b) {   // t -> (a,b), 0 <= b <= a, t = a(a+1)/2 + b
+  a = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
+  while ((a + 1) * (a + 2) / 2 <= t) ++a;
+  while (a * (a + 1) / 2 > t) --a;
+  b = t - a * (a + 1) / 2;
+}
+
+__global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float* __restrict__ Ain, int g, float* __restrict__ Lout,
+                                                                    float* __restrict__ Xout, float* __restrict__ Xpad,
+                                                                    int32_t* info) {
+  extern __shared__ __align__(16) float sm[];
+  const int NB = (g + TB - 1) / TB, gp = NB * TB;
+  float* tiles = sm;                                  // NB(NB+1)/2 tiles
+  float* xd = tiles + (NB * (NB + 1) / 2) * TS;       // NB diagonal inverses (column-major tiles)
+  float* rdiag = xd + NB * TS;                        // gp reciprocals of diag(L)
+  const int grp = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int ly = lane >> 2, lx = lane & 3;
+  const float* Ag = Ain + (long long)grp * g * g;
+  // X is produced row-major with leading dimension gp; when g is a multiple of 32 that is the output itself
+  float* X = (Xout && gp == g) ? Xout + (long long)grp * g * g : Xpad + (long long)grp * gp * gp;
+
+  for (int idx = t; idx < gp * gp; idx += NW * 32) {
+    const int i = idx / gp, j = idx % gp;
+    if ((j >> 5) > (i >> 5)) continue;
+    const float v = (i < g && j < g) ? Ag[(long long)i * g + j] : (i == j ? 1.f : 0.f);
+    tile_at(tiles, i >> 5, j >> 5)[(j & 31) * TP + (i & 31)] = v;
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ Cholesky
+  for (int J = 0; J < NB; ++J) {
+    if (warp == 0) {
+      int bad = 0;
+      warp_potrf32(tile_at(tiles, J, J), rdiag + J * TB, lane, bad);
+      if (bad && lane == 0 && info && J * TB + bad <= g) atomicCAS(&info[WC_INFO_NOT_PD], 0, grp * g + J * TB + bad);
+    }
+    __syncthreads();
+    const float* Ljj = tile_at(tiles, J, J);
+    const int npanel = NB - 1 - J;
+    // panel solves (npanel tiles) + the inverse of the diagonal tile (one more job)
+    for (int job = warp; job <= npanel; job += NW) {
+      float x[32];
+      if (job < npanel) {
+        float* T = tile_at(tiles, J + 1 + job, J);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) x[c] = T[c * TP + lane];
+        warp_trsm_row(x, Ljj, rdiag + J * TB);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) T[c * TP + lane] = x[c];
+      } else if (Xout) {
+        // inv(L_JJ): row `lane` of L^-T = column `lane` of L^-1
+#pragma unroll
+        for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.f : 0.f;
+        warp_trsm_row(x, Ljj, rdiag + J * TB);
+        float* D = xd + J * TS;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          D[lane * TP + c] = x[c];                                           // element (row c, col lane)
+          X[(long long)(J * TB + c) * gp + J * TB + lane] = x[c];
+        }
+      }
+    }
+    __syncthreads();
+    // trailing updates: tile(I,K) -= L_IJ L_KJ^T for J < K <= I
+    const int nupd = npanel * (npanel + 1) / 2;
+    for (int job = warp; job < nupd; job += NW) {
+      int a, b;
+      tri_index(job, a, b);
+      const int I = J + 1 + a, K = J + 1 + b;
+      float acc[4][8];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+      warp_tile_fma(acc, tile_at(tiles, I, J), tile_at(tiles, K, J), TP, ly, lx);
+      float* C = tile_at(tiles, I, K);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4* p = reinterpret_cast<float4*>(C + (8 * lx + c) * TP + 4 * ly);
+        float4 v = *p;
+        v.x -= acc[0][c]; v.y -= acc[1][c]; v.z -= acc[2][c]; v.w -= acc[3][c];
+        *p = v;
+      }
+    }
+    __syncthreads();
+  }
+
+  if (Lout) {
+    float* Lg = Lout + (long long)grp * g * g;
+    for (int idx = t; idx < g * g; idx += NW * 32) {
+      const int i = idx / g, j = idx % g;
+      Lg[idx] = (j <= i) ? tile_at(tiles, i >> 5, j >> 5)[(j & 31) * TP + (i & 31)] : 0.f;
+    }
+  }
+  if (!Xout) return;
+
+  // ------------------------------------------------------------------ inverse
+  // strictly-upper tiles of X are zero
+  for (int idx = t; idx < gp * gp; idx += NW * 32) {
+    const int i = idx / gp, j = idx % gp;
+    if ((j >> 5) > (i >> 5)) X[idx] = 0.f;
+  }
+  // each warp owns up to two off-diagonal tiles (NB <= 8 -> 28 tiles); accumulators live in registers
+  const int noff = NB * (NB - 1) / 2;
+  float S[2][4][8];
+  int tI[2], tJ[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int job = warp + s * NW;
+    tI[s] = -1; tJ[s] = 0;
+    if (job < noff) { int a, b; tri_index(job, a, b); tI[s] = a + 1; tJ[s] = b; }   // I = a+1 > J = b
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) S[s][r][c] = 0.f;
+  }
+  __syncthreads();   // diagonal tiles of X (global) and the zero fill are visible
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+    if (tI[s] >= 0)   // S_IJ = L_IJ X_JJ
+      warp_tile_fma(S[s], tile_at(tiles, tI[s], tJ[s]), X + (long long)(tJ[s] * TB) * gp + tJ[s] * TB, gp, ly, lx);
+  for (int d = 1; d < NB; ++d) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (tI[s] >= 0 && tI[s] - tJ[s] == d) {
+        float out[4][8];
+        warp_neg_mul_from_regs(out, xd + tI[s] * TS, S[s], ly, lx);
+        float* dst = X + (long long)(tI[s] * TB + 4 * ly) * gp + tJ[s] * TB + 8 * lx;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          *reinterpret_cast<float4*>(dst + (long long)r * gp) = make_float4(out[r][0], out[r][1], out[r][2], out[r][3]);
+          *reinterpret_cast<float4*>(dst + (long long)r * gp + 4) = make_float4(out[r][4], out[r][5], out[r][6], out[r][7]);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (tI[s] >= 0 && tI[s] - tJ[s] > d)   // S_IJ += L_{I,J+d} X_{J+d,J}
+        warp_tile_fma(S[s], tile_at(tiles, tI[s], tJ[s] + d), X + (long long)((tJ[s] + d) * TB) * gp + tJ[s] * TB, gp, ly, lx);
+  }
+  if (gp != g) {
+    __syncthreads();
+    float* Xg = Xout + (long long)grp * g * g;
+    for (int idx = t; idx < g * g; idx += NW * 32) Xg[idx] = X[(long long)(idx / g) * gp + idx % g];
+  }
+}
+
+}  // namespace
+
+size_t wc_chol_pad_floats(int C, int g) {
+  int NB = (g + TB - 1) / TB, gp = NB * TB;
+  return gp == g ? 0 : (size_t)(C / g) * gp * gp;
+}
+
+// Ain (G,g,g) SPD -> Lout (G,g,g) lower factor (nullable), Xout (G,g,g) = L^-1 (nullable). Xpad: scratch of
+// wc_chol_pad_floats floats (only used when g is not a multiple of 32).
+int wc_chol_inv_launch(const float* Ain, int C, int g, float* Lout, float* Xout, float* Xpad, int32_t* info, cudaStream_t st) {
+  if (g > 256) return WC_E_UNSUPPORTED;
+  const int NB = (g + TB - 1) / TB;
+  size_t smem = ((size_t)(NB * (NB + 1) / 2 + NB) * TS + (size_t)NB * TB) * sizeof(float);
+  static size_t attr_smem = 0;
+  if (smem > 48 * 1024 && smem > attr_smem) {
+    WC_CUDA(cudaFuncSetAttribute(chol_inv_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  chol_inv_tiled_kernel<<<C / g, NW * 32, smem, st>>>(Ain, g, Lout, Xout, Xpad, info);
+  WC_CHECK_LAUNCH();
+  return 0;
+}

@@ -58,3 +58,7 @@ struct WcSmm {
   int tri;                     // 0 none, 1 keep lower (incl. diag) of C, 2 keep upper (incl. diag); others zeroed
 };
 int wc_smm_launch(const WcSmm& p, cudaStream_t st);
+
+// tiled Cholesky + inverse (wc_chol.cu)
+size_t wc_chol_pad_floats(int C, int g);
+int wc_chol_inv_launch(const float* Ain, int C, int g, float* Lout, float* Xout, float* Xpad, int32_t* info, cudaStream_t st);

@@ -146,84 +146,6 @@ __global__ void factor_prep_kernel(const float* __restrict__ mean, const float* 
   Ashr[idx] = (1.f - eps) * cov + (r == c ? eps + extra_eps : 0.f);                // :691 (+ :671 for ZCA)
 }
 
-__device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }   // packed lower, j <= i
-
-// One CTA per group.  Packed lower-triangular matrix in shared memory:
-// right-looking Cholesky (one column per step), then row-by-row in-place inverse.
-__global__ void __launch_bounds__(1024) chol_inv_kernel(const float* __restrict__ Ain, int g,
-                                                        float* __restrict__ Lout, float* __restrict__ Linv_out,
-                                                        int32_t* info) {
-  extern __shared__ float sm[];
-  float* a = sm;                       // g(g+1)/2
-  float* col = a + g * (g + 1) / 2;    // g
-  float* piv = col + g;                // g
-  const int grp = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
-  const float* Ag = Ain + (long long)grp * g * g;
-  for (int idx = t; idx < g * g; idx += nt) {
-    int i = idx / g, j = idx % g;
-    if (j <= i) a[pk(i, j)] = Ag[idx];
-  }
-  const int warp = t >> 5, lane = t & 31, nw = nt >> 5;
-  for (int k = 0; k < g; ++k) {
-    __syncthreads();
-    float p = a[pk(k, k)];
-    if (!(p > 0.f)) {  // also catches NaN
-      if (t == 0 && info) atomicCAS(&info[WC_INFO_NOT_PD], 0, grp * g + k + 1);
-      p = 1e-30f;
-    }
-    for (int i = k + 1 + t; i < g; i += nt) col[i] = a[pk(i, k)];
-    if (t == 0) piv[k] = p;
-    __syncthreads();
-    float inv = 1.f / p;
-    for (int i = k + 1 + warp; i < g; i += nw) {
-      float lik = col[i] * inv;
-      float* row = a + pk(i, 0);
-      for (int j = k + 1 + lane; j <= i; j += 32) row[j] = fmaf(-lik, col[j], row[j]);
-    }
-  }
-  __syncthreads();
-  // scale columns: L_ij = a_ij / sqrt(piv_j), L_jj = sqrt(piv_j)
-  for (int idx = t; idx < g * g; idx += nt) {
-    int i = idx / g, j = idx % g;
-    if (j < i) a[pk(i, j)] *= rsqrtf(piv[j]);
-    else if (j == i) a[pk(i, i)] = sqrtf(piv[i]);
-  }
-  __syncthreads();
-  if (Lout) {
-    float* Lg = Lout + (long long)grp * g * g;
-    for (int idx = t; idx < g * g; idx += nt) {
-      int i = idx / g, j = idx % g;
-      Lg[idx] = (j <= i) ? a[pk(i, j)] : 0.f;
-    }
-  }
-  if (!Linv_out) return;
-  __syncthreads();
-  // in-place inverse, row by row: X[i,j] = (delta_ij - sum_{k=j}^{i-1} L[i,k] X[k,j]) / L[i,i]
-  // thread (j, part): 4 threads share one column j and split the k range
-  const int part = t & 3, jcol = t >> 2;
-  for (int i = 0; i < g; ++i) {
-    float lii = a[pk(i, i)];
-    float v = 0.f;
-    bool active = jcol <= i && jcol < g;   // blockDim.x >= 4 g is required by the launcher
-    if (active) {
-      const float* row = a + pk(i, 0);
-      float sacc = 0.f;
-      for (int k = jcol + part; k < i; k += 4) sacc = fmaf(row[k], a[pk(k, jcol)], sacc);
-      v = sacc;
-    }
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    __syncthreads();   // all reads of row i (as L) done before it is overwritten with X
-    if (active && part == 0) a[pk(i, jcol)] = ((jcol == i ? 1.f : 0.f) - v) / lii;
-    __syncthreads();
-  }
-  float* Xg = Linv_out + (long long)grp * g * g;
-  for (int idx = t; idx < g * g; idx += nt) {
-    int i = idx / g, j = idx % g;
-    Xg[idx] = (j <= i) ? a[pk(i, j)] : 0.f;
-  }
-}
-
 // One-sided (Hestenes) Jacobi SVD of the Cholesky factor L (A = L L^T = U diag(sigma^2) U^T).
 // One CTA per group; Bm is a (G,g,g) COLUMN-major scratch (column j contiguous) in global memory (L1/L2
 // resident, only this CTA touches its slice).  A warp owns one column pair per step.
@@ -430,27 +352,18 @@ extern "C" size_t wc_factor_workspace_bytes(int C, int g, int decomposition, int
   size_t n = 2;
   if (decomposition == WC_DECOMP_ZCA) n += 2;
   if (renorm) n += 4;
-  return n * gg_bytes(C, g);
+  return n * gg_bytes(C, g) + wc_align_up(wc_chol_pad_floats(C, g) * 4, 256);
 }
 
 namespace {
 // factor one (G,g,g) SPD matrix `Ashr` -> Wm (inverse square root), optional sqrt factor, optional U/lam
 int factor_matrix(const float* Ashr, int C, int g, int decomposition, float* Wm, float* sqrt_out, float* U, float* lam,
-                  float* L /*scratch or output*/, float* Bm, float* Us, int32_t* info, cudaStream_t st) {
+                  float* L /*scratch or output*/, float* Bm, float* Us, float* Xpad, int32_t* info, cudaStream_t st) {
   const int G = C / g;
-  size_t smem = ((size_t)g * (g + 1) / 2 + 2 * (size_t)g) * 4;
-  int threads = min(1024, max(128, ((4 * g + 31) / 32) * 32));
-  if (4 * g > 1024) return WC_E_UNSUPPORTED;   // g <= 256
-  if (smem > 227 * 1024) return WC_E_UNSUPPORTED;
-  if (smem > 48 * 1024) WC_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long total = (long long)C * g;
-  if (decomposition == WC_DECOMP_CHOLESKY) {
-    chol_inv_kernel<<<G, threads, smem, st>>>(Ashr, g, sqrt_out, Wm, info);
-    WC_CHECK_LAUNCH();
-    return 0;
-  }
-  chol_inv_kernel<<<G, threads, smem, st>>>(Ashr, g, L, nullptr, info);
-  WC_CHECK_LAUNCH();
+  if (decomposition == WC_DECOMP_CHOLESKY) return wc_chol_inv_launch(Ashr, C, g, sqrt_out, Wm, Xpad, info, st);
+  int rcc = wc_chol_inv_launch(Ashr, C, g, L, nullptr, Xpad, info, st);
+  if (rcc) return rcc;
   jacobi_kernel<<<G, 1024, 0, st>>>(L, g, Bm, U, lam, info);
   WC_CHECK_LAUNCH();
   scale_cols_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(U, lam, C, g, -0.25f, Us);
@@ -476,7 +389,7 @@ extern "C" int wc_factor_fwd(const float* mean, const float* S, const float* cou
   if (decomposition != WC_DECOMP_CHOLESKY && decomposition != WC_DECOMP_ZCA) return WC_E_ARG;
   if (decomposition == WC_DECOMP_ZCA && training && (!U || !lam)) return WC_E_ARG;
   if (training && renorm && !R) return WC_E_ARG;
-  if (g > 512) return WC_E_UNSUPPORTED;
+  if (g > 256) return WC_E_UNSUPPORTED;   // one CTA holds the whole group matrix in shared memory
   if (workspace_bytes < wc_factor_workspace_bytes(C, g, decomposition, renorm && training)) return WC_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const int G = C / g;
@@ -488,6 +401,7 @@ extern "C" int wc_factor_fwd(const float* mean, const float* S, const float* cou
   size_t off = 2 * gb;
   const bool zca = decomposition == WC_DECOMP_ZCA;
   if (zca) { Bm = reinterpret_cast<float*>(ws + off); Us = reinterpret_cast<float*>(ws + off + gb); off += 2 * gb; }
+  float* Xpad = reinterpret_cast<float*>(ws + ((zca ? 4 : 2) + ((renorm && training) ? 4 : 0)) * gb);
   const float extra = zca ? eps : 0.f;   // conditional_layers.py:671 adds eps*I again on top of :691
   long long total = (long long)C * g;
   int rc;
@@ -497,7 +411,7 @@ extern "C" int wc_factor_fwd(const float* mean, const float* S, const float* cou
                                                             moving_mean, moving_cov, Ashr);
     WC_CHECK_LAUNCH();
     if (zca && (!U || !lam)) return WC_E_ARG;   // eigenvector / eigenvalue scratch is required in every phase
-    return factor_matrix(Ashr, C, g, decomposition, Weff, nullptr, U, lam, L, Bm, Us, info, st);
+    return factor_matrix(Ashr, C, g, decomposition, Weff, nullptr, U, lam, L, Bm, Us, Xpad, info, st);
   }
   float *Amov = nullptr, *Wmov = nullptr, *Lb = nullptr, *Umov = nullptr;
   if (renorm) {
@@ -508,13 +422,13 @@ extern "C" int wc_factor_fwd(const float* mean, const float* S, const float* cou
                                                             moving_mean, moving_cov, Amov);
     WC_CHECK_LAUNCH();
     // lam scratch for the moving factor: reuse R's first C floats (R is written afterwards)
-    rc = factor_matrix(Amov, C, g, decomposition, Wmov, nullptr, Umov, R, L, Bm, Us, info, st);
+    rc = factor_matrix(Amov, C, g, decomposition, Wmov, nullptr, Umov, R, L, Bm, Us, Xpad, info, st);
     if (rc) return rc;
   }
   factor_prep_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(mean, S, count_dev, (float)count_host, C, g, eps, extra, momentum, 1,
                                                           moving_mean, moving_cov, Ashr);
   WC_CHECK_LAUNCH();
-  rc = factor_matrix(Ashr, C, g, decomposition, Wm, renorm ? Lb : nullptr, U, lam, L, Bm, Us, info, st);
+  rc = factor_matrix(Ashr, C, g, decomposition, Wm, renorm ? Lb : nullptr, U, lam, L, Bm, Us, Xpad, info, st);
   if (rc) return rc;
   if (renorm) {
     rc = smm(smm_gg(Wmov, false, Lb, false, R, g, G), st);           // R = l_mov_inverse . stop_gradient(l)   (:697-698)

@@ -22,20 +22,34 @@ constexpr int TB = 32, TP = 36, TS = TP * TB;   // tile edge, pitch, floats per 
 constexpr int NW = 16;                          // warps per CTA
 constexpr unsigned FULL = 0xffffffffu;
 
+__device__ long long g_chol_ts[64];
+#define TS_MARK(i) do { if (t == 0 && blockIdx.x == 0) g_chol_ts[i] = clock64(); } while (0)
+
 __device__ __forceinline__ float* tile_at(float* base, int I, int J) { return base + (I * (I + 1) / 2 + J) * TS; }
 
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // in-place lower Cholesky of a 32x32 tile; lane owns one row.  rdiag[c] = 1 / L[c][c].
+// The diagonal element of each row is tracked in its own register so that the pivot chain is
+// shfl -> rsqrt -> mul -> fma per column (no dependency through the off-diagonal shuffles).
 __device__ void warp_potrf32(float* T, float* rdiag, int lane, int& bad) {
   float a[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) a[c] = T[c * TP + lane];
+  float dg = T[lane * TP + lane];
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
-    float piv = __shfl_sync(FULL, a[k], k);
+    float piv = __shfl_sync(FULL, dg, k);
     if (!(piv > 0.f)) { if (!bad) bad = k + 1; piv = 1e-30f; }
-    const float rs = rsqrtf(piv);
-    const float lk = a[k] * rs;
+    float rs = rsqrt_approx(piv);
+    rs = rs * fmaf(-0.5f * piv * rs, rs, 1.5f);      // one Newton step: full fp32 accuracy
+    const float lk = (lane == k) ? piv * rs : a[k] * rs;
     a[k] = lk;
+    dg = fmaf(-lk, lk, dg);
     if (lane == k) rdiag[k] = rs;
 #pragma unroll
     for (int j = k + 1; j < 32; ++j) {
@@ -47,20 +61,21 @@ __device__ void warp_potrf32(float* T, float* rdiag, int lane, int& bad) {
   for (int c = 0; c < 32; ++c) T[c * TP + lane] = (c <= lane) ? a[c] : 0.f;
 }
 
-// solve X L^T = A for one 32x32 tile (lane = row of X).  x[] holds the row of A on entry, of X on exit.
+// solve X L^T = A for one 32x32 tile (lane = row of X), right-looking: once x[m] is final, every later
+// column is updated with column m of L, which is contiguous in the column-major tile (128-bit broadcast loads).
 __device__ __forceinline__ void warp_trsm_row(float (&x)[32], const float* Ljj, const float* rdiag) {
 #pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    float s0 = x[c], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int m = 0; m < 32; ++m) {
+    x[m] *= rdiag[m];
+    const float xm = x[m];
 #pragma unroll
-    for (int m = 0; m < c; ++m) {
-      const float l = Ljj[m * TP + c];               // L[c][m], same address for every lane (broadcast)
-      if ((m & 3) == 0) s0 = fmaf(-x[m], l, s0);
-      else if ((m & 3) == 1) s1 = fmaf(-x[m], l, s1);
-      else if ((m & 3) == 2) s2 = fmaf(-x[m], l, s2);
-      else s3 = fmaf(-x[m], l, s3);
+    for (int q = (m + 1) / 4; q < 8; ++q) {
+      const float4 l = *reinterpret_cast<const float4*>(Ljj + m * TP + 4 * q);   // L[4q..4q+3][m]
+      if (4 * q + 0 > m) x[4 * q + 0] = fmaf(-xm, l.x, x[4 * q + 0]);
+      if (4 * q + 1 > m) x[4 * q + 1] = fmaf(-xm, l.y, x[4 * q + 1]);
+      if (4 * q + 2 > m) x[4 * q + 2] = fmaf(-xm, l.z, x[4 * q + 2]);
+      if (4 * q + 3 > m) x[4 * q + 3] = fmaf(-xm, l.w, x[4 * q + 3]);
     }
-    x[c] = ((s0 + s1) + (s2 + s3)) * rdiag[c];
   }
 }
 
@@ -122,22 +137,42 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
   // X is produced row-major with leading dimension gp; when g is a multiple of 32 that is the output itself
   float* X = (Xout && gp == g) ? Xout + (long long)grp * g * g : Xpad + (long long)grp * gp * gp;
 
-  for (int idx = t; idx < gp * gp; idx += NW * 32) {
-    const int i = idx / gp, j = idx % gp;
-    if ((j >> 5) > (i >> 5)) continue;
-    const float v = (i < g && j < g) ? Ag[(long long)i * g + j] : (i == j ? 1.f : 0.f);
-    tile_at(tiles, i >> 5, j >> 5)[(j & 31) * TP + (i & 31)] = v;
+  // load the lower tiles (128-bit loads when rows are 16-byte aligned), pad with the identity; the strictly
+  // upper tiles of the output X are zero-filled here so the stores drain while the factorisation runs
+  const bool vec_ok = (g & 3) == 0;
+#pragma unroll 4
+  for (int i = warp; i < gp; i += NW) {
+    for (int j4 = lane * 4; j4 < gp; j4 += 128) {
+      if ((j4 >> 5) > (i >> 5)) {
+        if (Xout) *reinterpret_cast<float4*>(X + (long long)i * gp + j4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+      float v[4];
+      if (vec_ok && i < g && j4 + 3 < g) {
+        const float4 q = *reinterpret_cast<const float4*>(Ag + (long long)i * g + j4);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const int j = j4 + e; v[e] = (i < g && j < g) ? Ag[(long long)i * g + j] : (i == j ? 1.f : 0.f); }
+      }
+      float* T = tile_at(tiles, i >> 5, j4 >> 5) + (i & 31);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) T[((j4 + e) & 31) * TP] = v[e];
+    }
   }
   __syncthreads();
+  TS_MARK(0);
 
   // ------------------------------------------------------------------ Cholesky
   for (int J = 0; J < NB; ++J) {
+    TS_MARK(1 + 3 * J);
     if (warp == 0) {
       int bad = 0;
       warp_potrf32(tile_at(tiles, J, J), rdiag + J * TB, lane, bad);
       if (bad && lane == 0 && info && J * TB + bad <= g) atomicCAS(&info[WC_INFO_NOT_PD], 0, grp * g + J * TB + bad);
     }
     __syncthreads();
+    TS_MARK(2 + 3 * J);
     const float* Ljj = tile_at(tiles, J, J);
     const int npanel = NB - 1 - J;
     // panel solves (npanel tiles) + the inverse of the diagonal tile (one more job)
@@ -164,6 +199,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
       }
     }
     __syncthreads();
+    TS_MARK(3 + 3 * J);
     // trailing updates: tile(I,K) -= L_IJ L_KJ^T for J < K <= I
     const int nupd = npanel * (npanel + 1) / 2;
     for (int job = warp; job < nupd; job += NW) {
@@ -188,6 +224,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
     __syncthreads();
   }
 
+  TS_MARK(30);
   if (Lout) {
     float* Lg = Lout + (long long)grp * g * g;
     for (int idx = t; idx < g * g; idx += NW * 32) {
@@ -198,11 +235,6 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
   if (!Xout) return;
 
   // ------------------------------------------------------------------ inverse
-  // strictly-upper tiles of X are zero
-  for (int idx = t; idx < gp * gp; idx += NW * 32) {
-    const int i = idx / gp, j = idx % gp;
-    if ((j >> 5) > (i >> 5)) X[idx] = 0.f;
-  }
   // each warp owns up to two off-diagonal tiles (NB <= 8 -> 28 tiles); accumulators live in registers
   const int noff = NB * (NB - 1) / 2;
   float S[2][4][8];
@@ -218,11 +250,13 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
       for (int c = 0; c < 8; ++c) S[s][r][c] = 0.f;
   }
   __syncthreads();   // diagonal tiles of X (global) and the zero fill are visible
+  TS_MARK(31);
 #pragma unroll
   for (int s = 0; s < 2; ++s)
     if (tI[s] >= 0)   // S_IJ = L_IJ X_JJ
       warp_tile_fma(S[s], tile_at(tiles, tI[s], tJ[s]), X + (long long)(tJ[s] * TB) * gp + tJ[s] * TB, gp, ly, lx);
   for (int d = 1; d < NB; ++d) {
+    TS_MARK(32 + 2 * d);
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       if (tI[s] >= 0 && tI[s] - tJ[s] == d) {
@@ -237,11 +271,13 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
       }
     }
     __syncthreads();
+    TS_MARK(33 + 2 * d);
 #pragma unroll
     for (int s = 0; s < 2; ++s)
       if (tI[s] >= 0 && tI[s] - tJ[s] > d)   // S_IJ += L_{I,J+d} X_{J+d,J}
         warp_tile_fma(S[s], tile_at(tiles, tI[s], tJ[s] + d), X + (long long)((tJ[s] + d) * TB) * gp + tJ[s] * TB, gp, ly, lx);
   }
+  TS_MARK(50);
   if (gp != g) {
     __syncthreads();
     float* Xg = Xout + (long long)grp * g * g;
@@ -270,4 +306,8 @@ int wc_chol_inv_launch(const float* Ain, int C, int g, float* Lout, float* Xout,
   chol_inv_tiled_kernel<<<C / g, NW * 32, smem, st>>>(Ain, g, Lout, Xout, Xpad, info);
   WC_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int wc_debug_chol_timing(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_chol_ts, sizeof(long long) * 64);
 }

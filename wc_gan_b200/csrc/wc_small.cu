@@ -26,32 +26,41 @@ __global__ void __launch_bounds__(256) smm_kernel(WcSmm p, SmmExtra ex) {
   const bool a_kfast = (p.csA == 1) || (p.rsA != 1);   // which index varies fastest across threads when loading
   const bool b_jfast = (p.csB == 1) || (p.rsB != 1);
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int q = 0; q < p.nsum; ++q) {
+  // loader coordinates of this thread's 4 A and 4 B elements per k-chunk
+  int aii[4], akk[4], bjj[4], bkb[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    int idx = threadIdx.x + e * 256;
+    int lo = idx & 31, hi = idx >> 5;
+    aii[e] = a_kfast ? hi : lo; akk[e] = a_kfast ? lo : hi;
+    bjj[e] = b_jfast ? lo : hi; bkb[e] = b_jfast ? hi : lo;
+  }
+  const int nk = (p.K + 31) / 32;
+  const int total = p.nsum * nk;
+  float ra[4], rb[4];
+  auto gload = [&](int it) {
+    const int q = it / nk, k0 = (it % nk) * 32;
     const float* Aq = A + (long long)q * p.sA;
     const float* Bq = B + (long long)q * p.sB;
-    for (int k0 = 0; k0 < p.K; k0 += 32) {
-      __syncthreads();
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        int idx = threadIdx.x + e * 256;
-        int lo = idx & 31, hi = idx >> 5;
-        int ii = a_kfast ? hi : lo, kk = a_kfast ? lo : hi;
-        float v = 0.f;
-        if (i0 + ii < p.M && k0 + kk < p.K) v = Aq[(long long)(i0 + ii) * p.rsA + (long long)(k0 + kk) * p.csA];
-        As[ii][kk] = v;
-        int jj = b_jfast ? lo : hi, kb = b_jfast ? hi : lo;
-        float w = 0.f;
-        if (j0 + jj < p.N && k0 + kb < p.K) w = Bq[(long long)(k0 + kb) * p.rsB + (long long)(j0 + jj) * p.csB];
-        Bs[kb][jj] = w;
-      }
-      __syncthreads();
+    for (int e = 0; e < 4; ++e) {
+      ra[e] = (i0 + aii[e] < p.M && k0 + akk[e] < p.K) ? Aq[(long long)(i0 + aii[e]) * p.rsA + (long long)(k0 + akk[e]) * p.csA] : 0.f;
+      rb[e] = (j0 + bjj[e] < p.N && k0 + bkb[e] < p.K) ? Bq[(long long)(k0 + bkb[e]) * p.rsB + (long long)(j0 + bjj[e]) * p.csB] : 0.f;
+    }
+  };
+  if (total > 0) gload(0);
+  for (int it = 0; it < total; ++it) {
+    __syncthreads();
 #pragma unroll
-      for (int kk = 0; kk < 32; ++kk) {
-        float a0 = As[ty * 2][kk], a1 = As[ty * 2 + 1][kk];
-        float c0 = Bs[kk][tx * 2], c1 = Bs[kk][tx * 2 + 1];
-        acc[0][0] = fmaf(a0, c0, acc[0][0]); acc[0][1] = fmaf(a0, c1, acc[0][1]);
-        acc[1][0] = fmaf(a1, c0, acc[1][0]); acc[1][1] = fmaf(a1, c1, acc[1][1]);
-      }
+    for (int e = 0; e < 4; ++e) { As[aii[e]][akk[e]] = ra[e]; Bs[bkb[e]][bjj[e]] = rb[e]; }
+    __syncthreads();
+    if (it + 1 < total) gload(it + 1);     // next chunk's loads overlap this chunk's math
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      float a0 = As[ty * 2][kk], a1 = As[ty * 2 + 1][kk];
+      float c0 = Bs[kk][tx * 2], c1 = Bs[kk][tx * 2 + 1];
+      acc[0][0] = fmaf(a0, c0, acc[0][0]); acc[0][1] = fmaf(a0, c1, acc[0][1]);
+      acc[1][0] = fmaf(a1, c0, acc[1][0]); acc[1][1] = fmaf(a1, c1, acc[1][1]);
     }
   }
   float alpha = p.alpha;

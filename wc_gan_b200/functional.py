@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, sync
 from ._lib import check, lib, ptr
 
 
@@ -122,7 +122,7 @@ class WhiteningColoringFn(torch.autograd.Function):
             raise ValueError(f'channels {Cin} not divisible by group_size {g}')
         G = Cin // g
         dec = _lib.WC_DECOMP[spec.decomposition]
-        world = dist.get_world_size(group) if (group is not None and dist.is_initialized()) else 1
+        world = sync.world_size(group)
         sync = spec.whiten and training and world > 1
 
         mean = Weff = Wm = R = U = lam = count_dev = None
@@ -139,8 +139,7 @@ class WhiteningColoringFn(torch.autograd.Function):
                 _call('wc_stats_fwd', ptr(x), N * HW, Cin, g, ptr(ws), nb, ptr(mean_l), ptr(S_l), st)
                 if sync:
                     rec[-1:].fill_(count)
-                    recs = _f32(world, rec.numel(), device=dev)
-                    dist.all_gather_into_tensor(recs, rec, group=group)
+                    recs = sync.gather_shard_records(rec, group)
                     mean, S, count_dev = _f32(Cin, device=dev), _f32(G, g, g, device=dev), _f32(1, device=dev)
                     _call('wc_stats_merge', ptr(recs), world, Cin, g, ptr(mean), ptr(S), ptr(count_dev), st)
                 else:
@@ -227,7 +226,7 @@ class WhiteningColoringFn(torch.autograd.Function):
             A = cvec = None
             if stats_grad:
                 if ctx.sync:
-                    dist.all_reduce(red, group=ctx.group)
+                    sync.allreduce_adjoint(red, ctx.group)
                 A, cvec = _f32(G, g, g, device=dev), _f32(Cin, device=dev)
                 nb = lib.wc_factor_bwd_workspace_bytes(Cin, g, dec, int(spec.renorm))
                 ws = _ws(nb, dev)

@@ -123,7 +123,7 @@ class WhiteningColoringFn(torch.autograd.Function):
         G = Cin // g
         dec = _lib.WC_DECOMP[spec.decomposition]
         world = sync.world_size(group)
-        sync = spec.whiten and training and world > 1
+        do_sync = spec.whiten and training and world > 1
 
         mean = Weff = Wm = R = U = lam = count_dev = None
         count = float(N * HW)
@@ -137,7 +137,7 @@ class WhiteningColoringFn(torch.autograd.Function):
                 nb = lib.wc_stats_workspace_bytes(N * HW, Cin, g)
                 ws = _ws(nb, dev)
                 _call('wc_stats_fwd', ptr(x), N * HW, Cin, g, ptr(ws), nb, ptr(mean_l), ptr(S_l), st)
-                if sync:
+                if do_sync:
                     rec[-1:].fill_(count)
                     recs = sync.gather_shard_records(rec, group)
                     mean, S, count_dev = _f32(Cin, device=dev), _f32(G, g, g, device=dev), _f32(1, device=dev)
@@ -178,7 +178,7 @@ class WhiteningColoringFn(torch.autograd.Function):
         _call('wc_apply_fwd', ptr(x), N, HW, Cin, Cout, ptr(mean), ptr(T), ptr(Tp), ptr(b), ptr(cls), K, band,
                                ptr(y), ptr(info), st)
 
-        ctx.spec, ctx.training, ctx.group, ctx.sync = spec, training, group, sync
+        ctx.spec, ctx.training, ctx.group, ctx.sync = spec, training, group, do_sync
         ctx.dims = (N, HW, Cin, Cout, g, K, E, count)
         ctx.has = tuple(t is not None for t in (Wu, bu, Wc, bc, class_matrix, D, bf))
         ctx.save_for_backward(x, mean, cls, Weff, Wm, R, U, lam, Wk, T, ehat, count_dev, class_matrix, D)

@@ -230,7 +230,8 @@ __global__ void pivot_kernel(const float* __restrict__ x, int rows, int C, float
 //   d = sum(x-p)/M, mean = p + d, S = S_p - M d d^T   (diagonal blocks only)
 __global__ void stats_finalize_kernel(const float* __restrict__ partS, const float* __restrict__ partSum,
                                       int nchunks, long long strideS, int C, int g, double M,
-                                      const float* __restrict__ pivot, float* __restrict__ mean, float* __restrict__ S) {
+                                      const float* __restrict__ pivot, float* __restrict__ mean, float* __restrict__ S,
+                                      int lower_only) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)C * g;
   if (idx >= total) return;
@@ -239,7 +240,9 @@ __global__ void stats_finalize_kernel(const float* __restrict__ partS, const flo
   int i = grp * g + rem / g, j = grp * g + rem % g;
   float s = 0.f, di = 0.f, dj = 0.f;
   for (int q = 0; q < nchunks; ++q) {
-    s += partS[(long long)q * strideS + (long long)i * C + j];
+    // the tensor-core path only accumulates the blocks with j <= i (the scatter is symmetric)
+    s += lower_only ? partS[(long long)q * strideS + (long long)max(i, j) * C + min(i, j)]
+                    : partS[(long long)q * strideS + (long long)i * C + j];
     di += partSum[(long long)q * C + i];
     dj += partSum[(long long)q * C + j];
   }
@@ -322,7 +325,7 @@ StatsPlan plan_stats(int64_t M, int C, int g) {
 }  // namespace
 
 bool wc_tc_gram_ok(int Cin, int Cout);
-int wc_tc_gram_self(const float* x, long long M, int C, const float* pivot, float* Sp, float* sums, cudaStream_t st);
+int wc_tc_gram_self(const float* x, long long M, int C, int g, const float* pivot, float* Sp, float* sums, cudaStream_t st);
 int wc_tc_gram_cross(const float* x, const float* dy, int N, int HW, int C, const float* mean, const int32_t* order,
                      const int32_t* slot_of, float* P, float* s, cudaStream_t st);
 
@@ -354,10 +357,10 @@ extern "C" int wc_stats_fwd(const float* x, int64_t M, int C, int g, float* work
     // (partial slot 0); the finalize kernel keeps the diagonal blocks when g < C.
     WC_CUDA(cudaMemsetAsync(psum, 0, (size_t)C * 4, st));
     WC_CUDA(cudaMemsetAsync(pS, 0, (size_t)C * C * 4, st));
-    int rc = wc_tc_gram_self(x, M, C, pivot, pS, psum, st);
+    int rc = wc_tc_gram_self(x, M, C, g, pivot, pS, psum, st);
     if (rc) return rc;
     long long tot = (long long)C * g;
-    stats_finalize_kernel<<<wc_cdiv(tot, 256), 256, 0, st>>>(pS, psum, 1, (long long)C * C, C, g, (double)M, pivot, mean, S);
+    stats_finalize_kernel<<<wc_cdiv(tot, 256), 256, 0, st>>>(pS, psum, 1, (long long)C * C, C, g, (double)M, pivot, mean, S, 1);
     WC_CHECK_LAUNCH();
     return 0;
   }
@@ -373,7 +376,7 @@ extern "C" int wc_stats_fwd(const float* x, int64_t M, int C, int g, float* work
   if (vec) gram_kernel<true><<<grid, NT, 0, st>>>(p); else gram_kernel<false><<<grid, NT, 0, st>>>(p);
   WC_CHECK_LAUNCH();
   long long total = (long long)C * g;
-  stats_finalize_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(pS, psum, pl.nchunks, (long long)C * C, C, g, (double)M, pivot, mean, S);
+  stats_finalize_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(pS, psum, pl.nchunks, (long long)C * C, C, g, (double)M, pivot, mean, S, 0);
   WC_CHECK_LAUNCH();
   return 0;
 }

@@ -138,8 +138,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_apply_kernel(TcApplyParams p) 
     // K block = 128 rows x 32 channels = 512 chunks of 8 channels; thread handles chunks t and t+256:
     // row = q/4, chunk-in-row = q%4 -> 4 consecutive threads read one row's 128 contiguous bytes.
     const int crow0 = t >> 2, cch = t & 3;
-    float4 v[2][2];
-    auto gload = [&](int it) {
+    // Global loads run TWO K blocks ahead of the conversion (two register buffers): ~32 KB in flight per CTA,
+    // which is what it takes to cover HBM latency at full bandwidth with two CTAs per SM.
+    float4 va[2][2], vb[2][2];
+    auto gload = [&](int it, float4 (&v)[2][2]) {
       const int sg = it / cfg::NKB, kb = it % cfg::NKB;
       const float* A = p.seg[sg].A;
 #pragma unroll
@@ -154,8 +156,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_apply_kernel(TcApplyParams p) 
         }
       }
     };
-    gload(0);
-    for (int it = 0; it < total_kb; ++it) {
+    auto process = [&](int it, float4 (&v)[2][2]) {
       const int s = it % cfg::STAGES;
       const uint32_t ph = (it / cfg::STAGES) & 1;
       const int sg = it / cfg::NKB, kb = it % cfg::NKB;
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_apply_kernel(TcApplyParams p) 
         split2(b.x, b.y, hi[h][2], lo[h][2]);
         split2(b.z, b.w, hi[h][3], lo[h][3]);
       }
-      if (it + 1 < total_kb) gload(it + 1);            // next block's loads fly while we wait for the stage
+      if (it + 2 < total_kb) gload(it + 2, v);          // refill this buffer: its loads fly over the next block
       mbar_wait(&empty_bar[s], ph ^ 1);
       uint8_t* a_hi = smem + s * cfg::STAGE;
 #pragma unroll
@@ -187,6 +188,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_apply_kernel(TcApplyParams p) 
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
+    };
+    gload(0, va);
+    if (total_kb > 1) gload(1, vb);
+    for (int it = 0; it < total_kb; it += 2) {
+      process(it, va);
+      if (it + 1 < total_kb) process(it + 1, vb);
     }
     // ------------------------------------------------------------------ epilogue (same 8 warps)
     mbar_wait(&acc_bar, 0);

@@ -25,12 +25,13 @@ constexpr int KR = 32;                 // rows (K of the MMA) per stage
 constexpr int NCONV_WARPS = 8;
 constexpr int NCONV = NCONV_WARPS * 32;
 constexpr int NTHREADS = (NCONV_WARPS + 1) * 32;
-constexpr int UNIT_ROWS = 512;         // a unit never crosses a sample boundary
+constexpr int UNIT_ROWS = 64;          // a unit never crosses a sample boundary
 
 struct TcGramParams {
   const float* A; const float* B;       // [rows][C]
   const float* ma; const float* mb;     // shifts (nullable)
-  int self;                             // 1: B == A (same shift): convert once
+  int self;                             // 1: B == A (same shift): convert once; only blocks j <= i inside a group are flushed
+  int g;                                // self mode: group size (flush only what the finalize kernel reads)
   int N, HW, ups;                       // samples, rows per sample, units per sample
   long long units_per_cta;
   const int32_t* order; const int32_t* slot_of;
@@ -166,8 +167,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p) {
     if (p.mb) { mb0 = *reinterpret_cast<const float4*>(p.mb + cc * 8); mb1 = *reinterpret_cast<const float4*>(p.mb + cc * 8 + 4); }
 
     // one "phase" = one operand of one step; loads are prefetched one phase ahead
-    float4 v[cfg::CHUNKS_PER_THREAD][2];
-    auto gload = [&](const Step& st, int operand) {
+    // two register buffers: global loads run two phases ahead of the conversion (~64 KB in flight per SM)
+    float4 v0[cfg::CHUNKS_PER_THREAD][2], v1[cfg::CHUNKS_PER_THREAD][2];
+    auto gload = [&](const Step& st, int operand, float4 (&v)[cfg::CHUNKS_PER_THREAD][2]) {
       const float* src = operand == 0 ? p.A : p.B;
 #pragma unroll
       for (int h = 0; h < cfg::CHUNKS_PER_THREAD; ++h) {
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p) {
       }
     };
     uint32_t hi[cfg::CHUNKS_PER_THREAD][4], lo[cfg::CHUNKS_PER_THREAD][4];
-    auto convert = [&](const Step& st, int operand) {      // registers v -> bf16 hi/lo words (+ column sums)
+    auto convert = [&](const Step& st, int operand, float4 (&v)[cfg::CHUNKS_PER_THREAD][2]) {   // v -> bf16 hi/lo words (+ column sums)
       const float4 m0 = operand == 0 ? ma0 : mb0, m1 = operand == 0 ? ma1 : mb1;
       float* sum = operand == 0 ? sa : sb;
       const bool want = operand == 0 ? want_a : want_b;
@@ -214,8 +216,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p) {
 #pragma unroll 1
       for (int mh = 0; mh < cfg::MH; ++mh) {
         const int i = mh * 128 + q * 32 + lane;
+        const int i0 = mh * 128 + q * 32;
+        int clo = 0, chi = C;                      // self mode: only blocks the finalize kernel reads (j <= i, same group)
+        if (p.self) { clo = (i0 / p.g) * p.g; chi = min(((i0 + 31) / p.g + 1) * p.g, i0 + 32); }
 #pragma unroll 1
         for (int c0 = half * (C / 2); c0 < (half + 1) * (C / 2); c0 += 32) {
+          if (c0 >= chi || c0 + 32 <= clo) continue;   // warp-uniform
           float acc[32];
           tmem_ld32(td + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * C + c0), acc);
           float* dst = out + (long long)i * C + c0;
@@ -244,31 +250,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p) {
       }
     };
 
+    struct Phase { Step st; int op; int it; bool valid; };
     StepIter iter(p, ub, ue);
-    Step cur = iter.next();
     const int nops = p.self ? 1 : 2;
-    gload(cur, 0);
+    Step gen_step = iter.next();
+    int gen_op = 0, gen_it = 0;
+    auto gen = [&](Phase& ph) {
+      ph.valid = gen_step.valid;
+      if (!ph.valid) return;
+      ph.st = gen_step; ph.op = gen_op; ph.it = gen_it;
+      if (++gen_op == nops) { gen_op = 0; gen_step = iter.next(); ++gen_it; }
+    };
     uint32_t nflush = 0;
-    int it = 0, cur_slot = cur.slot;
-    while (cur.valid) {
-      Step nxt = iter.next();
-      if (cur.flush_before) { flush(cur_slot, nflush & 1); ++nflush; }
-      cur_slot = cur.slot;
-      const int s = it % cfg::STAGES;
-      const uint32_t ph = (it / cfg::STAGES) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      uint8_t* stage = smem + s * stage_bytes;
-      for (int op = 0; op < nops; ++op) {
-        convert(cur, op);                                   // registers v hold operand `op` of `cur`
-        if (op + 1 < nops) gload(cur, op + 1);              // prefetch the next phase while we store
-        else if (nxt.valid) gload(nxt, 0);
-        store(stage + op * 2 * cfg::IMG);
+    int cur_slot = gen_step.slot;
+    auto process = [&](Phase& ph, float4 (&v)[cfg::CHUNKS_PER_THREAD][2]) {
+      const int s = ph.it % cfg::STAGES;
+      if (ph.op == 0) {
+        if (ph.st.flush_before) { flush(cur_slot, nflush & 1); ++nflush; }
+        cur_slot = ph.st.slot;
+        mbar_wait(&empty_bar[s], ((ph.it / cfg::STAGES) & 1) ^ 1);
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
-      cur = nxt;
-      ++it;
+      convert(ph.st, ph.op, v);
+      const int op = ph.op;
+      gen(ph);                                              // this buffer now belongs to the phase after next
+      if (ph.valid) gload(ph.st, ph.op, v);
+      store(smem + s * stage_bytes + op * 2 * cfg::IMG);
+      if (op == nops - 1) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+      }
+    };
+    Phase ph0, ph1;
+    gen(ph0);
+    if (ph0.valid) gload(ph0.st, ph0.op, v0);
+    gen(ph1);
+    if (ph1.valid) gload(ph1.st, ph1.op, v1);
+    while (ph0.valid) {
+      process(ph0, v0);
+      if (!ph1.valid) break;
+      process(ph1, v1);
     }
     flush(cur_slot, nflush & 1);
   }
@@ -299,9 +320,9 @@ int launch_tc_gram(TcGramParams& p, cudaStream_t st) {
 bool wc_tc_gram_ok(int Cin, int Cout) { return Cin == Cout && (Cin == 128 || Cin == 256); }
 
 // Sp (C,C) and sums (C) must be zero on entry (the caller memsets them on the same stream).
-int wc_tc_gram_self(const float* x, long long M, int C, const float* pivot, float* Sp, float* sums, cudaStream_t st) {
+int wc_tc_gram_self(const float* x, long long M, int C, int g, const float* pivot, float* Sp, float* sums, cudaStream_t st) {
   TcGramParams p{};
-  p.A = x; p.B = x; p.ma = pivot; p.mb = pivot; p.self = 1;
+  p.A = x; p.B = x; p.ma = pivot; p.mb = pivot; p.self = 1; p.g = g;
   p.N = 1; p.HW = (int)M;
   p.order = nullptr; p.slot_of = nullptr;
   p.out = Sp; p.out_slot_stride = 0;
@@ -313,7 +334,7 @@ int wc_tc_gram_self(const float* x, long long M, int C, const float* pivot, floa
 int wc_tc_gram_cross(const float* x, const float* dy, int N, int HW, int C, const float* mean, const int32_t* order,
                      const int32_t* slot_of, float* P, float* s, cudaStream_t st) {
   TcGramParams p{};
-  p.A = x; p.B = dy; p.ma = mean; p.mb = nullptr; p.self = 0;
+  p.A = x; p.B = dy; p.ma = mean; p.mb = nullptr; p.self = 0; p.g = C;
   p.N = N; p.HW = HW;
   p.order = order; p.slot_of = slot_of;
   p.out = P; p.out_slot_stride = (long long)C * C;

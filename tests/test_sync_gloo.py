@@ -68,7 +68,9 @@ def _worker(rank, world, port, q):
                           reduced_override=(red[:ng].reshape(G, G_SIZE, G_SIZE), red[ng:]))
         gk = bwd['u_kernel'].clone()
         dist.all_reduce(gk)     # parameter gradients are summed by the data-parallel wrapper (DDP), not by the layer
-        q.put((rank, fwd['y'], bwd['x'], gk, fwd['new_moving_mean'], fwd['new_moving_variance']))
+        # numpy copies: torch tensors travel through the queue as shared-memory files that vanish when the worker exits
+        q.put((rank,) + tuple(t.detach().numpy().copy() for t in
+                              (fwd['y'], bwd['x'], gk, fwd['new_moving_mean'], fwd['new_moving_variance'])))
     finally:
         dist.destroy_process_group()
 
@@ -87,7 +89,7 @@ def test_two_rank_sync_batch_matches_full_batch():
     out = {}
     for _ in range(2):
         r = q.get(timeout=120)
-        out[r[0]] = r[1:]
+        out[r[0]] = tuple(torch.from_numpy(a) for a in r[1:])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

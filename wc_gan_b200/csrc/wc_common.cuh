@@ -22,6 +22,20 @@ void wc_count_launch();
     if (e__ != cudaSuccess) return (int)e__;                \
   } while (0)
 
+// ---- debug-only instrumentation (not part of include/wc_b200.h) ---------------------------------------
+// wc_debug_set(flags): bit0 = kernels record globaltimer marks into a device buffer [block][slot] (allocated by
+// wc_debug_set, the only place this library allocates); other bits are kernel-specific experiment switches.
+constexpr int WC_DBG_BLOCKS = 160, WC_DBG_SLOTS = 8;
+int wc_debug_flags();
+unsigned long long* wc_debug_buf();     // nullptr unless bit0 is set
+__device__ __forceinline__ void wc_mark(unsigned long long* buf, int slot) {
+  if (buf && blockIdx.x < WC_DBG_BLOCKS) {
+    unsigned long long tns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+    buf[blockIdx.x * WC_DBG_SLOTS + slot] = tns;
+  }
+}
+
 static inline bool wc_aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 static inline size_t wc_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int wc_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

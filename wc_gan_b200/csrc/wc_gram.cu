@@ -325,7 +325,7 @@ StatsPlan plan_stats(int64_t M, int C, int g) {
 }  // namespace
 
 bool wc_tc_gram_ok(int Cin, int Cout);
-int wc_tc_gram_self(const float* x, long long M, int C, int g, const float* pivot, float* Sp, float* sums, cudaStream_t st);
+int wc_tc_gram_self(const float* x, long long M, int C, int g, float* pivot_out, float* Sp, float* sums, cudaStream_t st);
 int wc_tc_gram_cross(const float* x, const float* dy, int N, int HW, int C, const float* mean, const int32_t* order,
                      const int32_t* slot_of, float* P, float* s, cudaStream_t st);
 
@@ -349,14 +349,11 @@ extern "C" int wc_stats_fwd(const float* x, int64_t M, int C, int g, float* work
   float* pivot = reinterpret_cast<float*>(ws + pl.off_pivot);
   float* psum = reinterpret_cast<float*>(ws + pl.off_sum);
   float* pS = reinterpret_cast<float*>(ws + pl.off_S);
-  int prow = (int)(M < 1024 ? M : 1024);
-  pivot_kernel<<<wc_cdiv(C, 32), 256, 0, st>>>(x, prow, C, pivot);
-  WC_CHECK_LAUNCH();
   if (g_use_tc_gram && wc_tc_gram_ok(C, C) && wc_aligned16(x)) {
     // tensor-core path: the full C x C scatter is accumulated with vector reductions into one zeroed buffer
-    // (partial slot 0); the finalize kernel keeps the diagonal blocks when g < C.
-    WC_CUDA(cudaMemsetAsync(psum, 0, (size_t)C * 4, st));
-    WC_CUDA(cudaMemsetAsync(pS, 0, (size_t)C * C * 4, st));
+    // (partial slot 0; column sums and scatter are adjacent: one memset); the kernel computes its own pivot and
+    // the finalize kernel keeps the diagonal blocks when g < C.
+    WC_CUDA(cudaMemsetAsync(psum, 0, (pl.off_S - pl.off_sum) + (size_t)C * C * 4, st));
     int rc = wc_tc_gram_self(x, M, C, g, pivot, pS, psum, st);
     if (rc) return rc;
     long long tot = (long long)C * g;
@@ -364,6 +361,9 @@ extern "C" int wc_stats_fwd(const float* x, int64_t M, int C, int g, float* work
     WC_CHECK_LAUNCH();
     return 0;
   }
+  int prow = (int)(M < 1024 ? M : 1024);
+  pivot_kernel<<<wc_cdiv(C, 32), 256, 0, st>>>(x, prow, C, pivot);
+  WC_CHECK_LAUNCH();
   GramParams p{};
   p.A = x; p.B = x; p.lda = C; p.ldb = C; p.ma = pivot; p.mb = pivot; p.nI = C; p.nJ = C;
   p.grouped = 1; p.g = g; p.tw = pl.tw; p.tpg = pl.tpg; p.ntiles = pl.ntiles;

@@ -629,3 +629,22 @@ extern "C" int wc_version(void) { return WC_B200_VERSION; }
 static std::atomic<long long> g_launches{0};
 void wc_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" long long wc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// ---- debug-only instrumentation ------------------------------------------------------------------------
+static int g_dbg_flags = 0;
+static unsigned long long* g_dbg_buf = nullptr;
+int wc_debug_flags() { return g_dbg_flags; }
+unsigned long long* wc_debug_buf() { return (g_dbg_flags & 1) ? g_dbg_buf : nullptr; }
+extern "C" int wc_debug_set(int flags) {
+  g_dbg_flags = flags;
+  if ((flags & 1) && !g_dbg_buf) {
+    cudaError_t e = cudaMalloc(&g_dbg_buf, sizeof(unsigned long long) * WC_DBG_BLOCKS * WC_DBG_SLOTS);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (g_dbg_buf) cudaMemset(g_dbg_buf, 0, sizeof(unsigned long long) * WC_DBG_BLOCKS * WC_DBG_SLOTS);
+  return 0;
+}
+extern "C" int wc_debug_marks(unsigned long long* host_out) {
+  if (!g_dbg_buf) return -1;
+  return (int)cudaMemcpy(host_out, g_dbg_buf, sizeof(unsigned long long) * WC_DBG_BLOCKS * WC_DBG_SLOTS, cudaMemcpyDeviceToHost);
+}

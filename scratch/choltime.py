@@ -16,10 +16,4 @@ for J in range(8):
     a, b, c = ts[1+3*J], ts[2+3*J], ts[3+3*J]
     nxt = ts[1+3*(J+1)] if J < 7 else ts[30]
     print(f'J={J}: potrf {b-a}  trsm+inv {c-b}  update {nxt-c}')
-print('Lout..zero/sync', ts[31]-ts[30])
-print('init S', ts[34]-ts[31])
-for d in range(1, 8):
-    a, b = ts[32+2*d], ts[33+2*d]
-    nxt = ts[32+2*(d+1)] if d < 7 else ts[50]
-    print(f'd={d}: mult {b-a} upd {nxt-b}')
-print('total', ts[50]-ts[0])
+print('load', ts[0]-ts[62], 'chol', ts[30]-ts[0], 'Lout', ts[63]-ts[30], 'total', ts[63]-ts[62])

@@ -125,7 +125,7 @@ __device__ __forceinline__ void tri_index(int t, int& a, int& b) {   // t -> (a,
 
 __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float* __restrict__ Ain, int g, float* __restrict__ Lout,
                                                                     float* __restrict__ Xout, float* __restrict__ Xpad,
-                                                                    int32_t* info) {
+                                                                    int32_t* info, int split_inverse) {
   extern __shared__ __align__(16) float sm[];
   const int NB = (g + TB - 1) / TB, gp = NB * TB;
   float* tiles = sm;                                  // NB(NB+1)/2 tiles
@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
   // X is produced row-major with leading dimension gp; when g is a multiple of 32 that is the output itself
   float* X = (Xout && gp == g) ? Xout + (long long)grp * g * g : Xpad + (long long)grp * gp * gp;
 
+  TS_MARK(62);
   // load the lower tiles (128-bit loads when rows are 16-byte aligned), pad with the identity; the strictly
   // upper tiles of the output X are zero-filled here so the stores drain while the factorisation runs
   const bool vec_ok = (g & 3) == 0;
@@ -232,7 +233,8 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
       Lg[idx] = (j <= i) ? tile_at(tiles, i >> 5, j >> 5)[(j & 31) * TP + (i & 31)] : 0.f;
     }
   }
-  if (!Xout) return;
+  TS_MARK(63);
+  if (!Xout || split_inverse) return;   // split: trinv_kernel forms the off-diagonal blocks of X on many CTAs
 
   // ------------------------------------------------------------------ inverse
   // each warp owns up to two off-diagonal tiles (NB <= 8 -> 28 tiles); accumulators live in registers
@@ -285,6 +287,83 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
   }
 }
 
+
+// ---- L^-1 on many CTAs ------------------------------------------------------------------------------------
+// Column j of X = L^-1 depends only on L, so the inverse parallelises over columns: one CTA per slab of 8 columns
+// runs a blocked forward substitution  x_I = inv(L_II) (e_I - sum_{K<I} L_IK x_K)  with the 32 x 32 diagonal-block
+// inverses that the Cholesky kernel already wrote into X.  g must be a multiple of 32.  L is row-major (G,g,g).
+constexpr int TI_COLS = 8, TI_THREADS = 32 * TI_COLS, TI_LP = 260, TI_DP = 33, TI_NPRE = 7;
+
+__global__ void __launch_bounds__(TI_THREADS) trinv_kernel(const float* __restrict__ L, int g, float* __restrict__ X, unsigned long long* dbg, int dflags) {
+  extern __shared__ __align__(16) float sm[];
+  const int NB = g / TB;
+  const int slabs = g / TI_COLS;
+  const int grp = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+  const int j0 = slab * TI_COLS, J = j0 / TB;
+  if (J == NB - 1) return;                             // last block column: only the diagonal block, already in X
+  const float* Lg = L + (long long)grp * g * g;
+  float* Xg = X + (long long)grp * g * g;
+  float* Ls = sm;                                      // [32][TI_LP] current row panel of L (rows read back as float4)
+  float* Ds = Ls + TB * TI_LP;                         // [32][TI_DP] inverse of the current diagonal block
+  float* xs = Ds + TB * TI_DP;                         // [TI_COLS][g] solution, k contiguous (16-byte aligned)
+  float* rs = xs + TI_COLS * g;                        // [32][TI_COLS + 1] right-hand side of the current block row
+  const int t = threadIdx.x, r = t & 31, c = t >> 5;
+  // x_J = inv(L_JJ)[:, j0..j0+7]: columns of the diagonal-block inverse the Cholesky kernel left in X
+  xs[c * g + J * TB + r] = Xg[(long long)(J * TB + r) * g + j0 + c];
+  // register prefetch of the next block row: panel L[I-block rows, 32J .. 32I) (up to 32 x 224 floats) and inv(L_II)
+  float4 pre[TI_NPRE], dpre;
+  auto prefetch = [&](int I) {
+    // 8 threads per panel row, each takes every 8th float4 of the row (32 (I - J) floats per row)
+    const float4* src = reinterpret_cast<const float4*>(Lg + (long long)(I * TB + (t >> 3)) * g + J * TB) + (t & 7);
+#pragma unroll
+    for (int q = 0; q < TI_NPRE; ++q)
+      if (q < I - J && !(dflags & 16)) pre[q] = __ldg(src + 8 * q);
+    if (!(dflags & 16)) dpre = __ldg(reinterpret_cast<const float4*>(Xg + (long long)(I * TB + (t >> 3)) * g + I * TB) + (t & 7));
+  };
+  auto commit = [&](int I) {
+    float* dstp = Ls + (t >> 3) * TI_LP + (t & 7) * 4;
+#pragma unroll
+    for (int q = 0; q < TI_NPRE; ++q)
+      if (q < I - J) *reinterpret_cast<float4*>(dstp + 32 * q) = pre[q];
+    float* d = Ds + (t >> 3) * TI_DP + (t & 7) * 4;
+    d[0] = dpre.x; d[1] = dpre.y; d[2] = dpre.z; d[3] = dpre.w;
+  };
+  if (t == 0) wc_mark(dbg, 0);
+  prefetch(J + 1);
+  for (int I = J + 1; I < NB; ++I) {
+    __syncthreads();                                   // previous step's readers of Ls / Ds / rs are done; xs of block I-1 visible
+    if (t == 0 && I - J < WC_DBG_SLOTS) wc_mark(dbg, I - J);
+    commit(I);
+    if (I + 1 < NB) prefetch(I + 1);
+    __syncthreads();
+    // rhs[r][c] = - sum_k L[I*32 + r][J*32 + k] x[k][c]
+    const int kn = (I - J) * TB;
+    const float* lrow = Ls + r * TI_LP;
+    const float* xc = xs + c * g + J * TB;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < kn; k += 4) {
+      const float4 lv = *reinterpret_cast<const float4*>(lrow + k);
+      const float4 xv = *reinterpret_cast<const float4*>(xc + k);
+      a0 = fmaf(lv.x, xv.x, a0); a1 = fmaf(lv.y, xv.y, a1);
+      a2 = fmaf(lv.z, xv.z, a2); a3 = fmaf(lv.w, xv.w, a3);
+    }
+    rs[r * (TI_COLS + 1) + c] = -((a0 + a1) + (a2 + a3));
+    __syncthreads();
+    // x_I = inv(L_II) rhs   (lower triangular)
+    const float* drow = Ds + r * TI_DP;
+    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < TB; k += 2) {
+      v0 = fmaf(drow[k], rs[k * (TI_COLS + 1) + c], v0);          // the strict upper triangle of inv(L_II) is stored as zeros
+      v1 = fmaf(drow[k + 1], rs[(k + 1) * (TI_COLS + 1) + c], v1);
+    }
+    const float v = v0 + v1;
+    xs[c * g + I * TB + r] = v;
+    if (!(dflags & 32)) Xg[(long long)(I * TB + r) * g + j0 + c] = v;
+  }
+}
+
 }  // namespace
 
 size_t wc_chol_pad_floats(int C, int g) {
@@ -303,8 +382,20 @@ int wc_chol_inv_launch(const float* Ain, int C, int g, float* Lout, float* Xout,
     WC_CUDA(cudaFuncSetAttribute(chol_inv_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  chol_inv_tiled_kernel<<<C / g, NW * 32, smem, st>>>(Ain, g, Lout, Xout, Xpad, info);
+  // g >= 128 (multiple of 32): the off-diagonal blocks of the inverse are formed by trinv_kernel on g/8 CTAs per group
+  const bool split = Xout && Lout && g >= 128 && (g % TB) == 0;
+  chol_inv_tiled_kernel<<<C / g, NW * 32, smem, st>>>(Ain, g, Lout, Xout, Xpad, info, split ? 1 : 0);
   WC_CHECK_LAUNCH();
+  if (split) {
+    size_t tsm = ((size_t)TB * TI_LP + (size_t)TB * TI_DP + (size_t)TI_COLS * g + (size_t)TB * (TI_COLS + 1)) * sizeof(float);
+    static size_t tattr = 0;
+    if (tsm > 48 * 1024 && tsm > tattr) {
+      WC_CUDA(cudaFuncSetAttribute(trinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+      tattr = tsm;
+    }
+    trinv_kernel<<<(C / g) * (g / TI_COLS), TI_THREADS, tsm, st>>>(Lout, g, Xout, wc_debug_buf(), wc_debug_flags());
+    WC_CHECK_LAUNCH();
+  }
   return 0;
 }
 

@@ -14,7 +14,136 @@ namespace {
 
 struct SmmExtra { const float* count_dev; float count_host; int count_mode; float diag_scale; };
 
-__global__ void __launch_bounds__(256) smm_kernel(WcSmm p, SmmExtra ex) {
+// ---- fast path: one CTA computes a 32 x 32 tile of C ------------------------------------------------------------
+// Latency is what matters here (a 256^3 product is ~1 us of FP32 FFMA spread over 64 CTAs), so each K panel (up to 256)
+// of both operands is fetched with ONE batch of 128-bit loads per operand into shared memory as As[k][i], Bs[k][j]
+// (operands whose k index is the contiguous one are transposed on the way in), and the tile is then computed from
+// there with 4 x 2 register blocking (128 threads).  Requires M, N multiples of 32, K a multiple of 4, unit fast
+// strides and 16-byte aligned rows; anything else takes smm_generic_kernel.
+constexpr int SMM_T = 32, SMM_KC = 256, SMM_P = 36, SMM_THREADS = 512, SMM_KG = 4;   // 4 k-groups of 128 threads
+constexpr int SMM_SMEM = 2 * SMM_KC * SMM_P * 4;
+constexpr int SMM_NV = SMM_KC * SMM_T / 4 / SMM_THREADS;   // float4 per thread per operand panel: 4
+
+// panel(k, m) for k < kc, m < 32 -> dst[k * SMM_P + m].  kfast: element (m, k) at src[m * ld + k]; else at src[k * ld + m]
+template <bool kKFast>
+__device__ __forceinline__ void smm_load_panel(const float* __restrict__ src, long long ld, int kc, float4 (&v)[SMM_NV], int t) {
+  if (kKFast) {
+    const int m = t & 31, k4w = t >> 5;            // lanes walk m: conflict-free transposed stores
+    const int nk4 = kc >> 2;
+#pragma unroll
+    for (int q = 0; q < SMM_NV; ++q) {
+      const int k4 = k4w + q * (SMM_THREADS / 32);
+      if (k4 < nk4) v[q] = __ldg(reinterpret_cast<const float4*>(src + (long long)m * ld) + k4);
+    }
+  } else {
+    const int c4 = t & 7, kw = t >> 3;             // 8 lanes cover the 128 contiguous bytes of one k
+#pragma unroll
+    for (int q = 0; q < SMM_NV; ++q) {
+      const int k = kw + q * (SMM_THREADS / 8);
+      if (k < kc) v[q] = __ldg(reinterpret_cast<const float4*>(src + (long long)k * ld) + c4);
+    }
+  }
+}
+template <bool kKFast>
+__device__ __forceinline__ void smm_store_panel(const float4 (&v)[SMM_NV], int kc, float* __restrict__ dst, int t) {
+  if (kKFast) {
+    const int m = t & 31, k4w = t >> 5;
+    const int nk4 = kc >> 2;
+#pragma unroll
+    for (int q = 0; q < SMM_NV; ++q) {
+      const int k4 = k4w + q * (SMM_THREADS / 32);
+      if (k4 < nk4) {
+        float* d = dst + (k4 * 4) * SMM_P + m;
+        d[0] = v[q].x; d[SMM_P] = v[q].y; d[2 * SMM_P] = v[q].z; d[3 * SMM_P] = v[q].w;
+      }
+    }
+  } else {
+    const int c4 = t & 7, kw = t >> 3;
+#pragma unroll
+    for (int q = 0; q < SMM_NV; ++q) {
+      const int k = kw + q * (SMM_THREADS / 8);
+      if (k < kc) *reinterpret_cast<float4*>(dst + k * SMM_P + c4 * 4) = v[q];
+    }
+  }
+}
+
+template <bool kAK, bool kBK>
+__global__ void __launch_bounds__(SMM_THREADS) smm_kernel(WcSmm p, SmmExtra ex) {
+  extern __shared__ __align__(16) float smm_sm[];
+  float* As = smm_sm;                       // [k][SMM_P]
+  float* Bs = smm_sm + SMM_KC * SMM_P;      // [k][SMM_P]
+  const int z = blockIdx.z, b1 = z / p.nb2, b2 = z % p.nb2;
+  const float* A = p.A + b1 * p.bA1 + b2 * p.bA2;
+  const float* B = p.B + b1 * p.bB1 + b2 * p.bB2;
+  float* C = p.C + b1 * p.bC1 + b2 * p.bC2;
+  const int i0 = blockIdx.y * SMM_T, j0 = blockIdx.x * SMM_T;
+  const int t = threadIdx.x, kg = t >> 7, tt = t & 127, tx = tt & 15, ty = tt >> 4;
+  const long long lda = kAK ? p.rsA : p.csA, ldb = kBK ? p.csB : p.rsB;
+  float acc[4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = 0.f;
+  const int nkc = (p.K + SMM_KC - 1) / SMM_KC;
+  for (int it = 0; it < p.nsum * nkc; ++it) {
+    const int q = it / nkc, k0 = (it % nkc) * SMM_KC;
+    const int kc = min(SMM_KC, p.K - k0);
+    const float* Aq = A + (long long)q * p.sA + (kAK ? (long long)i0 * lda + k0 : (long long)k0 * lda + i0);
+    const float* Bq = B + (long long)q * p.sB + (kBK ? (long long)j0 * ldb + k0 : (long long)k0 * ldb + j0);
+    float4 va[SMM_NV], vb[SMM_NV];
+    smm_load_panel<kAK>(Aq, lda, kc, va, t);
+    smm_load_panel<kBK>(Bq, ldb, kc, vb, t);
+    if (it) __syncthreads();
+    smm_store_panel<kAK>(va, kc, As, t);
+    smm_store_panel<kBK>(vb, kc, Bs, t);
+    __syncthreads();
+    // k-group kg takes every 4th k (kc is a multiple of 4)
+#pragma unroll 8
+    for (int kk = kg; kk < kc; kk += SMM_KG) {
+      const float4 a = *reinterpret_cast<const float4*>(As + kk * SMM_P + 4 * ty);
+      const float2 b = *reinterpret_cast<const float2*>(Bs + kk * SMM_P + 2 * tx);
+      acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+      acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+      acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]);
+      acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]);
+    }
+  }
+  // reduce the k-groups through shared memory (As is free after the barrier)
+  __syncthreads();
+  float* red = smm_sm;                      // [SMM_KG - 1][8][128]
+  if (kg > 0) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) red[((kg - 1) * 8 + a * 2 + b) * 128 + tt] = acc[a][b];
+  }
+  __syncthreads();
+  if (kg > 0) return;
+#pragma unroll
+  for (int g2 = 0; g2 < SMM_KG - 1; ++g2)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) acc[a][b] += red[(g2 * 8 + a * 2 + b) * 128 + tt];
+  float alpha = p.alpha;
+  if (ex.count_mode) {
+    float cnt = ex.count_dev ? ex.count_dev[0] : ex.count_host;
+    alpha /= (ex.count_mode == 1 ? cnt : (cnt - 1.f));
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int i = i0 + ty * 4 + a, j = j0 + tx * 2 + b;
+      float* cp = C + (long long)i * p.rsC + (long long)j * p.csC;
+      float v = alpha * acc[a][b];
+      if (i == j) v *= ex.diag_scale;
+      if ((p.tri == 1 && j > i) || (p.tri == 2 && j < i)) v = 0.f;
+      else if (p.beta != 0.f) v += p.beta * (*cp);
+      *cp = v;
+    }
+}
+
+// ---- generic path: any shape, any strides ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) smm_generic_kernel(WcSmm p, SmmExtra ex) {
   __shared__ float As[32][33];
   __shared__ float Bs[32][33];
   const int z = blockIdx.z, b1 = z / p.nb2, b2 = z % p.nb2;
@@ -83,12 +212,38 @@ __global__ void __launch_bounds__(256) smm_kernel(WcSmm p, SmmExtra ex) {
     }
 }
 
+
+template <bool kAK, bool kBK>
+int smm_fast_launch(const WcSmm& p, const SmmExtra& ex, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    WC_CUDA(cudaFuncSetAttribute(smm_kernel<kAK, kBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMM_SMEM));
+    attr_set = true;
+  }
+  smm_kernel<kAK, kBK><<<grid, SMM_THREADS, SMM_SMEM, st>>>(p, ex);
+  WC_CHECK_LAUNCH();
+  return 0;
+}
+
+inline bool mult4(long long v) { return (v & 3) == 0; }
+
 int smm(const WcSmm& p, cudaStream_t st, const float* count_dev = nullptr, float count_host = 0.f,
         int count_mode = 0, float diag_scale = 1.f) {
   if (p.M <= 0 || p.N <= 0 || p.nb1 <= 0 || p.nb2 <= 0) return 0;
-  dim3 grid(wc_cdiv(p.N, 32), wc_cdiv(p.M, 32), p.nb1 * p.nb2);
   SmmExtra ex{count_dev, count_host, count_mode, diag_scale};
-  smm_kernel<<<grid, 256, 0, st>>>(p, ex);
+  const bool ak = p.csA == 1, bk = p.rsB == 1;       // k is the contiguous index of the operand
+  const bool ai = p.rsA == 1, bj = p.csB == 1;
+  const long long lda = ak ? p.rsA : p.csA, ldb = bk ? p.csB : p.rsB;
+  const bool fast = (p.M % SMM_T == 0) && (p.N % SMM_T == 0) && (p.K % 4 == 0) && (ak || ai) && (bk || bj) &&
+                    mult4(lda) && mult4(ldb) && wc_aligned16(p.A) && wc_aligned16(p.B) &&
+                    mult4(p.bA1) && mult4(p.bA2) && mult4(p.bB1) && mult4(p.bB2) && mult4(p.sA) && mult4(p.sB);
+  if (fast) {
+    dim3 grid(p.N / SMM_T, p.M / SMM_T, p.nb1 * p.nb2);
+    if (ak) return bk ? smm_fast_launch<true, true>(p, ex, grid, st) : smm_fast_launch<true, false>(p, ex, grid, st);
+    return bk ? smm_fast_launch<false, true>(p, ex, grid, st) : smm_fast_launch<false, false>(p, ex, grid, st);
+  }
+  dim3 grid(wc_cdiv(p.N, 32), wc_cdiv(p.M, 32), p.nb1 * p.nb2);
+  smm_generic_kernel<<<grid, 256, 0, st>>>(p, ex);
   WC_CHECK_LAUNCH();
   return 0;
 }
@@ -370,7 +525,7 @@ int factor_matrix(const float* Ashr, int C, int g, int decomposition, float* Wm,
                   float* L /*scratch or output*/, float* Bm, float* Us, float* Xpad, int32_t* info, cudaStream_t st) {
   const int G = C / g;
   long long total = (long long)C * g;
-  if (decomposition == WC_DECOMP_CHOLESKY) return wc_chol_inv_launch(Ashr, C, g, sqrt_out, Wm, Xpad, info, st);
+  if (decomposition == WC_DECOMP_CHOLESKY) return wc_chol_inv_launch(Ashr, C, g, sqrt_out ? sqrt_out : L, Wm, Xpad, info, st);
   int rcc = wc_chol_inv_launch(Ashr, C, g, L, nullptr, Xpad, info, st);
   if (rcc) return rcc;
   jacobi_kernel<<<G, 1024, 0, st>>>(L, g, Bm, U, lam, info);

@@ -202,7 +202,6 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
         group = dist.group.WORLD
     import wc_gan_b200 as W
-    from wc_gan_b200 import functional as F
     from wc_gan_b200._lib import lib
 
     barrier = (lambda: dist.barrier()) if world > 1 else None
@@ -211,10 +210,36 @@ def run_ours(args):
     stack = build_stack(W, torch, 'd', 'uconv', SHAPE[-1], dev, group=group)
     params = [p for p in stack.parameters()]
 
-    def step(i):
+    def eager_step(i):
         x = xs[i % NBUF].requires_grad_(True)
         y = stack(x)
         return y, torch.autograd.grad(y, [x] + params, dys[i % NBUF])
+
+    # The step is launch-bound on the host (about 25 small launches per layer), so by default it is captured once per
+    # input buffer set in a CUDA graph and replayed; --no-graph times the eager path.  Same kernels, same work.
+    graphs = []
+    if not args.no_graph:
+        for i in range(3):
+            eager_step(i)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(NBUF):
+                eager_step(i)                      # warm the capture stream's workspaces
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for i in range(NBUF):
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=side):
+                out = eager_step(i)
+            graphs.append((gph, out))
+
+    def step(i):
+        if graphs:
+            graphs[i % NBUF][0].replay()
+            return graphs[i % NBUF][1]
+        return eager_step(i)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -225,6 +250,8 @@ def run_ours(args):
     l1 = lib.wc_launch_count()
     ms, t0, t1 = time_steps(torch, step, args.steps, 0, barrier)
     launches = lib.wc_launch_count() - l1
+    if graphs:   # replays do not pass through the library's counter: count one eager step
+        lc = lib.wc_launch_count(); eager_step(0); launches = (lib.wc_launch_count() - lc) * args.steps
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -234,13 +261,9 @@ def run_ours(args):
     value = world * alg_bytes(SHAPE) / (per_step * 1e-3) / 1e9
     hbm, peak_src = peaks()
 
-    # ---- per-stage device time (CUDA events around every C-ABI call, on the launching stream)
-    F.PROFILE = {}
-    for i in range(min(args.steps, 20)):
-        step(i)
-    torch.cuda.synchronize()
-    stages = {k: statistics.mean(s.elapsed_time(e) for s, e in v) for k, v in F.PROFILE.items()}
-    F.PROFILE = None
+    # ---- per-stage device time: the four M x C stages launched standalone through the fine-grained C ABI on the
+    #      same rotating buffers, CUDA events on the launching stream around `n` back-to-back launches
+    stages = stage_times(torch, lib, xs, dys, min(max(args.steps, 10), 50))
     M, C = SHAPE[0] * SHAPE[1] * SHAPE[2], SHAPE[3]
     stage_bytes = {'wc_stats_fwd': 4 * M * C, 'wc_apply_fwd': 8 * M * C, 'wc_reduce_bwd': 8 * M * C, 'wc_apply_bwd': 12 * M * C}
     dom = max(stage_bytes, key=lambda k: stages.get(k, 0.0))
@@ -263,7 +286,7 @@ def run_ours(args):
                'data': 'synthetic', 'config': workload_config(world), 'roofline': roofline,
                'hbm_frac_fwd_bwd': value / world / hbm, 'hbm_frac_fwd_bwd_single_touch': value / world / hbm / 2,
                'stages_ms': stages, 'gpu_launches': int(launches), 'clocks': clocks,
-               'path': int(lib.wc_path_for(M, C, C, C))}
+               'path': int(lib.wc_path_for(M, C, C, C)), 'cuda_graph': bool(graphs)}
 
     # ---- end to end through the public module with HOST buffers (H2D + D2H inside the timed region)
     xh = [x.cpu().pin_memory() for x in xs[:2]]
@@ -314,6 +337,47 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def stage_times(torch, lib, xs, dys, n):
+    """ms per launch of K1 (wc_stats_fwd), K3 (wc_apply_fwd), K4 (wc_reduce_bwd), K6 (wc_apply_bwd) at the bench shape.
+    Each stage includes its helper launches (memset, finalize).  Operand values do not matter for the timing."""
+    from wc_gan_b200._lib import ptr
+    N, H, Wd, C = SHAPE
+    HW, M = H * Wd, N * H * Wd
+    dev = xs[0].device
+    st = torch.cuda.current_stream().cuda_stream
+    f = lambda *sh: torch.zeros(sh, dtype=torch.float32, device=dev)
+    mean, S, T, b, A, cvec = f(C), f(C, C), torch.randn(C, C, device=dev) / 16, f(C), torch.randn(C, C, device=dev) / 16, f(C)
+    nb = lib.wc_stats_workspace_bytes(M, C, C)
+    ws = f(nb // 4 + 4)
+    Ps = f(C * C + C)
+    y = torch.empty_like(xs[0])
+    Tp, TAp = f(lib.wc_pack_bytes(C, 1, 0) // 4), f(lib.wc_pack_bytes(C, 1, 1) // 4)
+    assert lib.wc_pack_fwd(ptr(T), C, 1, ptr(Tp), st) == 0 and lib.wc_pack_bwd(ptr(T), ptr(A), C, C, 1, ptr(TAp), st) == 0
+    nbuf = len(xs)
+    fns = {
+        'wc_stats_fwd': lambda i: lib.wc_stats_fwd(ptr(xs[i % nbuf]), M, C, C, ptr(ws), nb, ptr(mean), ptr(S), st),
+        'wc_apply_fwd': lambda i: lib.wc_apply_fwd(ptr(xs[i % nbuf]), N, HW, C, C, ptr(mean), ptr(T), ptr(Tp), ptr(b), None, 1, 0,
+                                                   ptr(y), None, st),
+        'wc_reduce_bwd': lambda i: lib.wc_reduce_bwd(ptr(xs[i % nbuf]), ptr(dys[i % nbuf]), N, HW, C, C, ptr(mean), None, 1,
+                                                     ptr(Ps), ptr(Ps[C * C:]), None, 0, st),
+        'wc_apply_bwd': lambda i: lib.wc_apply_bwd(ptr(xs[i % nbuf]), ptr(dys[i % nbuf]), N, HW, C, C, ptr(mean), ptr(T), ptr(A),
+                                                   ptr(TAp), ptr(cvec), C, None, 1, ptr(y), st),
+    }
+    out = {}
+    for name, fn in fns.items():
+        for i in range(3):
+            assert fn(i) == 0, name
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) / n
+    return out
+
+
 def sweep(torch, W, dev, hbm):
     """cfg1 / cfg2 / cfg3 variants: ms per fwd+bwd, effective GB/s on 32*M*C, fraction of the HBM peak."""
     cases = [
@@ -357,6 +421,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-sweep', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-graph', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == 'reference':

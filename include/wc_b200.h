@@ -177,6 +177,58 @@ int wc_apply_bwd(const float* x, const float* dy, int N, int HW, int Cin, int Co
                  const float* cvec, int g,
                  const int32_t* cls, int K, float* dx, wc_stream_t stream);
 
+
+/* ---- whole-layer calls ------------------------------------------------------------------------------
+ * One call per direction enqueues every stage above (K1, K2, K2b, pack, K3 | K4, K5a, K5b, pack, K6) on
+ * `stream`: what DecorelationNormalization.call + the coloring layer's call (gan/conditional_layers.py:646-712,
+ * :790-848, :971-1034, generator.py:41-88) and TF's autodiff of them do per training step.  The host fills one
+ * WcLayerCall; the library carves `saved` (written by forward, read by backward) and `workspace` (scratch of the
+ * running call) itself.  Synchronised-batch whitening splits each direction in two phases around the host's
+ * collective (WC_PHASE_*); a single GPU runs both phases in one call.                                      */
+#define WC_PHASE_STATS   1   /* forward: K1 -> shard record {mean[C], S[G g g], count} at saved + layout.rec       */
+#define WC_PHASE_APPLY   2   /* forward: K2, K2b, pack, K3 (statistics from the record or from mean_ext / S_ext)     */
+#define WC_PHASE_REDUCE  1   /* backward: K4, K5a -> parameter gradients and red = {dWeff (G,g,g), gbar[Cin]}         */
+#define WC_PHASE_DX      2   /* backward: K5b, pack, K6 -> dx                                                        */
+
+typedef struct WcLayerCall {
+  /* shapes and switches */
+  int32_t N, HW, Cin, Cout, g, K, E;
+  int32_t whiten, decomposition, renorm, training, triangular;
+  int32_t phases, use_tensor_cores;
+  float eps, momentum;
+  double count;                 /* rows of the global batch; count_dev[0] overrides it when non-NULL */
+  const float* count_dev;
+  /* parameters and state (any may be NULL) */
+  const float *Wu, *bu, *Wc, *bc, *class_matrix, *D, *bf;
+  float *moving_mean, *moving_cov;
+  const int32_t* cls;
+  int32_t* info;
+  /* forward */
+  const float* x;
+  float* y;
+  const float *mean_ext, *S_ext;   /* merged statistics (synchronised batch); NULL: use this shard's record */
+  /* backward */
+  const float* dy;
+  float* dx;                       /* NULL: no input gradient wanted */
+  float *dWu, *dbu, *dWc, *dbc, *dclass_matrix, *dD, *dbf;
+  float* red;                      /* (G g g + Cin) floats, all-reduced by the host between the backward phases */
+  /* caller-owned memory */
+  void* saved;     size_t saved_bytes;
+  void* workspace; size_t workspace_bytes;
+} WcLayerCall;
+
+/* byte offsets into `saved` ((size_t)-1 when the piece does not exist for this configuration) */
+typedef struct WcSavedLayout {
+  size_t rec, mean, S, rec_count;   /* shard record: mean | S | count, contiguous from `rec` */
+  size_t Weff, Wm, R, U, lam, Wk, T, b, ehat, Tp_fwd, Tp_bwd, A, cvec, total;
+} WcSavedLayout;
+
+int wc_layer_saved_layout(const WcLayerCall* c, WcSavedLayout* out);
+size_t wc_layer_saved_bytes(const WcLayerCall* c);
+size_t wc_layer_workspace_bytes(const WcLayerCall* c, int backward);
+int wc_layer_fwd(const WcLayerCall* c, wc_stream_t stream);
+int wc_layer_bwd(const WcLayerCall* c, wc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,5 @@
-"""Host-side control flow of the autograd.Function with the kernel launches stubbed out: which C-ABI stages are
-enqueued, in which order, for each create_norm variant.  Runs on CPU so that Python-level mistakes are caught
+"""Host-side control flow of the autograd.Function with the kernel launches stubbed out: which C-ABI calls are
+enqueued, with which WcLayerCall contents, for each create_norm variant.  Runs on CPU so that Python-level mistakes are caught
 before a GPU run; no arithmetic happens here (outputs are uninitialised)."""
 import pytest
 import torch
@@ -9,7 +9,7 @@ import torch
 def stubbed(monkeypatch):
     from wc_gan_b200 import functional as F
     calls = []
-    monkeypatch.setattr(F, '_call', lambda name, *a: calls.append(name))
+    monkeypatch.setattr(F, '_call', lambda name, *a: calls.append((name, a)))
     monkeypatch.setattr(F, '_need_cuda', lambda t, name: None)
     monkeypatch.setattr(F, '_stream', lambda: 0)
     return calls
@@ -26,22 +26,28 @@ def test_stage_sequence(stubbed, norm, after_norm, c):
     stack.train()
     y = stack(x, cls)
     assert y.shape == x.shape
-    fwd = list(stubbed)
-    tc = c == 128
-    expect = (['wc_stats_fwd', 'wc_factor_fwd'] if norm != 'n' else []) + ['wc_compose_fwd'] + (['wc_pack_fwd'] if tc else []) + ['wc_apply_fwd']
-    assert fwd == expect
+    assert [n for n, _ in stubbed] == ['wc_layer_fwd']            # one foreign call per direction
+    call = stubbed[0][1][0]._obj
+    assert call.phases == 3 and call.training == 1
+    assert call.whiten == (norm != 'n') and call.renorm == (norm == 'dr')
+    assert call.K == (3 if after_norm in ('cconv', 'ucconv', 'fconv', 'ufconv') else 1)
+    assert bool(call.Wu) == (after_norm in ('uconv', 'ucconv', 'ufconv'))
+    assert bool(call.Wc) == (after_norm in ('cconv', 'ucconv')) and bool(call.D) == (after_norm in ('fconv', 'ufconv'))
+    assert call.saved_bytes >= 4 * c * c and bool(call.y) and bool(call.x)
     del stubbed[:]
     y.backward(torch.zeros_like(y))
-    bwd = list(stubbed)
-    expect = ['wc_reduce_bwd', 'wc_color_bwd'] + (['wc_factor_bwd'] if norm != 'n' else []) + (['wc_pack_bwd'] if tc else []) + ['wc_apply_bwd']
-    assert bwd == expect
+    assert [n for n, _ in stubbed] == ['wc_layer_bwd']
+    call = stubbed[0][1][0]._obj
+    assert call.phases == 3 and bool(call.dx) and bool(call.dy)
+    assert bool(call.red) == (norm != 'n')                       # the whitening adjoint only exists in the training phase
+    assert bool(call.dWu) == (after_norm in ('uconv', 'ucconv', 'ufconv'))
     # inference phase: no statistics, no factorisation adjoint
     del stubbed[:]
     stack.eval()
     y = stack(x, cls)
     y.backward(torch.zeros_like(y))
-    assert 'wc_stats_fwd' not in stubbed and 'wc_factor_bwd' not in stubbed
-    assert ('wc_factor_fwd' in stubbed) == (norm != 'n')
+    assert [n for n, _ in stubbed] == ['wc_layer_fwd', 'wc_layer_bwd']
+    assert stubbed[0][1][0]._obj.training == 0 and not stubbed[1][1][0]._obj.red
 
 
 def test_label_validation(stubbed):

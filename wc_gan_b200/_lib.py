@@ -33,6 +33,23 @@ def _load() -> ctypes.CDLL:
 
 lib = _load()
 
+
+class WcLayerCall(ctypes.Structure):
+    """include/wc_b200.h: struct WcLayerCall (field order and types must match)."""
+    _fields_ = ([(n, c_int32) for n in ('N', 'HW', 'Cin', 'Cout', 'g', 'K', 'E', 'whiten', 'decomposition', 'renorm',
+                                        'training', 'triangular', 'phases', 'use_tensor_cores')] +
+                [('eps', c_float), ('momentum', c_float), ('count', c_double)] +
+                [(n, c_void_p) for n in ('count_dev', 'Wu', 'bu', 'Wc', 'bc', 'class_matrix', 'D', 'bf', 'moving_mean',
+                                         'moving_cov', 'cls', 'info', 'x', 'y', 'mean_ext', 'S_ext', 'dy', 'dx', 'dWu',
+                                         'dbu', 'dWc', 'dbc', 'dclass_matrix', 'dD', 'dbf', 'red')] +
+                [('saved', c_void_p), ('saved_bytes', c_size_t), ('workspace', c_void_p), ('workspace_bytes', c_size_t)])
+
+
+class WcSavedLayout(ctypes.Structure):
+    _fields_ = [(n, c_size_t) for n in ('rec', 'mean', 'S', 'rec_count', 'Weff', 'Wm', 'R', 'U', 'lam', 'Wk', 'T', 'b',
+                                        'ehat', 'Tp_fwd', 'Tp_bwd', 'A', 'cvec', 'total')]
+
+
 _P = c_void_p
 _SIGS = {
     'wc_version': (c_int, []),
@@ -60,6 +77,11 @@ _SIGS = {
     'wc_factor_bwd': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_double, c_int, c_int, c_float, c_int, c_int,
                               _P, _P, _P, c_size_t, _P]),
     'wc_apply_bwd': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, c_int, _P, _P]),
+    'wc_layer_saved_layout': (c_int, [ctypes.POINTER(WcLayerCall), ctypes.POINTER(WcSavedLayout)]),
+    'wc_layer_saved_bytes': (c_size_t, [ctypes.POINTER(WcLayerCall)]),
+    'wc_layer_workspace_bytes': (c_size_t, [ctypes.POINTER(WcLayerCall), c_int]),
+    'wc_layer_fwd': (c_int, [ctypes.POINTER(WcLayerCall), _P]),
+    'wc_layer_bwd': (c_int, [ctypes.POINTER(WcLayerCall), _P]),
 }
 for _name, (_res, _args) in _SIGS.items():
     _fn = getattr(lib, _name)

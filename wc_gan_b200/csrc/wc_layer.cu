@@ -1,0 +1,202 @@
+// Whole-layer entry points: one C call per direction sequences the stages of the WC layer on the caller's stream.
+// Replaces, per training step, DecorelationNormalization.call + the coloring layer's call
+// (gan/conditional_layers.py:646-712, :790-848, :971-1034; generator.py:41-88) and TF's autodiff through them.
+// The stage functions are the ones exported individually in include/wc_b200.h; this file only carves the caller's
+// `saved` / `workspace` blocks and calls them in order, so the host pays for one foreign call, not ten.
+#include "wc_common.cuh"
+
+namespace {
+
+constexpr size_t NONE = (size_t)-1;
+
+struct Carver {
+  size_t off = 0;
+  size_t take(size_t bytes) { size_t o = off; off += wc_align_up(bytes, 256); return o; }
+};
+
+inline bool conditional(const WcLayerCall& c) { return c.K > 1 && c.cls != nullptr; }
+inline bool has_coloring(const WcLayerCall& c) { return c.Wu || c.Wc || c.D; }
+inline bool use_tc(const WcLayerCall& c) {
+  return c.use_tensor_cores && (wc_path_for((int64_t)c.N * c.HW, c.Cin, c.Cout, c.g) & 1);
+}
+
+int check(const WcLayerCall* c) {
+  if (!c) return WC_E_ARG;
+  if (c->N <= 0 || c->HW <= 0 || c->Cin <= 0 || c->Cout <= 0 || c->K <= 0 || c->E < 0) return WC_E_ARG;
+  if (c->whiten && (c->g <= 0 || c->Cin % c->g)) return WC_E_ARG;
+  if (c->class_matrix && (!c->D || c->E <= 0)) return WC_E_ARG;
+  if (!has_coloring(*c) && c->Cin != c->Cout) return WC_E_ARG;
+  return 0;
+}
+
+void layout(const WcLayerCall& c, WcSavedLayout& L) {
+  Carver cv;
+  const size_t f = sizeof(float);
+  const size_t gg = c.whiten ? (size_t)c.Cin * c.g : 0;
+  const size_t kcc = (size_t)c.K * c.Cin * c.Cout;
+  const bool train_w = c.whiten && c.training;
+  L.rec = L.mean = L.S = L.rec_count = L.Weff = L.Wm = L.R = L.U = L.lam = L.Wk = L.T = L.b = L.ehat = L.Tp_fwd = L.Tp_bwd =
+      L.A = L.cvec = NONE;
+  if (train_w) {
+    L.rec = cv.take(((size_t)c.Cin + gg + 1) * f);
+    L.mean = L.rec; L.S = L.rec + (size_t)c.Cin * f; L.rec_count = L.S + gg * f;
+  }
+  if (c.whiten) {
+    L.Weff = cv.take(gg * f);
+    L.Wm = (train_w && c.renorm) ? cv.take(gg * f) : L.Weff;
+    if (train_w && c.renorm) L.R = cv.take(gg * f);
+    if (c.decomposition == WC_DECOMP_ZCA) { L.U = cv.take(gg * f); L.lam = cv.take((size_t)c.Cin * f); }
+  }
+  L.Wk = cv.take(kcc * f);
+  L.T = c.whiten ? cv.take(kcc * f) : L.Wk;
+  if (c.bu || c.bc || c.bf) L.b = cv.take((size_t)c.K * c.Cout * f);
+  if (c.class_matrix) L.ehat = cv.take((size_t)c.K * c.E * f);
+  if (use_tc(c)) {
+    L.Tp_fwd = cv.take(wc_pack_bytes(c.Cin, c.K, 0));
+    L.Tp_bwd = cv.take(wc_pack_bytes(c.Cin, c.K, 1));
+  }
+  if (train_w) { L.A = cv.take(gg * f); L.cvec = cv.take((size_t)c.Cin * f); }
+  L.total = cv.off;
+}
+
+struct FwdWs { size_t stats, stats_bytes, factor, factor_bytes, total; };
+FwdWs fwd_ws(const WcLayerCall& c) {
+  Carver cv; FwdWs w{};
+  if (c.whiten && c.training) { w.stats_bytes = wc_stats_workspace_bytes((int64_t)c.N * c.HW, c.Cin, c.g); w.stats = cv.take(w.stats_bytes); }
+  if (c.whiten) { w.factor_bytes = wc_factor_workspace_bytes(c.Cin, c.g, c.decomposition, c.renorm && c.training); w.factor = cv.take(w.factor_bytes); }
+  w.total = cv.off ? cv.off : 256;
+  return w;
+}
+struct BwdWs { size_t Ps, reduce, reduce_bytes, color, color_bytes, factor, factor_bytes, total; };
+BwdWs bwd_ws(const WcLayerCall& c) {
+  Carver cv; BwdWs w{};
+  w.Ps = cv.take(((size_t)c.K * c.Cin * c.Cout + (size_t)c.K * c.Cout) * sizeof(float));   // P | s contiguous: one memset
+  w.reduce_bytes = wc_reduce_workspace_bytes(c.N, c.HW, c.Cin, c.Cout, c.K); w.reduce = cv.take(w.reduce_bytes);
+  w.color_bytes = wc_color_bwd_workspace_bytes(c.Cin, c.Cout, c.g > 0 ? c.g : c.Cin, c.K, c.E); w.color = cv.take(w.color_bytes);
+  if (c.whiten && c.training) { w.factor_bytes = wc_factor_bwd_workspace_bytes(c.Cin, c.g, c.decomposition, c.renorm); w.factor = cv.take(w.factor_bytes); }
+  w.total = cv.off;
+  return w;
+}
+
+template <typename T> inline T* at(void* base, size_t off) { return off == NONE ? nullptr : reinterpret_cast<T*>(reinterpret_cast<char*>(base) + off); }
+
+}  // namespace
+
+extern "C" int wc_layer_saved_layout(const WcLayerCall* c, WcSavedLayout* out) {
+  int rc = check(c);
+  if (rc || !out) return rc ? rc : WC_E_ARG;
+  layout(*c, *out);
+  return 0;
+}
+extern "C" size_t wc_layer_saved_bytes(const WcLayerCall* c) {
+  if (check(c)) return 0;
+  WcSavedLayout L; layout(*c, L);
+  return L.total;
+}
+extern "C" size_t wc_layer_workspace_bytes(const WcLayerCall* c, int backward) {
+  if (check(c)) return 0;
+  return backward ? bwd_ws(*c).total : fwd_ws(*c).total;
+}
+
+extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
+  int rc = check(cp);
+  if (rc) return rc;
+  const WcLayerCall& c = *cp;
+  if (!c.x || !c.saved) return WC_E_ARG;
+  WcSavedLayout L; layout(c, L);
+  if (c.saved_bytes < L.total) return WC_E_WORKSPACE;
+  FwdWs W = fwd_ws(c);
+  if ((c.whiten) && (!c.workspace || c.workspace_bytes < W.total)) return WC_E_WORKSPACE;
+  if (!wc_aligned16(c.saved) || (c.workspace && !wc_aligned16(c.workspace))) return WC_E_ALIGN;
+  const int64_t M = (int64_t)c.N * c.HW;
+  const bool train_w = c.whiten && c.training;
+  if (c.whiten && (!c.moving_mean || !c.moving_cov)) return WC_E_ARG;
+
+  if ((c.phases & WC_PHASE_STATS) && train_w) {
+    rc = wc_stats_fwd(c.x, M, c.Cin, c.g, at<float>(c.workspace, W.stats), W.stats_bytes, at<float>(c.saved, L.mean),
+                      at<float>(c.saved, L.S), stream);
+    if (rc) return rc;
+  }
+  if (!(c.phases & WC_PHASE_APPLY)) return 0;
+  if (!c.y) return WC_E_ARG;
+  const float* mean = nullptr;
+  if (c.whiten) {
+    const float* S = nullptr;
+    if (train_w) {
+      mean = c.mean_ext ? c.mean_ext : at<float>(c.saved, L.mean);
+      S = c.S_ext ? c.S_ext : at<float>(c.saved, L.S);
+      if (c.mean_ext)   // keep the statistics the layer actually used where backward looks for them
+        WC_CUDA(cudaMemcpyAsync(at<float>(c.saved, L.mean), c.mean_ext, (size_t)c.Cin * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+      mean = at<float>(c.saved, L.mean);
+    } else {
+      mean = c.moving_mean;
+    }
+    rc = wc_factor_fwd(train_w ? mean : nullptr, S, c.count_dev, c.count, c.Cin, c.g, c.eps, c.momentum, c.decomposition,
+                       c.renorm, c.training, c.moving_mean, c.moving_cov, at<float>(c.saved, L.Weff),
+                       at<float>(c.saved, train_w ? L.Wm : L.Weff), at<float>(c.saved, L.R), at<float>(c.saved, L.U),
+                       at<float>(c.saved, L.lam), c.info, at<float>(c.workspace, W.factor), W.factor_bytes, stream);
+    if (rc) return rc;
+  }
+  // identity coloring (after_norm == 'n', generator.py:79-80): W_k = I is written by the compose kernel from Wu == NULL
+  rc = wc_compose_fwd(at<float>(c.saved, L.Weff), c.Cin, c.Cout, c.whiten ? c.g : c.Cin, c.K, c.Wu, c.bu, c.Wc, c.bc,
+                      c.triangular, c.class_matrix, c.D, c.E, c.bf, at<float>(c.saved, L.ehat), at<float>(c.saved, L.Wk),
+                      at<float>(c.saved, L.T), at<float>(c.saved, L.b), stream);
+  if (rc) return rc;
+  void* Tp = at<void>(c.saved, L.Tp_fwd);
+  if (Tp) {
+    rc = wc_pack_fwd(at<float>(c.saved, L.T), c.Cin, c.K, Tp, stream);
+    if (rc) return rc;
+    rc = wc_pack_bwd(at<float>(c.saved, L.T), nullptr, c.Cin, c.whiten ? c.g : c.Cin, c.K, at<void>(c.saved, L.Tp_bwd), stream);
+    if (rc) return rc;
+  }
+  const int band = (c.whiten && !has_coloring(c) && c.g < c.Cin) ? c.g : 0;
+  return wc_apply_fwd(c.x, c.N, c.HW, c.Cin, c.Cout, mean, at<float>(c.saved, L.T), Tp, at<float>(c.saved, L.b),
+                      conditional(c) ? c.cls : nullptr, c.K, band, c.y, c.info, stream);
+}
+
+extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
+  int rc = check(cp);
+  if (rc) return rc;
+  const WcLayerCall& c = *cp;
+  if (!c.x || !c.dy || !c.saved || !c.workspace) return WC_E_ARG;
+  WcSavedLayout L; layout(c, L);
+  if (c.saved_bytes < L.total) return WC_E_WORKSPACE;
+  BwdWs W = bwd_ws(c);
+  if (c.workspace_bytes < W.total) return WC_E_WORKSPACE;
+  if (!wc_aligned16(c.saved) || !wc_aligned16(c.workspace)) return WC_E_ALIGN;
+  const bool train_w = c.whiten && c.training;
+  const bool stats_grad = train_w && c.dx != nullptr;
+  if (stats_grad && !c.red) return WC_E_ARG;
+  const int g = c.whiten ? c.g : c.Cin;
+  const size_t gg = (size_t)c.Cin * g;
+  const float* mean = c.whiten ? (train_w ? at<float>(c.saved, L.mean) : c.moving_mean) : nullptr;
+  const int32_t* cls = conditional(c) ? c.cls : nullptr;
+  float* P = at<float>(c.workspace, W.Ps);
+  float* s = P + (size_t)c.K * c.Cin * c.Cout;
+
+  if (c.phases & WC_PHASE_REDUCE) {
+    rc = wc_reduce_bwd(c.x, c.dy, c.N, c.HW, c.Cin, c.Cout, mean, cls, c.K, P, s, at<float>(c.workspace, W.reduce),
+                       W.reduce_bytes, stream);
+    if (rc) return rc;
+    rc = wc_color_bwd(P, s, at<float>(c.saved, L.Weff), at<float>(c.saved, L.Wk), c.Cin, c.Cout, g, c.K, c.dWu, c.dbu, c.dWc,
+                      c.dbc, c.triangular, c.class_matrix, at<float>(c.saved, L.ehat), c.D, c.E, c.dD, c.dclass_matrix, c.dbf,
+                      stats_grad ? c.red : nullptr, stats_grad ? c.red + gg : nullptr, at<float>(c.workspace, W.color),
+                      W.color_bytes, stream);
+    if (rc) return rc;
+  }
+  if (!(c.phases & WC_PHASE_DX) || !c.dx) return 0;
+  float *A = nullptr, *cvec = nullptr;
+  if (stats_grad) {
+    A = at<float>(c.saved, L.A); cvec = at<float>(c.saved, L.cvec);
+    rc = wc_factor_bwd(c.red, c.red + gg, at<float>(c.saved, L.Weff), at<float>(c.saved, L.Wm), at<float>(c.saved, L.R),
+                       at<float>(c.saved, L.U), at<float>(c.saved, L.lam), c.count_dev, c.count, c.Cin, g, c.eps, c.decomposition,
+                       c.renorm, A, cvec, at<float>(c.workspace, W.factor), W.factor_bytes, stream);
+    if (rc) return rc;
+  }
+  void* Tp = at<void>(c.saved, L.Tp_bwd);
+  if (Tp && A) {
+    rc = wc_pack_bwd(nullptr, A, c.Cin, g, c.K, Tp, stream);     // T's image was packed in forward; add A's
+    if (rc) return rc;
+  }
+  return wc_apply_bwd(c.x, c.dy, c.N, c.HW, c.Cin, c.Cout, mean, at<float>(c.saved, L.T), A, Tp, cvec, g, cls, c.K, c.dx, stream);
+}

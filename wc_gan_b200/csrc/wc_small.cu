@@ -426,14 +426,14 @@ __global__ void build_wk_kernel(int Cin, int Cout, int K, const float* __restric
                                 const float* __restrict__ Wc, const float* __restrict__ bc, int triangular,
                                 const float* __restrict__ cm, const float* __restrict__ D, int E,
                                 const float* __restrict__ bf, float* __restrict__ ehat, float* __restrict__ Wk,
-                                float* __restrict__ b) {
+                                float* __restrict__ b, int identity) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long per = (long long)Cin * Cout;
   if (idx >= per * K) return;
   int k = (int)(idx / per);
   long long ij = idx % per;
   int i = (int)(ij / Cout), j = (int)(ij % Cout);
-  float w = Wu ? Wu[ij] : 0.f;
+  float w = Wu ? Wu[ij] : ((identity && i == j) ? 1.f : 0.f);   // no coloring at all: W = I (generator.py:79-80)
   if (Wc && !(triangular && j < i)) w += Wc[idx];              // matrix_band_part(kernel, 0, -1): upper triangle
   if (cm) {
     float sq = 0.f;
@@ -618,7 +618,7 @@ extern "C" int wc_compose_fwd(const float* Weff, int Cin, int Cout, int g, int K
   cudaStream_t st = (cudaStream_t)stream;
   long long per = (long long)Cin * Cout;
   build_wk_kernel<<<wc_cdiv(per * K, 256), 256, 0, st>>>(Cin, Cout, K, Wu, bu, Wc, bc, triangular, class_matrix, D, E, bf,
-                                                         ehat, Wk, b);
+                                                         ehat, Wk, b, (!Wu && !Wc && !D) ? 1 : 0);
   WC_CHECK_LAUNCH();
   if (!Weff) {
     if (T != Wk) WC_CUDA(cudaMemcpyAsync(T, Wk, (size_t)per * K * 4, cudaMemcpyDeviceToDevice, st));

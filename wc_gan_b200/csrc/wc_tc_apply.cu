@@ -297,13 +297,15 @@ extern "C" int wc_pack_fwd(const float* T, int C, int K, void* packed, wc_stream
 }
 
 extern "C" int wc_pack_bwd(const float* T, const float* A, int C, int g, int K, void* packed, wc_stream_t stream) {
-  if (!T || !packed || K <= 0) return WC_E_ARG;
+  if ((!T && !A) || !packed || K <= 0) return WC_E_ARG;
   if (!tc_shape_ok(C, C)) return WC_E_UNSUPPORTED;
   if (A && (g <= 0 || C % g)) return WC_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   long long chunks = (long long)K * C * (C / KB) * 4;
-  pack_b_kernel<<<wc_cdiv(chunks, 256), 256, 0, st>>>(T, C, K, (long long)C * C, 1, C, (uint8_t*)packed, (long long)C * C * 4);
-  WC_CHECK_LAUNCH();
+  if (T) {    // T == NULL: T's image is already in place (packed once in forward), only A's is refreshed
+    pack_b_kernel<<<wc_cdiv(chunks, 256), 256, 0, st>>>(T, C, K, (long long)C * C, 1, C, (uint8_t*)packed, (long long)C * C * 4);
+    WC_CHECK_LAUNCH();
+  }
   if (A) {
     chunks = (long long)C * (C / KB) * 4;
     pack_b_kernel<<<wc_cdiv(chunks, 256), 256, 0, st>>>(A, C, 1, 0, 2, g, (uint8_t*)packed + (size_t)K * C * C * 4, 0);

@@ -6,9 +6,15 @@ Replaces the graph that generator.py:82-88 builds out of DecorelationNormalizati
 (gan/conditional_layers.py:646-712) followed by Conv2D 1x1 / ConditionalConv11 (:790-848) /
 FactorizedConv11 (:971-1034) and Add (generator.py:58,76).  PyTorch is plumbing here (device
 memory, streams, autograd graph, torch.distributed); every FLOP runs in libwc_b200.so.
+
+Each direction is ONE foreign call (wc_layer_fwd / wc_layer_bwd, include/wc_b200.h "whole-layer calls"):
+the host fills a WcLayerCall, allocates the output, the `saved` block (what backward needs) and takes a
+cached scratch workspace; the library sequences its kernels on the current stream.  With a process group
+each direction is split in two phases around the collective (wc_gan_b200/sync.py).
 """
 from __future__ import annotations
 
+import ctypes
 from dataclasses import dataclass
 from typing import Optional
 
@@ -16,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib, sync
-from ._lib import check, lib, ptr
+from ._lib import WcLayerCall, WcSavedLayout, check, lib, ptr
 
 
 @dataclass(frozen=True)
@@ -32,12 +38,15 @@ class WCSpec:
     number_of_classes: int = 1
 
 
-# When set to a dict, every C-ABI stage is bracketed by CUDA events on the launching stream:
-#   PROFILE[stage] = [(start_event, end_event), ...]      (bench.py reads the per-stage durations)
+# When set to a dict, every C-ABI call is bracketed by CUDA events on the launching stream:
+#   PROFILE[name] = [(start_event, end_event), ...]
 PROFILE = None
 
 # False forces the FP32 FFMA kernels everywhere (tests compare the two device paths).
 USE_TENSOR_CORES = True
+
+PHASE_STATS, PHASE_APPLY = 1, 2      # forward  (WC_PHASE_*)
+PHASE_REDUCE, PHASE_DX = 1, 2        # backward
 
 
 def _call(name: str, *args) -> None:
@@ -68,22 +77,37 @@ def _f32(*shape, device):
     return torch.empty(shape, dtype=torch.float32, device=device)
 
 
-def _ws(nbytes: int, device):
-    return torch.empty((max(int(nbytes), 16) + 3) // 4, dtype=torch.float32, device=device)
-
-
-_EYES = {}
-
-
-def _eye(c: int, device) -> torch.Tensor:
-    key = (c, str(device))
-    if key not in _EYES:
-        _EYES[key] = torch.eye(c, dtype=torch.float32, device=device)
-    return _EYES[key]
-
-
 def new_info(device) -> torch.Tensor:
     return torch.zeros(_lib.INFO_SLOTS, dtype=torch.int32, device=device)
+
+
+# scratch workspaces: one per (device, stream, direction), grown on demand.  Work on a stream is ordered, so a
+# workspace is never in use by two calls at once.
+_WORKSPACES = {}
+
+
+def _workspace(nbytes: int, device, stream: int, direction: int) -> torch.Tensor:
+    key = (str(device), stream, direction)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() * 4 < nbytes:
+        ws = torch.empty((max(nbytes, 256) + 3) // 4, dtype=torch.float32, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+# (saved_bytes, fwd_ws_bytes, bwd_ws_bytes, layout) per static configuration
+_PLANS = {}
+
+
+def _plan(call: WcLayerCall, key):
+    pl = _PLANS.get(key)
+    if pl is None:
+        lay = WcSavedLayout()
+        check(lib.wc_layer_saved_layout(ctypes.byref(call), ctypes.byref(lay)), 'wc_layer_saved_layout')
+        pl = (int(lay.total), int(lib.wc_layer_workspace_bytes(ctypes.byref(call), 0)),
+              int(lib.wc_layer_workspace_bytes(ctypes.byref(call), 1)), lay)
+        _PLANS[key] = pl
+    return pl
 
 
 class WhiteningColoringFn(torch.autograd.Function):
@@ -125,84 +149,65 @@ class WhiteningColoringFn(torch.autograd.Function):
         world = sync.world_size(group)
         do_sync = spec.whiten and training and world > 1
 
-        mean = Weff = Wm = R = U = lam = count_dev = None
-        count = float(N * HW)
-        if spec.whiten:
-            Weff = _f32(G, g, g, device=dev)
-            if dec == 1:
-                U, lam = _f32(G, g, g, device=dev), _f32(Cin, device=dev)
-            if training:
-                rec = _f32(Cin + G * g * g + 1, device=dev)      # {mean, S, count}: what a shard contributes
-                mean_l, S_l = rec[:Cin], rec[Cin:Cin + G * g * g]
-                nb = lib.wc_stats_workspace_bytes(N * HW, Cin, g)
-                ws = _ws(nb, dev)
-                _call('wc_stats_fwd', ptr(x), N * HW, Cin, g, ptr(ws), nb, ptr(mean_l), ptr(S_l), st)
-                if do_sync:
-                    rec[-1:].fill_(count)
-                    recs = sync.gather_shard_records(rec, group)
-                    mean, S, count_dev = _f32(Cin, device=dev), _f32(G, g, g, device=dev), _f32(1, device=dev)
-                    _call('wc_stats_merge', ptr(recs), world, Cin, g, ptr(mean), ptr(S), ptr(count_dev), st)
-                else:
-                    mean, S = mean_l, S_l
-                Wm = _f32(G, g, g, device=dev)
-                R = _f32(G, g, g, device=dev) if spec.renorm else None
-            else:
-                mean, S = moving_mean.reshape(-1), None
-            nb = lib.wc_factor_workspace_bytes(Cin, g, dec, int(spec.renorm and training))
-            ws = _ws(nb, dev)
-            _call('wc_factor_fwd', ptr(mean) if training else None, ptr(S), ptr(count_dev), count, Cin, g,
-                                    spec.epsilon, spec.momentum, dec, int(spec.renorm), int(training),
-                                    ptr(moving_mean), ptr(moving_cov), ptr(Weff),
-                                    ptr(Wm if training else Weff), ptr(R), ptr(U), ptr(lam),
-                                    ptr(info), ptr(ws), nb, st)
-            if not training:
-                Wm = Weff
+        c = WcLayerCall()
+        c.N, c.HW, c.Cin, c.Cout, c.g, c.K, c.E = N, HW, Cin, Cout, g, K, E
+        c.whiten, c.decomposition, c.renorm = int(spec.whiten), dec, int(spec.renorm)
+        c.training, c.triangular = int(training), int(spec.triangular)
+        c.use_tensor_cores = int(USE_TENSOR_CORES)
+        c.eps, c.momentum = spec.epsilon, spec.momentum
+        c.count = float(N * HW)
+        c.Wu, c.bu, c.Wc, c.bc = ptr(Wu), ptr(bu), ptr(Wc), ptr(bc)
+        c.class_matrix, c.D, c.bf = ptr(class_matrix), ptr(D), ptr(bf)
+        c.moving_mean, c.moving_cov = ptr(moving_mean), ptr(moving_cov)
+        c.cls, c.info = ptr(cls), ptr(info)
+        has = tuple(t is not None for t in (Wu, bu, Wc, bc, class_matrix, D, bf))
+        key = (N, HW, Cin, Cout, g, K, E, c.whiten, dec, c.renorm, c.training, c.triangular, c.use_tensor_cores, has)
+        saved_bytes, fws, bws, lay = _plan(c, key)
 
-        Wu_k = Wu
-        if Wu is None and Wc is None and D is None:       # after_norm == 'n': identity coloring (generator.py:79-80)
-            Wu_k = _eye(Cin, dev)
-        Wk = _f32(K, Cin, Cout, device=dev)
-        T = _f32(K, Cin, Cout, device=dev) if spec.whiten else Wk
-        b = _f32(K, Cout, device=dev) if any(t is not None for t in (bu, bc, bf)) else None
-        ehat = _f32(K, E, device=dev) if class_matrix is not None else None
-        _call('wc_compose_fwd', ptr(Weff), Cin, Cout, g, K, ptr(Wu_k), ptr(bu), ptr(Wc), ptr(bc),
-                                 int(spec.triangular), ptr(class_matrix), ptr(D), E, ptr(bf),
-                                 ptr(ehat), ptr(Wk), ptr(T), ptr(b), st)
+        saved = torch.empty(saved_bytes // 4, dtype=torch.float32, device=dev)
+        ws = _workspace(fws, dev, st, 0)
         y = _f32(N, H, W_, Cout, device=dev)
-        band = g if (spec.whiten and Wu is None and Wc is None and D is None and g < Cin) else 0
-        use_tc = bool(lib.wc_path_for(N * HW, Cin, Cout, g) & 1) and USE_TENSOR_CORES
-        Tp = None
-        if use_tc:
-            Tp = _ws(lib.wc_pack_bytes(Cin, K, 0), dev)
-            _call('wc_pack_fwd', ptr(T), Cin, K, ptr(Tp), st)
-        _call('wc_apply_fwd', ptr(x), N, HW, Cin, Cout, ptr(mean), ptr(T), ptr(Tp), ptr(b), ptr(cls), K, band,
-                               ptr(y), ptr(info), st)
+        c.x, c.y = ptr(x), ptr(y)
+        c.saved, c.saved_bytes = ptr(saved), saved_bytes
+        c.workspace, c.workspace_bytes = ptr(ws), ws.numel() * 4
+        keep = [saved]
+        if do_sync:
+            # phase 1: this shard's record {mean, S, count}; all-gather; Chan merge; phase 2 with the global statistics
+            c.phases = PHASE_STATS
+            _call('wc_layer_fwd', ctypes.byref(c), st)
+            nrec = Cin + G * g * g + 1
+            rec = saved[lay.rec // 4: lay.rec // 4 + nrec]
+            rec[-1:].fill_(c.count)
+            recs = sync.gather_shard_records(rec, group)
+            merged = _f32(nrec, device=dev)     # mean | S | count of the concatenated batch
+            _call('wc_stats_merge', ptr(recs), world, Cin, g, ptr(merged), ptr(merged[Cin:]), ptr(merged[nrec - 1:]), st)
+            c.mean_ext, c.S_ext, c.count_dev = ptr(merged), ptr(merged[Cin:]), ptr(merged[nrec - 1:])
+            keep.append(merged)
+            c.phases = PHASE_APPLY
+            _call('wc_layer_fwd', ctypes.byref(c), st)
+        else:
+            c.phases = PHASE_STATS | PHASE_APPLY
+            _call('wc_layer_fwd', ctypes.byref(c), st)
 
-        ctx.spec, ctx.training, ctx.group, ctx.sync = spec, training, group, do_sync
-        ctx.dims = (N, HW, Cin, Cout, g, K, E, count)
-        ctx.has = tuple(t is not None for t in (Wu, bu, Wc, bc, class_matrix, D, bf))
-        ctx.save_for_backward(x, mean, cls, Weff, Wm, R, U, lam, Wk, T, ehat, count_dev, class_matrix, D)
+        ctx.call, ctx.keep, ctx.group, ctx.sync = c, keep, group, do_sync
+        ctx.dims = (N, H, W_, Cin, Cout, g, K, E, bws)
+        ctx.has = has
+        ctx.stats_train = bool(spec.whiten and training)
+        ctx.save_for_backward(x, cls, Wu, bu, Wc, bc, class_matrix, D, bf, moving_mean)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, mean, cls, Weff, Wm, R, U, lam, Wk, T, ehat, count_dev, class_matrix, D = ctx.saved_tensors
-        spec, training = ctx.spec, ctx.training
-        N, HW, Cin, Cout, g, K, E, count = ctx.dims
+        x = ctx.saved_tensors[0]
+        c: WcLayerCall = ctx.call
+        N, H, W_, Cin, Cout, g, K, E, bws = ctx.dims
         has_Wu, has_bu, has_Wc, has_bc, has_cm, has_D, has_bf = ctx.has
         need = ctx.needs_input_grad
         dev = x.device
         st = _stream()
         _need_cuda(dy, 'grad_output')
         dy = dy.contiguous()
-        dec = _lib.WC_DECOMP[spec.decomposition]
         G = Cin // g
-
-        P, s = _f32(K, Cin, Cout, device=dev), _f32(K, Cout, device=dev)
-        nb = lib.wc_reduce_workspace_bytes(N, HW, Cin, Cout, K)
-        ws = _ws(nb, dev)
-        _call('wc_reduce_bwd', ptr(x), ptr(dy), N, HW, Cin, Cout, ptr(mean), ptr(cls), K, ptr(P), ptr(s),
-                                ptr(ws), nb, st)
 
         dWu = _f32(Cin, Cout, device=dev) if (has_Wu and need[1]) else None
         dbu = _f32(Cout, device=dev) if (has_bu and need[2]) else None
@@ -211,36 +216,25 @@ class WhiteningColoringFn(torch.autograd.Function):
         dcm = _f32(K, E, device=dev) if (has_cm and need[5]) else None
         dD = _f32(E, Cin, Cout, device=dev) if (has_D and need[6]) else None
         dbf = _f32(K, Cout, device=dev) if (has_bf and need[7]) else None
-        stats_grad = spec.whiten and training and need[0]
+        dx = torch.empty_like(x) if need[0] else None
+        stats_grad = ctx.stats_train and need[0]
         red = _f32(G * g * g + Cin, device=dev) if stats_grad else None
-        dWeff = red[:G * g * g] if stats_grad else None
-        gbar = red[G * g * g:] if stats_grad else None
-        nb = lib.wc_color_bwd_workspace_bytes(Cin, Cout, g, K, E)
-        ws = _ws(nb, dev)
-        _call('wc_color_bwd', ptr(P), ptr(s), ptr(Weff), ptr(Wk), Cin, Cout, g, K,
-                               ptr(dWu), ptr(dbu), ptr(dWc), ptr(dbc), int(spec.triangular),
-                               ptr(class_matrix), ptr(ehat), ptr(D), E, ptr(dD), ptr(dcm), ptr(dbf),
-                               ptr(dWeff), ptr(gbar), ptr(ws), nb, st)
-        dx = None
-        if need[0]:
-            A = cvec = None
-            if stats_grad:
-                if ctx.sync:
-                    sync.allreduce_adjoint(red, ctx.group)
-                A, cvec = _f32(G, g, g, device=dev), _f32(Cin, device=dev)
-                nb = lib.wc_factor_bwd_workspace_bytes(Cin, g, dec, int(spec.renorm))
-                ws = _ws(nb, dev)
-                _call('wc_factor_bwd', ptr(dWeff), ptr(gbar), ptr(Weff), ptr(Wm), ptr(R), ptr(U), ptr(lam),
-                                        ptr(count_dev), count, Cin, g, spec.epsilon, dec, int(spec.renorm),
-                                        ptr(A), ptr(cvec), ptr(ws), nb, st)
-            dx = torch.empty_like(x)
-            TAp = None
-            if bool(lib.wc_path_for(N * HW, Cin, Cout, g) & 1) and USE_TENSOR_CORES:
-                TAp = _ws(lib.wc_pack_bytes(Cin, K, 1), dev)
-                _call('wc_pack_bwd', ptr(T), ptr(A), Cin, g, K, ptr(TAp), st)
-            _call('wc_apply_bwd', ptr(x), ptr(dy), N, HW, Cin, Cout, ptr(mean), ptr(T), ptr(A), ptr(TAp), ptr(cvec), g,
-                                   ptr(cls), K, ptr(dx), st)
+        ws = _workspace(bws, dev, st, 1)
 
+        c.dy, c.dx = ptr(dy), ptr(dx)
+        c.dWu, c.dbu, c.dWc, c.dbc = ptr(dWu), ptr(dbu), ptr(dWc), ptr(dbc)
+        c.dclass_matrix, c.dD, c.dbf = ptr(dcm), ptr(dD), ptr(dbf)
+        c.red = ptr(red)
+        c.workspace, c.workspace_bytes = ptr(ws), ws.numel() * 4
+        if ctx.sync and stats_grad:
+            c.phases = PHASE_REDUCE
+            _call('wc_layer_bwd', ctypes.byref(c), st)
+            sync.allreduce_adjoint(red, ctx.group)
+            c.phases = PHASE_DX
+            _call('wc_layer_bwd', ctypes.byref(c), st)
+        else:
+            c.phases = PHASE_REDUCE | PHASE_DX
+            _call('wc_layer_bwd', ctypes.byref(c), st)
         return (dx, dWu, dbu, dWc, dbc, dcm, dD, dbf, None, None, None, None, None, None, None)
 
 

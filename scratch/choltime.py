@@ -11,7 +11,6 @@ lib.wc_debug_chol_timing.argtypes = [ctypes.c_void_p]
 print('rc', lib.wc_debug_chol_timing(buf))
 ts = list(buf)
 base = ts[0]
-print('load->start', 0)
 for J in range(8):
     a, b, c = ts[1+3*J], ts[2+3*J], ts[3+3*J]
     nxt = ts[1+3*(J+1)] if J < 7 else ts[30]

@@ -116,6 +116,17 @@ __device__ __forceinline__ void warp_neg_mul_from_regs(float (&out)[4][8], const
   }
 }
 
+// column-major smem tile (pitch TP) -> row-major global (leading dimension ld): 8 lanes write the 128 bytes of one row
+__device__ __forceinline__ void store_tile_rowmajor(const float* T, float* dst, int ld, int lane) {
+  const int rr = lane >> 3, q8 = lane & 7;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int row = 4 * e + rr;
+    const float* s = T + (4 * q8) * TP + row;
+    *reinterpret_cast<float4*>(dst + (long long)row * ld + 4 * q8) = make_float4(s[0], s[TP], s[2 * TP], s[3 * TP]);
+  }
+}
+
 __device__ __forceinline__ void tri_index(int t, int& a, int& b) {   // t -> (a,b), 0 <= b <= a, t = a(a+1)/2 + b
   a = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
   while ((a + 1) * (a + 2) / 2 <= t) ++a;
@@ -138,6 +149,49 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
   float* X = (Xout && gp == g) ? Xout + (long long)grp * g * g : Xpad + (long long)grp * gp * gp;
 
   TS_MARK(62);
+  float* Lg = Lout ? Lout + (long long)grp * g * g : nullptr;
+  if (gp == g) {
+    // fast path (g multiple of 32).  The input is symmetric, so column c of the column-major tile (I,J) is a contiguous
+    // piece of ROW J*32+c of A: 128-bit loads and 128-bit conflict-free stores, no transpose.  A warp takes whole tiles
+    // (lane = column) and keeps all of its loads in flight at once.
+    const int ntiles = NB * (NB + 1) / 2;
+    // 8 lanes read the 128 contiguous bytes of one tile column (a row of A), a warp instruction covers 4 columns
+    const int cq = lane >> 3, q8 = lane & 7;
+    float4 v[3][8];
+    int tI[3], tJ[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int tl = warp + q * NW;
+      tI[q] = -1; tJ[q] = 0;
+      if (tl < ntiles) {
+        tri_index(tl, tI[q], tJ[q]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          v[q][e] = __ldg(reinterpret_cast<const float4*>(Ag + (long long)(tJ[q] * TB + 4 * e + cq) * g + tI[q] * TB) + q8);
+      }
+    }
+    TS_MARK(55);
+    // strictly upper tiles of the outputs are zero; issue the stores now so they drain during the factorisation
+    for (int ut = warp; ut < NB * NB; ut += NW) {
+      const int I = ut / NB, J = ut % NB;
+      if (J <= I) continue;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const long long off = (long long)(I * TB + 4 * e + cq) * g + J * TB + 4 * q8;
+        if (Xout) *reinterpret_cast<float4*>(X + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (Lg) *reinterpret_cast<float4*>(Lg + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    TS_MARK(56);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int tl = warp + q * NW;
+      if (tl < ntiles) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) *reinterpret_cast<float4*>(tiles + tl * TS + (4 * e + cq) * TP + 4 * q8) = v[q][e];
+      }
+    }
+  } else {
   // load the lower tiles (128-bit loads when rows are 16-byte aligned), pad with the identity; the strictly
   // upper tiles of the output X are zero-filled here so the stores drain while the factorisation runs
   const bool vec_ok = (g & 3) == 0;
@@ -161,10 +215,14 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
       for (int e = 0; e < 4; ++e) T[((j4 + e) & 31) * TP] = v[e];
     }
   }
+  }
   __syncthreads();
   TS_MARK(0);
 
   // ------------------------------------------------------------------ Cholesky
+  // (Overlapping the next diagonal factorisation with the trailing updates was measured and does not pay: the update
+  // phase is bound by shared-memory operand bandwidth with all 16 warps busy, and the late steps are a serial
+  // update -> potrf chain either way.)
   for (int J = 0; J < NB; ++J) {
     TS_MARK(1 + 3 * J);
     if (warp == 0) {
@@ -176,8 +234,8 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
     TS_MARK(2 + 3 * J);
     const float* Ljj = tile_at(tiles, J, J);
     const int npanel = NB - 1 - J;
-    // panel solves (npanel tiles) + the inverse of the diagonal tile (one more job)
-    for (int job = warp; job <= npanel; job += NW) {
+    // panel solves (npanel tiles) + the inverse of the diagonal tile + the row-major copy of the diagonal tile
+    for (int job = warp; job <= npanel + 1; job += NW) {
       float x[32];
       if (job < npanel) {
         float* T = tile_at(tiles, J + 1 + job, J);
@@ -186,17 +244,21 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
         warp_trsm_row(x, Ljj, rdiag + J * TB);
 #pragma unroll
         for (int c = 0; c < 32; ++c) T[c * TP + lane] = x[c];
-      } else if (Xout) {
-        // inv(L_JJ): row `lane` of L^-T = column `lane` of L^-1
+        if (Lg && gp == g) { __syncwarp(); store_tile_rowmajor(T, Lg + (long long)((J + 1 + job) * TB) * g + J * TB, g, lane); }
+      } else if (job == npanel) {
+        if (Xout) {
+          // inv(L_JJ): row `lane` of L^-T = column `lane` of L^-1
 #pragma unroll
-        for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.f : 0.f;
-        warp_trsm_row(x, Ljj, rdiag + J * TB);
-        float* D = xd + J * TS;
+          for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.f : 0.f;
+          warp_trsm_row(x, Ljj, rdiag + J * TB);
+          float* D = xd + J * TS;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          D[lane * TP + c] = x[c];                                           // element (row c, col lane)
-          X[(long long)(J * TB + c) * gp + J * TB + lane] = x[c];
+          for (int c = 0; c < 32; ++c) D[lane * TP + c] = x[c];              // element (row c, col lane)
+          __syncwarp();
+          store_tile_rowmajor(D, X + (long long)(J * TB) * gp + J * TB, gp, lane);
         }
+      } else if (Lg && gp == g) {
+        store_tile_rowmajor(Ljj, Lg + (long long)(J * TB) * g + J * TB, g, lane);
       }
     }
     __syncthreads();
@@ -204,9 +266,9 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
     // trailing updates: tile(I,K) -= L_IJ L_KJ^T for J < K <= I
     const int nupd = npanel * (npanel + 1) / 2;
     for (int job = warp; job < nupd; job += NW) {
-      int a, b;
-      tri_index(job, a, b);
-      const int I = J + 1 + a, K = J + 1 + b;
+      int a, b2;
+      tri_index(job, a, b2);
+      const int I = J + 1 + a, K = J + 1 + b2;
       float acc[4][8];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
@@ -226,8 +288,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
   }
 
   TS_MARK(30);
-  if (Lout) {
-    float* Lg = Lout + (long long)grp * g * g;
+  if (Lg && gp != g) {
     for (int idx = t; idx < g * g; idx += NW * 32) {
       const int i = idx / g, j = idx % g;
       Lg[idx] = (j <= i) ? tile_at(tiles, i >> 5, j >> 5)[(j & 31) * TP + (i & 31)] : 0.f;

@@ -6,28 +6,33 @@
 // bits) and the product is accumulated as hi.hi + hi.lo + lo.hi in the fp32 TMEM accumulator ("bf16x3";
 // the dropped lo.lo term is 2^-18 relative).
 //
-// One CTA computes one 128-row x C output tile (rows of one sample), two CTAs are resident per SM so one
-// tile's epilogue overlaps the other's main loop.  Warp roles (320 threads):
-//   warps 0-7  A converters: coalesced 128-bit loads of fp32 activations -> centre -> bf16 hi/lo ->
-//              st.shared into the SWIZZLE_64B K-major operand tiles; afterwards the epilogue
-//              (tcgen05.ld -> smem transpose -> coalesced stores, + bias)
-//   warp  8    MMA issuer (one elected thread), owns the TMEM allocation
-//   warp  9    B loader: cp.async.bulk of pre-packed bf16 hi/lo operand images (written by wc_pack_*)
-// Stages are handed over with mbarriers (full: 8 converter warps + 1 expect_tx arrival; empty: tcgen05.commit).
+// Persistent kernel, one CTA per SM, 128-row x C output tiles handed out round-robin.  Warp roles (448 threads):
+//   warp  0     producer (one thread): tensor-map TMA loads of fp32 activation boxes [128 rows x 32 channels]
+//               (SWIZZLE_128B, out-of-range rows zero-filled) into a 4-deep staging ring, and 1-D bulk copies of
+//               the pre-packed bf16 hi/lo images of the C x C matrices (written by wc_pack_*) into the B ring
+//   warp  1     MMA issuer (one thread), owns TMEM: two 128 x C fp32 accumulators, so a tile's epilogue overlaps
+//               the next tile's main loop
+//   warps 2-5   epilogue: tcgen05.ld -> + bias -> swizzled shared tile -> TMA store (clipped at the sample end)
+//   warps 6-13  converters: ld.shared fp32 -> centre -> bf16 hi/lo -> K-major SWIZZLE_64B operand tiles
+// Every hand-over is an mbarrier pair (full/empty); smem is freed for the producer by tcgen05.commit.
 #include "wc_common.cuh"
 #include "wc_tc.cuh"
+#include <cuda.h>
 
 using namespace wctc;
 
 namespace {
 
-constexpr int KB = 32;                 // K elements per stage (64-byte rows, SWIZZLE_64B)
+constexpr int KB = 32;                 // K elements per stage (64-byte bf16 rows, SWIZZLE_64B)
 constexpr int TILE_M = 128;
-constexpr int NCONV_WARPS = 8;
-constexpr int NTHREADS = (NCONV_WARPS + 2) * 32;
+constexpr int NCONV_WARPS = 8, NEPI_WARPS = 4;
+constexpr int W_PROD = 0, W_MMA = 1, W_EPI0 = 2, W_CONV0 = W_EPI0 + NEPI_WARPS;
+constexpr int NTHREADS = (W_CONV0 + NCONV_WARPS) * 32;
+constexpr int NCONV = NCONV_WARPS * 32, NEPI = NEPI_WARPS * 32;
+constexpr int STG_BYTES = TILE_M * KB * 4;   // one fp32 activation box: 16 KB
+constexpr int NSTG = 4, NAOP = 3, NBOP = 2, NEPIBUF = 2;
 
 struct TcSeg {
-  const float* A;        // activations [rows][C]
   const float* mean;     // per-channel shift (nullable)
   const uint8_t* Bp;     // packed operand images: [slot][kb][hi|lo][C x 64 B]
   long long slot_stride; // bytes between slots (0 = shared)
@@ -37,188 +42,240 @@ struct TcApplyParams {
   TcSeg seg[2];
   int nseg;
   const float* bias; long long bias_slot_stride; float bias_sign;
-  int HW, tiles_per_sample;
+  int N, HW, tiles_per_sample;
+  long long total_tiles;
   const int32_t* cls; int K; int32_t* info;
-  float* out;
+  unsigned long long* dbg;
 };
 
 template <int C>
 struct Cfg {
   static constexpr int N = C;
   static constexpr int NKB = C / KB;                       // K blocks per segment
-  static constexpr int A_IMG = TILE_M * KB * 2;            // 8 KB
+  static constexpr int A_IMG = TILE_M * KB * 2;            // 8 KB: one bf16 split of an A tile
   static constexpr int B_IMG = N * KB * 2;                 // 16 KB (C=256) / 8 KB (C=128)
-  static constexpr int STAGE = 2 * A_IMG + 2 * B_IMG;      // 48 KB / 32 KB
-  static constexpr int STAGES = (C == 256) ? 2 : 3;
-  static constexpr int SMEM = STAGES * STAGE + 1024;       // + alignment slack
+  static constexpr int OFF_AOP = NSTG * STG_BYTES;
+  static constexpr int OFF_BOP = OFF_AOP + NAOP * 2 * A_IMG;
+  static constexpr int OFF_EPI = OFF_BOP + NBOP * 2 * B_IMG;
+  static constexpr int SMEM = OFF_EPI + NEPIBUF * STG_BYTES + 1024;   // + alignment slack
+  static constexpr int TMEM_COLS = 2 * N;                  // 512 / 256
 };
 
+struct TileInfo { int sample, r0, slot; };
+
+__device__ __forceinline__ TileInfo tile_info(const TcApplyParams& p, long long tile) {
+  TileInfo ti;
+  // tiles are visited from the end of the tensor: the rows the previous kernel read last are the ones most likely
+  // still resident in L2
+  const long long tr = p.total_tiles - 1 - tile;
+  ti.sample = (int)(tr / p.tiles_per_sample);
+  ti.r0 = (int)(tr % p.tiles_per_sample) * TILE_M;
+  ti.slot = 0;
+  if (p.cls) {
+    int c = p.cls[ti.sample];
+    if (c < 0 || c >= p.K) {
+      if (p.info && threadIdx.x == 0 && ti.r0 == 0) atomicMax(&p.info[WC_INFO_BAD_CLASS], ti.sample + 1);
+      c = c < 0 ? 0 : p.K - 1;
+    }
+    ti.slot = c;
+  }
+  return ti;
+}
+
 template <int C>
-__global__ void __launch_bounds__(NTHREADS, 2) tc_apply_kernel(TcApplyParams p) {
+__global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, const __grid_constant__ CUtensorMap tm_a0,
+                                                               const __grid_constant__ CUtensorMap tm_a1,
+                                                               const __grid_constant__ CUtensorMap tm_out) {
   using cfg = Cfg<C>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t full_bar[cfg::STAGES], empty_bar[cfg::STAGES], acc_bar;
+  __shared__ uint64_t stg_full[NSTG], stg_empty[NSTG], aop_full[NAOP], aop_empty[NAOP], bop_full[NBOP], bop_empty[NBOP],
+      acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float smean[2][C];
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int sample = blockIdx.x / p.tiles_per_sample;
-  const int rt = blockIdx.x % p.tiles_per_sample;
-  const int r0 = rt * TILE_M;
-  const int rows_valid = min(TILE_M, p.HW - r0);
-  const long long row_base = (long long)sample * p.HW + r0;
-  int slot = 0;
-  if (p.cls) {
-    int c = p.cls[sample];
-    if (c < 0 || c >= p.K) {
-      if (p.info && t == 0 && rt == 0) atomicMax(&p.info[WC_INFO_BAD_CLASS], sample + 1);
-      c = c < 0 ? 0 : p.K - 1;
-    }
-    slot = c;
-  }
+  const int total_kb = p.nseg * cfg::NKB;
 
   if (t == 0) {
-    for (int s = 0; s < cfg::STAGES; ++s) { mbar_init(&full_bar[s], NCONV_WARPS + 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&acc_bar, 1);
+    for (int s = 0; s < NSTG; ++s) { mbar_init(&stg_full[s], 1); mbar_init(&stg_empty[s], NCONV_WARPS); }
+    for (int s = 0; s < NAOP; ++s) { mbar_init(&aop_full[s], NCONV_WARPS); mbar_init(&aop_empty[s], 1); }
+    for (int s = 0; s < NBOP; ++s) { mbar_init(&bop_full[s], 1); mbar_init(&bop_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NEPI_WARPS); }
     mbar_fence_init();
+    tma_prefetch_desc(&tm_a0); tma_prefetch_desc(&tm_a1); tma_prefetch_desc(&tm_out);
   }
-  if (warp == NCONV_WARPS) { tmem_alloc(&tmem_slot, cfg::N); tmem_relinquish(); }
+  if (warp == W_MMA) { tmem_alloc(&tmem_slot, cfg::TMEM_COLS); tmem_relinquish(); }
+  for (int i = t; i < 2 * C; i += NTHREADS) {
+    const int sg = i / C, ch = i % C;
+    smean[sg][ch] = (sg < p.nseg && p.seg[sg].mean) ? p.seg[sg].mean[ch] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t td = tmem_slot;
-  const int total_kb = p.nseg * cfg::NKB;
+  if (t == 0) wc_mark(p.dbg, 0);
 
-  if (warp == NCONV_WARPS) {
+  if (warp == W_PROD) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      uint32_t ia = 0, ib = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileInfo ti = tile_info(p, tile);
+        for (int it = 0; it < total_kb; ++it) {
+          const int sg = it / cfg::NKB, kb = it % cfg::NKB;
+          {
+            const int s = ia % NSTG;
+            mbar_wait(&stg_empty[s], ((ia / NSTG) & 1) ^ 1);
+            mbar_arrive_expect_tx(&stg_full[s], STG_BYTES);
+            tma_load_3d(smem + s * STG_BYTES, sg == 0 ? &tm_a0 : &tm_a1, kb * KB, ti.r0, ti.sample, &stg_full[s]);
+            ++ia;
+          }
+          {
+            const int s = ib % NBOP;
+            const uint8_t* src = p.seg[sg].Bp + (long long)ti.slot * p.seg[sg].slot_stride + (long long)kb * (2 * cfg::B_IMG);
+            mbar_wait(&bop_empty[s], ((ib / NBOP) & 1) ^ 1);
+            uint8_t* dst = smem + cfg::OFF_BOP + s * 2 * cfg::B_IMG;
+            mbar_arrive_expect_tx(&bop_full[s], 2 * cfg::B_IMG);
+            bulk_g2s(dst, src, cfg::B_IMG, &bop_full[s]);
+            bulk_g2s(dst + cfg::B_IMG, src + cfg::B_IMG, cfg::B_IMG, &bop_full[s]);
+            ++ib;
+          }
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(TILE_M, cfg::N, 0, 0);
-      uint32_t acc = 0;
-      for (int it = 0; it < total_kb; ++it) {
-        const int s = it % cfg::STAGES;
-        const uint32_t ph = (it / cfg::STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t ia = 0, ib = 0, lt = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t ab = lt & 1;
+        mbar_wait(&acc_empty[ab], ((lt >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * cfg::STAGE);
-        const uint32_t a_lo = a_hi + cfg::A_IMG;
-        const uint32_t b_hi = a_hi + 2 * cfg::A_IMG;
-        const uint32_t b_lo = b_hi + cfg::B_IMG;
+        const uint32_t tacc = td + ab * cfg::N;
+        uint32_t acc = 0;
+        for (int it = 0; it < total_kb; ++it, ++ia, ++ib) {
+          const int sa = ia % NAOP, sb = ib % NBOP;
+          mbar_wait(&aop_full[sa], (ia / NAOP) & 1);
+          mbar_wait(&bop_full[sb], (ib / NBOP) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + cfg::OFF_AOP + sa * 2 * cfg::A_IMG);
+          const uint32_t a_lo = a_hi + cfg::A_IMG;
+          const uint32_t b_hi = smem_u32(smem + cfg::OFF_BOP + sb * 2 * cfg::B_IMG);
+          const uint32_t b_lo = b_hi + cfg::B_IMG;
 #pragma unroll
-        for (int kk = 0; kk < KB / 16; ++kk) {
-          const uint64_t dah = make_desc(a_hi + kk * 32, 16, 8 * KB * 2, LAYOUT_SW64);
-          const uint64_t dal = make_desc(a_lo + kk * 32, 16, 8 * KB * 2, LAYOUT_SW64);
-          const uint64_t dbh = make_desc(b_hi + kk * 32, 16, 8 * KB * 2, LAYOUT_SW64);
-          const uint64_t dbl = make_desc(b_lo + kk * 32, 16, 8 * KB * 2, LAYOUT_SW64);
-          umma_bf16(td, dah, dbh, idesc, acc);
-          umma_bf16(td, dah, dbl, idesc, 1);
-          umma_bf16(td, dal, dbh, idesc, 1);
-          acc = 1;
+          for (int kk = 0; kk < KB / 16; ++kk) {
+            const uint64_t dah = make_desc(a_hi + kk * 32, 16, 8 * KB * 2, LAYOUT_SW64);
+            const uint64_t dal = make_desc(a_lo + kk * 32, 16, 8 * KB * 2, LAYOUT_SW64);
+            const uint64_t dbh = make_desc(b_hi + kk * 32, 16, 8 * KB * 2, LAYOUT_SW64);
+            const uint64_t dbl = make_desc(b_lo + kk * 32, 16, 8 * KB * 2, LAYOUT_SW64);
+            umma_bf16(tacc, dah, dbh, idesc, acc);
+            umma_bf16(tacc, dah, dbl, idesc, 1);
+            umma_bf16(tacc, dal, dbh, idesc, 1);
+            acc = 1;
+          }
+          umma_commit(&aop_empty[sa]);     // both operand stages are reusable once these MMAs have read them
+          umma_commit(&bop_empty[sb]);
         }
-        umma_commit(&empty_bar[s]);      // stage reusable once these MMAs have read it
-      }
-      umma_commit(&acc_bar);             // accumulator complete
-    }
-  } else if (warp == NCONV_WARPS + 1) {
-    // ------------------------------------------------------------------ B loader
-    if (lane == 0) {
-      for (int it = 0; it < total_kb; ++it) {
-        const int s = it % cfg::STAGES;
-        const uint32_t ph = (it / cfg::STAGES) & 1;
-        const int sg = it / cfg::NKB, kb = it % cfg::NKB;
-        const uint8_t* src = p.seg[sg].Bp + (long long)slot * p.seg[sg].slot_stride + (long long)kb * (2 * cfg::B_IMG);
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* dst = smem + s * cfg::STAGE + 2 * cfg::A_IMG;
-        mbar_arrive_expect_tx(&full_bar[s], 2 * cfg::B_IMG);
-        bulk_g2s(dst, src, cfg::B_IMG, &full_bar[s]);
-        bulk_g2s(dst + cfg::B_IMG, src + cfg::B_IMG, cfg::B_IMG, &full_bar[s]);
+        umma_commit(&acc_full[ab]);        // accumulator complete
       }
     }
+  } else if (warp < W_CONV0) {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int te = t - W_EPI0 * 32;
+    const int q = warp & 3;                // TMEM lanes 32q .. 32q+31 are the ones this warp may read
+    const int row = q * 32 + lane;         // row of the tile held by this thread
+    uint32_t lt = 0, ec = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const TileInfo ti = tile_info(p, tile);
+      const uint32_t ab = lt & 1;
+      const float* bias = p.bias ? p.bias + (long long)ti.slot * p.bias_slot_stride : nullptr;
+      mbar_wait(&acc_full[ab], (lt >> 1) & 1);
+      tc_fence_after();
+      for (int c0 = 0; c0 < cfg::N; c0 += 32, ++ec) {
+        const uint32_t eb = ec & 1;
+        // the TMA store issued two chunks ago has finished reading this buffer
+        if (te == 0) bulk_wait_group_read<1>();
+        asm volatile("bar.sync 2, %0;" ::"n"(NEPI));
+        float acc[32];
+        tmem_ld32(td + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * cfg::N + c0), acc);
+        if (c0 + 32 == cfg::N) {           // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[ab]);
+        }
+        const uint32_t ebase = smem_u32(smem + cfg::OFF_EPI + eb * STG_BYTES) + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+          const float s = p.bias_sign;
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ebase + ((j ^ (row & 7)) << 4)), "f"(fmaf(s, bv.x, acc[4 * j])),
+                       "f"(fmaf(s, bv.y, acc[4 * j + 1])), "f"(fmaf(s, bv.z, acc[4 * j + 2])), "f"(fmaf(s, bv.w, acc[4 * j + 3])) : "memory");
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 2, %0;" ::"n"(NEPI));
+        if (te == 0) {
+          tma_store_3d(&tm_out, c0, ti.r0, ti.sample, smem + cfg::OFF_EPI + eb * STG_BYTES);
+          bulk_commit_group();
+        }
+      }
+    }
+    if (te == 0) bulk_wait_group<0>();
   } else {
-    // ------------------------------------------------------------------ A converters
-    // K block = 128 rows x 32 channels = 512 chunks of 8 channels; thread handles chunks t and t+256:
-    // row = q/4, chunk-in-row = q%4 -> 4 consecutive threads read one row's 128 contiguous bytes.
-    const int crow0 = t >> 2, cch = t & 3;
-    // Global loads run TWO K blocks ahead of the conversion (two register buffers): ~32 KB in flight per CTA,
-    // which is what it takes to cover HBM latency at full bandwidth with two CTAs per SM.
-    float4 va[2][2], vb[2][2];
-    auto gload = [&](int it, float4 (&v)[2][2]) {
-      const int sg = it / cfg::NKB, kb = it % cfg::NKB;
-      const float* A = p.seg[sg].A;
+    // ------------------------------------------------------------------ A converters (256 threads)
+    // staged box: row r = 128 contiguous bytes, its 16-byte chunk j sits at position j ^ (r & 7) (SWIZZLE_128B).
+    // A thread converts 8 channels of two rows (r, r + 64): 2 ld.shared.v4 + 2 st.shared.v4 per row.
+    const int tcv = t - W_CONV0 * 32;
+    const int crow0 = tcv >> 2, cch = tcv & 3;
+    const uint32_t stg_u32 = smem_u32(smem), aop_u32 = smem_u32(smem + cfg::OFF_AOP);
+    uint32_t ld_off[2][2], st_off[2];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int row = crow0 + h * 64;
-        if (row < rows_valid) {
-          const float4* src = reinterpret_cast<const float4*>(A + (row_base + row) * C + kb * KB + cch * 8);
-          v[h][0] = wc_ldg_stream(src);
-          v[h][1] = wc_ldg_stream(src + 1);
-        } else {
-          v[h][0] = v[h][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    };
-    auto process = [&](int it, float4 (&v)[2][2]) {
-      const int s = it % cfg::STAGES;
-      const uint32_t ph = (it / cfg::STAGES) & 1;
-      const int sg = it / cfg::NKB, kb = it % cfg::NKB;
-      float4 m0 = make_float4(0.f, 0.f, 0.f, 0.f), m1 = m0;
-      if (p.seg[sg].mean) {
-        const float4* mp = reinterpret_cast<const float4*>(p.seg[sg].mean + kb * KB + cch * 8);
-        m0 = __ldg(mp); m1 = __ldg(mp + 1);
-      }
-      uint32_t hi[2][4], lo[2][4];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const bool ok = (crow0 + h * 64) < rows_valid;   // rows past the tile end stay exactly zero
-        float4 a = v[h][0], b = v[h][1];
-        if (ok) { a.x -= m0.x; a.y -= m0.y; a.z -= m0.z; a.w -= m0.w; b.x -= m1.x; b.y -= m1.y; b.z -= m1.z; b.w -= m1.w; }
-        split2(a.x, a.y, hi[h][0], lo[h][0]);
-        split2(a.z, a.w, hi[h][1], lo[h][1]);
-        split2(b.x, b.y, hi[h][2], lo[h][2]);
-        split2(b.z, b.w, hi[h][3], lo[h][3]);
-      }
-      if (it + 2 < total_kb) gload(it + 2, v);          // refill this buffer: its loads fly over the next block
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      uint8_t* a_hi = smem + s * cfg::STAGE;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint32_t off = kmajor_chunk_off<KB>(crow0 + h * 64, cch);
-        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[h][0], hi[h][1], hi[h][2], hi[h][3]);
-        *reinterpret_cast<uint4*>(a_hi + cfg::A_IMG + off) = make_uint4(lo[h][0], lo[h][1], lo[h][2], lo[h][3]);
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
-    };
-    gload(0, va);
-    if (total_kb > 1) gload(1, vb);
-    for (int it = 0; it < total_kb; it += 2) {
-      process(it, va);
-      if (it + 1 < total_kb) process(it + 1, vb);
+    for (int h = 0; h < 2; ++h) {
+      const int r = crow0 + h * 64;
+      ld_off[h][0] = r * 128 + (((2 * cch) ^ (r & 7)) << 4);
+      ld_off[h][1] = r * 128 + (((2 * cch + 1) ^ (r & 7)) << 4);
+      st_off[h] = kmajor_chunk_off<KB>(r, cch);
     }
-    // ------------------------------------------------------------------ epilogue (same 8 warps)
-    mbar_wait(&acc_bar, 0);
-    tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
-    float* stg = reinterpret_cast<float*>(smem) + warp * (32 * 33);
-    const float* bias = p.bias ? p.bias + (long long)slot * p.bias_slot_stride : nullptr;
-    for (int c0 = half * (cfg::N / 2); c0 < (half + 1) * (cfg::N / 2); c0 += 32) {
-      float acc[32];
-      tmem_ld32(td + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+    uint32_t ia = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int it = 0; it < total_kb; ++it, ++ia) {
+        const int sg = it / cfg::NKB, kb = it % cfg::NKB;
+        const int s = ia % NSTG, sa = ia % NAOP;
+        const float4 m0 = *reinterpret_cast<const float4*>(&smean[sg][kb * KB + cch * 8]);
+        const float4 m1 = *reinterpret_cast<const float4*>(&smean[sg][kb * KB + cch * 8 + 4]);
+        mbar_wait(&stg_full[s], (ia / NSTG) & 1);
+        uint32_t hi[2][4], lo[2][4];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = acc[j];
-      __syncwarp();
-      const float bv = bias ? p.bias_sign * __ldg(bias + c0 + lane) : 0.f;
-#pragma unroll 4
-      for (int r = 0; r < 32; ++r) {
-        const int row = q * 32 + r;
-        if (row < rows_valid) p.out[(row_base + row) * C + c0 + lane] = stg[r * 33 + lane] + bv;
+        for (int h = 0; h < 2; ++h) {
+          float4 a = lds128(stg_u32 + s * STG_BYTES + ld_off[h][0]);
+          float4 b = lds128(stg_u32 + s * STG_BYTES + ld_off[h][1]);
+          a.x -= m0.x; a.y -= m0.y; a.z -= m0.z; a.w -= m0.w; b.x -= m1.x; b.y -= m1.y; b.z -= m1.z; b.w -= m1.w;
+          split2(a.x, a.y, hi[h][0], lo[h][0]);
+          split2(a.z, a.w, hi[h][1], lo[h][1]);
+          split2(b.x, b.y, hi[h][2], lo[h][2]);
+          split2(b.z, b.w, hi[h][3], lo[h][3]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stg_empty[s]);            // the box is in registers: give it back to the producer
+        mbar_wait(&aop_empty[sa], ((ia / NAOP) & 1) ^ 1);
+        const uint32_t dst = aop_u32 + sa * 2 * cfg::A_IMG;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          sts128(dst + st_off[h], hi[h][0], hi[h][1], hi[h][2], hi[h][3]);
+          sts128(dst + cfg::A_IMG + st_off[h], lo[h][0], lo[h][1], lo[h][2], lo[h][3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&aop_full[sa]);
       }
-      __syncwarp();
     }
   }
+  if (t == 0) wc_mark(p.dbg, 1);
   tc_fence_before();
   __syncthreads();
-  if (warp == NCONV_WARPS) tmem_dealloc(td, cfg::N);
+  if (warp == W_MMA) tmem_dealloc(td, cfg::TMEM_COLS);
 }
 
 // ---- operand packing: fp32 matrix -> bf16 hi/lo K-major SWIZZLE_64B images -------------------------------
@@ -259,20 +316,56 @@ __global__ void __launch_bounds__(256) pack_b_kernel(const float* __restrict__ M
   *reinterpret_cast<uint4*>(dst + b_img) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// fp32 activations viewed as [N][HW][C]; box = 128 rows x 32 channels of one sample, SWIZZLE_128B
+int make_act_map(CUtensorMap* tm, const float* base, int N, int HW, int C) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return WC_E_UNSUPPORTED;
+  const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)HW, (cuuint64_t)N};
+  const cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)HW * C * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)TILE_M, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : WC_E_UNSUPPORTED;
+}
+
 template <int C>
-int launch_tc_apply(TcApplyParams& p, int N, int HW, cudaStream_t st) {
+int launch_tc_apply(TcApplyParams& p, const float* a0, const float* a1, float* out, int N, int HW, cudaStream_t st) {
   const bool cond = p.cls != nullptr && p.K > 1;
   if (!cond) { HW = N * HW; N = 1; p.cls = nullptr; }
-  p.HW = HW;
+  p.N = N; p.HW = HW;
   p.tiles_per_sample = wc_cdiv(HW, TILE_M);
-  long long gx = (long long)N * p.tiles_per_sample;
-  if (gx > INT32_MAX) return WC_E_UNSUPPORTED;
+  p.total_tiles = (long long)N * p.tiles_per_sample;
+  p.dbg = wc_debug_buf();
+  alignas(64) CUtensorMap tm_a0, tm_a1, tm_out;
+  int rc = make_act_map(&tm_a0, a0, N, HW, C);
+  if (!rc) rc = make_act_map(&tm_a1, a1 ? a1 : a0, N, HW, C);
+  if (!rc) rc = make_act_map(&tm_out, out, N, HW, C);
+  if (rc) return rc;
   static bool attr_set = false;   // idempotent; a race only repeats the same call
   if (!attr_set) {
     WC_CUDA(cudaFuncSetAttribute(tc_apply_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<C>::SMEM));
     attr_set = true;
   }
-  tc_apply_kernel<C><<<(unsigned)gx, NTHREADS, Cfg<C>::SMEM, st>>>(p);
+  const unsigned grid = (unsigned)(p.total_tiles < WC_NUM_SMS ? p.total_tiles : WC_NUM_SMS);
+  tc_apply_kernel<C><<<grid, NTHREADS, Cfg<C>::SMEM, st>>>(p, tm_a0, tm_a1, tm_out);
   WC_CHECK_LAUNCH();
   return 0;
 }
@@ -318,25 +411,26 @@ extern "C" int wc_pack_bwd(const float* T, const float* A, int C, int g, int K, 
 int wc_tc_apply_fwd(const float* x, int N, int HW, int C, const float* mean, const void* packed, const float* b,
                     const int32_t* cls, int K, float* y, int32_t* info, cudaStream_t st) {
   TcApplyParams p{};
-  p.seg[0] = TcSeg{x, mean, (const uint8_t*)packed, (long long)C * C * 4};
+  p.seg[0] = TcSeg{mean, (const uint8_t*)packed, (long long)C * C * 4};
   p.nseg = 1;
   p.bias = b; p.bias_slot_stride = C; p.bias_sign = 1.f;
-  p.cls = cls; p.K = K; p.info = info; p.out = y;
-  return C == 256 ? launch_tc_apply<256>(p, N, HW, st) : launch_tc_apply<128>(p, N, HW, st);
+  p.cls = cls; p.K = K; p.info = info;
+  return C == 256 ? launch_tc_apply<256>(p, x, nullptr, y, N, HW, st) : launch_tc_apply<128>(p, x, nullptr, y, N, HW, st);
 }
 
 int wc_tc_apply_bwd(const float* x, const float* dy, int N, int HW, int C, const float* mean, const void* packed,
                     bool has_A, const float* cvec, const int32_t* cls, int K, float* dx, cudaStream_t st) {
   TcApplyParams p{};
-  p.seg[0] = TcSeg{dy, nullptr, (const uint8_t*)packed, (long long)C * C * 4};
+  p.seg[0] = TcSeg{nullptr, (const uint8_t*)packed, (long long)C * C * 4};
   p.nseg = 1;
   if (has_A) {
-    p.seg[1] = TcSeg{x, mean, (const uint8_t*)packed + (size_t)K * C * C * 4, 0};
+    p.seg[1] = TcSeg{mean, (const uint8_t*)packed + (size_t)K * C * C * 4, 0};
     p.nseg = 2;
   }
   p.bias = has_A ? cvec : nullptr; p.bias_slot_stride = 0; p.bias_sign = -1.f;
-  p.cls = cls; p.K = K; p.info = nullptr; p.out = dx;
-  return C == 256 ? launch_tc_apply<256>(p, N, HW, st) : launch_tc_apply<128>(p, N, HW, st);
+  p.cls = cls; p.K = K; p.info = nullptr;
+  return C == 256 ? launch_tc_apply<256>(p, dy, has_A ? x : nullptr, dx, N, HW, st)
+                  : launch_tc_apply<128>(p, dy, has_A ? x : nullptr, dx, N, HW, st);
 }
 
 bool wc_tc_apply_ok(int Cin, int Cout) { return tc_shape_ok(Cin, Cout); }

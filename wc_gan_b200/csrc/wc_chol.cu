@@ -425,11 +425,371 @@ __global__ void __launch_bounds__(TI_THREADS) trinv_kernel(const float* __restri
   }
 }
 
+
+// ======================================================================================================
+// Cluster Cholesky + inverse: one thread-block cluster of 8 CTAs per group matrix (g multiple of 32, 128 <= g <= 256)
+// ======================================================================================================
+// The one-CTA kernel above is bound by the serial chain potrf -> panel solves -> trailing updates with every tile
+// product on one SM.  Here CTA r of the cluster owns block-row r of L (left-looking):
+//     L_rJ = (A_rJ - sum_{K<J} L_rK L_JK^T) L_JJ^-T   for J < r,      L_rr = chol(A_rr - sum_{K<r} L_rK L_rK^T)
+// and, once its row is done, block-column r of X = L^-1:
+//     X_rr = inv(L_rr),     X_Ir = -inv(L_II) sum_{K=r..I-1} L_IK X_Kr   for I > r.
+// Finished tiles are published through a global scratch (L2) as column-major 32x32 tiles and announced with remote
+// mbarrier arrivals in the consumers' shared memory (DSMEM): A[J] = off-diagonal tiles of row J, B[J] = L_JJ and
+// 1/diag, D[J] = inv(L_JJ).  The critical path is  potrf(J) -> publish -> solve of tile (J+1,J) -> diagonal update ->
+// potrf(J+1); everything else runs behind that wavefront on the other CTAs.
+constexpr int CLN = 8;                 // CTAs per cluster = maximum number of block rows
+constexpr int CLW = 8;                 // warps per CTA
+constexpr int GT = TB * TB;            // floats per published tile (column-major, pitch 32)
+__device__ unsigned long long g_cl_ts[CLN][32];
+#define CL_MARK(i) do { if (dbg) { if (lane == 0 && warp == 0 && grp == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); g_cl_ts[r][i] = t__; } __syncwarp(); } } while (0)
+
+__device__ __forceinline__ uint32_t cl_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cl_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cl_fence() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void cl_arrive_remote(uint64_t* local_bar, uint32_t rank) {
+  const uint32_t la = (uint32_t)__cvta_generic_to_shared(local_bar);
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void cl_wait(uint64_t* bar) {   // each flag is used once per launch: phase 0
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "CL_WAIT:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], 0;\n\t"
+      "@P1 bra CL_DONE;\n\t"
+      "bra CL_WAIT;\n\t"
+      "CL_DONE:\n\t}" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+// acc(4x8 per lane) += A(32x32, k-major, pitch PA) * B(32x32, k-major, pitch PB); GA / GB: operand lives in the global
+// scratch (read through L2 only: it was written by another SM during this launch)
+template <int PA, int PB, bool GA, bool GB>
+__device__ __forceinline__ void cl_tile_fma(float (&acc)[4][8], const float* At, const float* Bt, int ly, int lx) {
+#pragma unroll 8
+  for (int kk = 0; kk < 32; ++kk) {
+    const float* ap = At + kk * PA + 4 * ly;
+    const float* bp = Bt + kk * PB + 8 * lx;
+    const float4 a = GA ? ldcg4(ap) : *reinterpret_cast<const float4*>(ap);
+    const float4 b0 = GB ? ldcg4(bp) : *reinterpret_cast<const float4*>(bp);
+    const float4 b1 = GB ? ldcg4(bp + 4) : *reinterpret_cast<const float4*>(bp + 4);
+    const float av[4] = {a.x, a.y, a.z, a.w};
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+  }
+}
+__device__ __forceinline__ void acc_zero(float (&acc)[4][8]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+}
+// accumulator -> column-major tile (pitch TP): element (4ly+r, 8lx+c)
+__device__ __forceinline__ void acc_store_colmajor(const float (&acc)[4][8], float* T, int ly, int lx) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<float4*>(T + (8 * lx + c) * TP + 4 * ly) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+}
+// accumulator -> row-major tile (pitch TP)
+__device__ __forceinline__ void acc_store_rowmajor(const float (&acc)[4][8], float* T, int ly, int lx, float sign) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float* d = T + (4 * ly + r) * TP + 8 * lx;
+    *reinterpret_cast<float4*>(d) = make_float4(sign * acc[r][0], sign * acc[r][1], sign * acc[r][2], sign * acc[r][3]);
+    *reinterpret_cast<float4*>(d + 4) = make_float4(sign * acc[r][4], sign * acc[r][5], sign * acc[r][6], sign * acc[r][7]);
+  }
+}
+// one warp: column-major smem tile (pitch TP) -> published tile (pitch 32), 128-bit coalesced
+__device__ __forceinline__ void publish_tile(const float* T, float* gt, int lane) {
+  const int cq = lane >> 3, q8 = lane & 7;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int col = 4 * e + cq;
+    *reinterpret_cast<float4*>(gt + col * TB + 4 * q8) = *reinterpret_cast<const float4*>(T + col * TP + 4 * q8);
+  }
+}
+// one warp: published tile -> column-major smem tile (pitch TP)
+__device__ __forceinline__ void fetch_tile_warp(const float* gt, float* T, int lane) {
+  const int cq = lane >> 3, q8 = lane & 7;
+  float4 v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = ldcg4(gt + (4 * e + cq) * TB + 4 * q8);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) *reinterpret_cast<float4*>(T + (4 * e + cq) * TP + 4 * q8) = v[e];
+}
+
+// in-place lower Cholesky of a 32x32 tile by one warp (lane = row).  Column k of the factor is broadcast through
+// shared memory (one store + 128-bit broadcast loads) instead of 31-k shuffles; the pivot chain per column is
+// shfl -> rsqrt -> mul -> fma.  rsqrt.approx is accurate to 2^-22.4 relative (PTX ISA), i.e. a few ulp of the fp32 result.
+// bc: 64 floats of shared memory.
+__device__ void warp_potrf32_bc(float* T, float* rdiag, float* bc, int lane, int& bad) {
+  float a[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) a[c] = T[c * TP + lane];
+  float dg = T[lane * TP + lane];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    float piv = __shfl_sync(FULL, dg, k);
+    if (!(piv > 0.f)) { if (!bad) bad = k + 1; piv = 1e-30f; }
+    const float rs = rsqrt_approx(piv);
+    const float lk = (lane == k) ? piv * rs : a[k] * rs;
+    a[k] = lk;
+    dg = fmaf(-lk, lk, dg);
+    if (lane == k) rdiag[k] = rs;
+    if (k < 31) {
+      float* b = bc + (k & 1) * 32;
+      b[lane] = lk;
+      __syncwarp();
+#pragma unroll
+      for (int q = (k + 1) / 4; q < 8; ++q) {
+        const float4 l = *reinterpret_cast<const float4*>(b + 4 * q);
+        if (4 * q + 0 > k) a[4 * q + 0] = fmaf(-lk, l.x, a[4 * q + 0]);
+        if (4 * q + 1 > k) a[4 * q + 1] = fmaf(-lk, l.y, a[4 * q + 1]);
+        if (4 * q + 2 > k) a[4 * q + 2] = fmaf(-lk, l.z, a[4 * q + 2]);
+        if (4 * q + 3 > k) a[4 * q + 3] = fmaf(-lk, l.w, a[4 * q + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c) T[c * TP + lane] = (c <= lane) ? a[c] : 0.f;
+}
+
+// all 256 threads: acc(2x2 per thread: rows 2tr+i, cols 2tc+j) += A(32x32, k-major, pitch TP) * B(32x32, k-major, pitch TP)
+__device__ __forceinline__ void cta_tile_mac(float (&acc)[2][2], const float* At, const float* Bt, int tr, int tc) {
+#pragma unroll
+  for (int kk = 0; kk < 32; ++kk) {
+    const float2 a = *reinterpret_cast<const float2*>(At + kk * TP + 2 * tr);
+    const float2 b = *reinterpret_cast<const float2*>(Bt + kk * TP + 2 * tc);
+    acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+    acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+  }
+}
+// all 256 threads: n published tiles (pitch 32, stride GT) -> column-major smem tiles (pitch TP, stride TS)
+__device__ __forceinline__ void cta_fetch_tiles(const float* gt, int n, float* dst, int t) {
+  const int col = t >> 3, q8 = t & 7;
+  float4 v[CLN];
+#pragma unroll
+  for (int i = 0; i < CLN; ++i)
+    if (i < n) v[i] = ldcg4(gt + i * GT + col * TB + 4 * q8);
+#pragma unroll
+  for (int i = 0; i < CLN; ++i)
+    if (i < n) *reinterpret_cast<float4*>(dst + i * TS + col * TP + 4 * q8) = v[i];
+}
+
+__global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
+    chol_cluster_kernel(const float* __restrict__ Ain, int g, float* __restrict__ scratch, long long scratch_stride,
+                        float* __restrict__ Lout, float* __restrict__ Xout, int32_t* info, int dbg) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ uint64_t flagA[CLN], flagB[CLN], flagD[CLN];
+  __shared__ __align__(16) float rd_own[TB], rd_stage[TB], bcast[2 * TB];
+  const int NB = g / TB;
+  const int grp = blockIdx.x / CLN;
+  const int r = (int)cl_rank();
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int tr = t & 15, tc = t >> 4;
+  float* own = sm;                       // CLN tiles: block row r of L, column-major
+  float* xcol = own + CLN * TS;          // CLN tiles: block column r of X, row-major, indexed by block row
+  float* ljj = xcol + CLN * TS;          // staged L_JJ / inv(L_II), column-major
+  float* stile = ljj + TS;               // S tile, row-major; also inv(L_rr) column-major
+  float* stg = stile + TS;               // CLN staged tiles of another block row
+  const float* Ag = Ain + (long long)grp * g * g;
+  float* gs = scratch + (long long)grp * scratch_stride;
+  float* gD = gs + (NB * (NB + 1) / 2) * GT;       // NB tiles inv(L_JJ)
+  float* gR = gD + NB * GT;                        // NB x 32 reciprocal diagonals
+  float* Lg = Lout ? Lout + (long long)grp * g * g : nullptr;
+  float* Xg = Xout + (long long)grp * g * g;
+  auto gtile = [&](int I, int J) { return gs + (I * (I + 1) / 2 + J) * GT; };
+
+  CL_MARK(0);
+  if (t == 0) {
+    for (int j = 0; j < CLN; ++j) {
+      const uint32_t a = (uint32_t)__cvta_generic_to_shared(&flagA[j]), b = (uint32_t)__cvta_generic_to_shared(&flagB[j]),
+                     d = (uint32_t)__cvta_generic_to_shared(&flagD[j]);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(d) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // load block row r: column c of the column-major tile (r,J) is a contiguous piece of ROW J*32+c of the symmetric input
+  if (r < NB) {
+    const int cq = lane >> 3, q8 = lane & 7;
+    for (int J = warp; J <= r; J += CLW) {
+      float4 v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = __ldg(reinterpret_cast<const float4*>(Ag + (long long)(J * TB + 4 * e + cq) * g + r * TB) + q8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) *reinterpret_cast<float4*>(own + J * TS + (4 * e + cq) * TP + 4 * q8) = v[e];
+    }
+    // strictly upper tiles of the outputs are zero
+    for (int J = r + 1 + warp; J < NB; J += CLW) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const long long off = (long long)(r * TB + 4 * e + cq) * g + J * TB + 4 * q8;
+        *reinterpret_cast<float4*>(Xg + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (Lg) *reinterpret_cast<float4*>(Lg + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  __syncthreads();
+  cl_sync();      // every CTA's flags are initialised before anyone can arrive on them
+  CL_MARK(1);
+
+  if (r < NB) {
+    // ------------------------------------------------------------------ block row r of L
+    for (int J = 0; J < r; ++J) {
+      float* T = own + J * TS;
+      if (J > 0) {
+        // T -= sum_{K<J} L_rK L_JK^T  (row J's tiles come from the scratch; this runs while CTA J factors its diagonal tile)
+        cl_wait(&flagA[J]);
+        cta_fetch_tiles(gtile(J, 0), J, stg, t);
+        __syncthreads();
+        float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        for (int K = 0; K < J; ++K) cta_tile_mac(acc, own + K * TS, stg + K * TS, tr, tc);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float2* p = reinterpret_cast<float2*>(T + (2 * tc + j) * TP + 2 * tr);
+          float2 v = *p;
+          v.x -= acc[0][j]; v.y -= acc[1][j];
+          *p = v;
+        }
+        __syncthreads();
+      }
+      if (warp == 0) {
+        if (J == r - 1) CL_MARK(2);
+        cl_wait(&flagB[J]);
+        if (J == r - 1) CL_MARK(3);
+        fetch_tile_warp(gtile(J, J), ljj, lane);
+        rd_stage[lane] = __ldcg(gR + J * TB + lane);
+        __syncwarp();
+        float x[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) x[c] = T[c * TP + lane];
+        warp_trsm_row(x, ljj, rd_stage);
+        float* gt = gtile(r, J);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) { T[c * TP + lane] = x[c]; gt[c * TB + lane] = x[c]; }
+        if (J == r - 1) {                     // all off-diagonal tiles of row r are published
+          cl_fence();
+          __syncwarp();
+          if (lane < NB && lane != r) cl_arrive_remote(&flagA[r], lane);
+        }
+        if (J == r - 1) CL_MARK(4);
+      }
+      __syncthreads();
+      {   // right-looking update of the diagonal tile: T_rr -= L_rJ L_rJ^T
+        float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        cta_tile_mac(acc, T, T, tr, tc);
+        float* Td = own + r * TS;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float2* p = reinterpret_cast<float2*>(Td + (2 * tc + j) * TP + 2 * tr);
+          float2 v = *p;
+          v.x -= acc[0][j]; v.y -= acc[1][j];
+          *p = v;
+        }
+      }
+      if (Lg && warp == 1) store_tile_rowmajor(T, Lg + (long long)(r * TB) * g + J * TB, g, lane);
+    }
+    __syncthreads();
+    CL_MARK(5);
+    // ------------------------------------------------------------------ diagonal tile
+    if (warp == 0) {
+      float* T = own + r * TS;
+      CL_MARK(6);
+      int bad = 0;
+      warp_potrf32_bc(T, rd_own, bcast, lane, bad);
+      CL_MARK(7);
+      if (bad && lane == 0 && info) atomicCAS(&info[WC_INFO_NOT_PD], 0, grp * g + r * TB + bad);
+      __syncwarp();
+      publish_tile(T, gtile(r, r), lane);
+      gR[r * TB + lane] = rd_own[lane];
+      cl_fence();
+      __syncwarp();
+      if (lane < NB && lane != r) cl_arrive_remote(&flagB[r], lane);
+      CL_MARK(8);
+      // inv(L_rr): row `lane` of L^-T = column `lane` of L^-1
+      float x[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.f : 0.f;
+      warp_trsm_row(x, T, rd_own);
+      float* D = stile;                       // column-major: element (row c, col lane)
+      float* Xr = xcol + r * TS;              // row-major
+#pragma unroll
+      for (int c = 0; c < 32; ++c) { D[lane * TP + c] = x[c]; Xr[c * TP + lane] = x[c]; }
+      __syncwarp();
+      publish_tile(D, gD + r * GT, lane);
+      cl_fence();
+      __syncwarp();
+      if (lane < NB && lane != r) cl_arrive_remote(&flagD[r], lane);
+      CL_MARK(9);
+      store_tile_rowmajor(D, Xg + (long long)(r * TB) * g + r * TB, g, lane);
+      if (Lg) store_tile_rowmajor(T, Lg + (long long)(r * TB) * g + r * TB, g, lane);
+    }
+    __syncthreads();
+    CL_MARK(10);
+    // ------------------------------------------------------------------ block column r of X
+    for (int I = r + 1; I < NB; ++I) {
+      cl_wait(&flagA[I]);
+      if (I == NB - 1) CL_MARK(11);
+      const int np = I - r;
+      cta_fetch_tiles(gtile(I, r), np, stg, t);      // L_IK, K = r .. I-1
+      __syncthreads();
+      {   // S = sum_K L_IK X_Kr  (row-major)
+        float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        for (int w = 0; w < np; ++w) cta_tile_mac(acc, stg + w * TS, xcol + (r + w) * TS, tr, tc);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          *reinterpret_cast<float2*>(stile + (2 * tr + i) * TP + 2 * tc) = make_float2(acc[i][0], acc[i][1]);
+      }
+      if (I == NB - 1) CL_MARK(12);
+      cl_wait(&flagD[I]);
+      if (I == NB - 1) CL_MARK(13);
+      cta_fetch_tiles(gD + I * GT, 1, ljj, t);       // inv(L_II), column-major
+      __syncthreads();
+      {   // X_Ir = -inv(L_II) S
+        float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        cta_tile_mac(acc, ljj, stile, tr, tc);
+        float* Xi = xcol + I * TS;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          *reinterpret_cast<float2*>(Xi + (2 * tr + i) * TP + 2 * tc) = make_float2(-acc[i][0], -acc[i][1]);
+      }
+      __syncthreads();
+      {   // row-major tile -> output rows, 128-bit coalesced
+        const int row = t >> 3, q8 = t & 7;
+        *reinterpret_cast<float4*>(Xg + (long long)(I * TB + row) * g + r * TB + 4 * q8) =
+            *reinterpret_cast<const float4*>(xcol + I * TS + row * TP + 4 * q8);
+      }
+    }
+  }
+  CL_MARK(14);
+  cl_sync();      // nobody leaves while a peer may still arrive on its flags
+  CL_MARK(15);
+}
+
+size_t chol_cluster_scratch_floats(int g) {
+  const int NB = g / TB;
+  return (size_t)(NB * (NB + 1) / 2 + NB) * GT + (size_t)NB * TB;
+}
+inline bool chol_cluster_ok(int g, const float* Xout) { return Xout && (g % TB) == 0 && g >= 128 && g <= TB * CLN; }
+
 }  // namespace
 
+// scratch floats the factorisation needs besides its outputs: the padded inverse when g is not a multiple of 32, the
+// published tiles of the cluster kernel when g >= 128
 size_t wc_chol_pad_floats(int C, int g) {
   int NB = (g + TB - 1) / TB, gp = NB * TB;
-  return gp == g ? 0 : (size_t)(C / g) * gp * gp;
+  if (gp != g) return (size_t)(C / g) * gp * gp;
+  return (g >= 128 && g <= TB * CLN) ? (size_t)(C / g) * chol_cluster_scratch_floats(g) : 0;
 }
 
 // Ain (G,g,g) SPD -> Lout (G,g,g) lower factor (nullable), Xout (G,g,g) = L^-1 (nullable). Xpad: scratch of
@@ -437,6 +797,18 @@ size_t wc_chol_pad_floats(int C, int g) {
 int wc_chol_inv_launch(const float* Ain, int C, int g, float* Lout, float* Xout, float* Xpad, int32_t* info, cudaStream_t st) {
   if (g > 256) return WC_E_UNSUPPORTED;
   const int NB = (g + TB - 1) / TB;
+  if (chol_cluster_ok(g, Xout) && !(wc_debug_flags() & 2048)) {
+    if (!Xpad) return WC_E_ARG;
+    const size_t csm = (size_t)(2 * CLN + 2 + CLW) * TS * sizeof(float);
+    static bool cattr = false;
+    if (!cattr) {
+      WC_CUDA(cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+      cattr = true;
+    }
+    chol_cluster_kernel<<<(C / g) * CLN, CLW * 32, csm, st>>>(Ain, g, Xpad, (long long)chol_cluster_scratch_floats(g), Lout, Xout, info, wc_debug_flags() & 1);
+    WC_CHECK_LAUNCH();
+    return 0;
+  }
   size_t smem = ((size_t)(NB * (NB + 1) / 2 + NB) * TS + (size_t)NB * TB) * sizeof(float);
   static size_t attr_smem = 0;
   if (smem > 48 * 1024 && smem > attr_smem) {
@@ -460,6 +832,9 @@ int wc_chol_inv_launch(const float* Ain, int C, int g, float* Lout, float* Xout,
   return 0;
 }
 
+extern "C" int wc_debug_chol_cluster_timing(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_cl_ts, sizeof(unsigned long long) * CLN * 32);
+}
 extern "C" int wc_debug_chol_timing(long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g_chol_ts, sizeof(long long) * 64);
 }

@@ -525,7 +525,7 @@ int factor_matrix(const float* Ashr, int C, int g, int decomposition, float* Wm,
                   float* L /*scratch or output*/, float* Bm, float* Us, float* Xpad, int32_t* info, cudaStream_t st) {
   const int G = C / g;
   long long total = (long long)C * g;
-  if (decomposition == WC_DECOMP_CHOLESKY) return wc_chol_inv_launch(Ashr, C, g, sqrt_out ? sqrt_out : L, Wm, Xpad, info, st);
+  if (decomposition == WC_DECOMP_CHOLESKY) return wc_chol_inv_launch(Ashr, C, g, sqrt_out, Wm, Xpad, info, st);   // L only on request
   int rcc = wc_chol_inv_launch(Ashr, C, g, L, nullptr, Xpad, info, st);
   if (rcc) return rcc;
   jacobi_kernel<<<G, 1024, 0, st>>>(L, g, Bm, U, lam, info);

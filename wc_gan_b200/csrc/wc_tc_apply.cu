@@ -45,7 +45,7 @@ struct TcApplyParams {
   int N, HW, tiles_per_sample;
   long long total_tiles;
   const int32_t* cls; int K; int32_t* info;
-  unsigned long long* dbg;
+  unsigned long long* dbg; int dbg_flags;   // debug marks / experiment switches (0 in normal use)
 };
 
 template <int C>
@@ -127,8 +127,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
           {
             const int s = ia % NSTG;
             mbar_wait(&stg_empty[s], ((ia / NSTG) & 1) ^ 1);
-            mbar_arrive_expect_tx(&stg_full[s], STG_BYTES);
-            tma_load_3d(smem + s * STG_BYTES, sg == 0 ? &tm_a0 : &tm_a1, kb * KB, ti.r0, ti.sample, &stg_full[s]);
+            if (p.dbg_flags & 1024) mbar_arrive(&stg_full[s]);
+            else {
+              mbar_arrive_expect_tx(&stg_full[s], STG_BYTES);
+              tma_load_3d(smem + s * STG_BYTES, sg == 0 ? &tm_a0 : &tm_a1, kb * KB, ti.r0, ti.sample, &stg_full[s]);
+            }
             ++ia;
           }
           {
@@ -136,9 +139,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
             const uint8_t* src = p.seg[sg].Bp + (long long)ti.slot * p.seg[sg].slot_stride + (long long)kb * (2 * cfg::B_IMG);
             mbar_wait(&bop_empty[s], ((ib / NBOP) & 1) ^ 1);
             uint8_t* dst = smem + cfg::OFF_BOP + s * 2 * cfg::B_IMG;
-            mbar_arrive_expect_tx(&bop_full[s], 2 * cfg::B_IMG);
-            bulk_g2s(dst, src, cfg::B_IMG, &bop_full[s]);
-            bulk_g2s(dst + cfg::B_IMG, src + cfg::B_IMG, cfg::B_IMG, &bop_full[s]);
+            if ((p.dbg_flags & 64) && ib >= NBOP) mbar_arrive(&bop_full[s]);
+            else {
+              mbar_arrive_expect_tx(&bop_full[s], 2 * cfg::B_IMG);
+              bulk_g2s(dst, src, cfg::B_IMG, &bop_full[s]);
+              bulk_g2s(dst + cfg::B_IMG, src + cfg::B_IMG, cfg::B_IMG, &bop_full[s]);
+            }
             ++ib;
           }
         }
@@ -170,9 +176,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
             const uint64_t dal = make_desc(a_lo + kk * 32, 16, 8 * KB * 2, LAYOUT_SW64);
             const uint64_t dbh = make_desc(b_hi + kk * 32, 16, 8 * KB * 2, LAYOUT_SW64);
             const uint64_t dbl = make_desc(b_lo + kk * 32, 16, 8 * KB * 2, LAYOUT_SW64);
-            umma_bf16(tacc, dah, dbh, idesc, acc);
-            umma_bf16(tacc, dah, dbl, idesc, 1);
-            umma_bf16(tacc, dal, dbh, idesc, 1);
+            if (!(p.dbg_flags & 256)) {
+              umma_bf16(tacc, dah, dbh, idesc, acc);
+              umma_bf16(tacc, dah, dbl, idesc, 1);
+              umma_bf16(tacc, dal, dbh, idesc, 1);
+            }
             acc = 1;
           }
           umma_commit(&aop_empty[sa]);     // both operand stages are reusable once these MMAs have read them
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
         }
         fence_proxy_async();
         asm volatile("bar.sync 2, %0;" ::"n"(NEPI));
-        if (te == 0) {
+        if (te == 0 && !(p.dbg_flags & 512)) {
           tma_store_3d(&tm_out, c0, ti.r0, ti.sample, smem + cfg::OFF_EPI + eb * STG_BYTES);
           bulk_commit_group();
         }
@@ -247,8 +255,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
         const float4 m1 = *reinterpret_cast<const float4*>(&smean[sg][kb * KB + cch * 8 + 4]);
         mbar_wait(&stg_full[s], (ia / NSTG) & 1);
         uint32_t hi[2][4], lo[2][4];
+        const bool skipc = p.dbg_flags & 128;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+          if (skipc) continue;
           float4 a = lds128(stg_u32 + s * STG_BYTES + ld_off[h][0]);
           float4 b = lds128(stg_u32 + s * STG_BYTES + ld_off[h][1]);
           a.x -= m0.x; a.y -= m0.y; a.z -= m0.z; a.w -= m0.w; b.x -= m1.x; b.y -= m1.y; b.z -= m1.z; b.w -= m1.w;
@@ -263,6 +273,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
         const uint32_t dst = aop_u32 + sa * 2 * cfg::A_IMG;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+          if (skipc) continue;
           sts128(dst + st_off[h], hi[h][0], hi[h][1], hi[h][2], hi[h][3]);
           sts128(dst + cfg::A_IMG + st_off[h], lo[h][0], lo[h][1], lo[h][2], lo[h][3]);
         }
@@ -353,7 +364,7 @@ int launch_tc_apply(TcApplyParams& p, const float* a0, const float* a1, float* o
   p.N = N; p.HW = HW;
   p.tiles_per_sample = wc_cdiv(HW, TILE_M);
   p.total_tiles = (long long)N * p.tiles_per_sample;
-  p.dbg = wc_debug_buf();
+  p.dbg = wc_debug_buf(); p.dbg_flags = wc_debug_flags();
   alignas(64) CUtensorMap tm_a0, tm_a1, tm_out;
   int rc = make_act_map(&tm_a0, a0, N, HW, C);
   if (!rc) rc = make_act_map(&tm_a1, a1 ? a1 : a0, N, HW, C);

@@ -43,11 +43,11 @@ k3 = lambda i: chk(lib.wc_apply_fwd(ptr(xs[i % NB]), N, HW, C, C, ptr(mean), ptr
 k6 = lambda i: chk(lib.wc_apply_bwd(ptr(xs[i % NB]), ptr(dys[i % NB]), N, HW, C, C, ptr(mean), ptr(T), ptr(A), ptr(pb), ptr(b), C, None, 1, ptr(outs[i % 2]), st))
 
 print('gram kernels: bit2 no red.global, bit4 no MMA, bit8 no convert')
-for flags in (0, 2, 4, 8, 2 | 4, 4 | 8, 2 | 4 | 8):
+for flags in (0, 16, 2, 4, 8, 2 | 4, 4 | 8, 2 | 4 | 8):
     lib.wc_debug_set(flags)
     print(f'  flags {flags:5d}  K1 {timeit(k1):6.1f} us   K4 {timeit(k4):6.1f} us', flush=True)
 print('apply kernels: 64 no B reload, 128 no convert, 256 no MMA, 512 no store, 1024 no A load')
-for flags in (0, 64, 128, 256, 512, 1024, 64 | 256, 64 | 128 | 256, 64 | 128 | 256 | 512, 64 | 128 | 256 | 1024, 64 | 128 | 256 | 512 | 1024,
+for flags in (0, 2048, 4096, 64, 128, 256, 512, 1024, 64 | 256, 64 | 128 | 256, 64 | 128 | 256 | 512, 64 | 128 | 256 | 1024, 64 | 128 | 256 | 512 | 1024,
               128 | 256 | 512 | 1024):
     lib.wc_debug_set(flags)
     print(f'  flags {flags:5d}  K3 {timeit(k3):6.1f} us   K6 {timeit(k6):6.1f} us', flush=True)

@@ -73,6 +73,10 @@ struct WcSmm {
 };
 int wc_smm_launch(const WcSmm& p, cudaStream_t st);
 
+// tensor-map encoder for the TMA kernels (wc_tc_apply.cu)
+int wc_make_f32_map3(void* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                     uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
+
 // tiled Cholesky + inverse (wc_chol.cu)
 size_t wc_chol_pad_floats(int C, int g);
 int wc_chol_inv_launch(const float* Ain, int C, int g, float* Lout, float* Xout, float* Xpad, int32_t* info, cudaStream_t st);

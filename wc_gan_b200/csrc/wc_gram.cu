@@ -327,7 +327,7 @@ StatsPlan plan_stats(int64_t M, int C, int g) {
 bool wc_tc_gram_ok(int Cin, int Cout);
 int wc_tc_gram_self(const float* x, long long M, int C, int g, float* pivot_out, float* Sp, float* sums, cudaStream_t st);
 int wc_tc_gram_cross(const float* x, const float* dy, int N, int HW, int C, const float* mean, const int32_t* order,
-                     const int32_t* slot_of, float* P, float* s, cudaStream_t st);
+                     const int32_t* slot_of, int K, float* P, float* s, cudaStream_t st);
 
 static bool g_use_tc_gram = true;
 extern "C" void wc_set_tensor_core_gram(int enable) { g_use_tc_gram = enable != 0; }
@@ -412,11 +412,15 @@ extern "C" int wc_reduce_bwd(const float* x, const float* dy, int N, int HW, int
     class_order_kernel<<<1, 1024, K * sizeof(int), st>>>(cls, N, K, order, slot_of);
     WC_CHECK_LAUNCH();
   }
-  WC_CUDA(cudaMemsetAsync(P, 0, (size_t)K * Cin * Cout * 4, st));
-  WC_CUDA(cudaMemsetAsync(s, 0, (size_t)K * Cout * 4, st));
+  if (s == P + (size_t)K * Cin * Cout) {   // P | s contiguous (wc_layer_bwd's workspace): one memset
+    WC_CUDA(cudaMemsetAsync(P, 0, ((size_t)K * Cin * Cout + (size_t)K * Cout) * 4, st));
+  } else {
+    WC_CUDA(cudaMemsetAsync(P, 0, (size_t)K * Cin * Cout * 4, st));
+    WC_CUDA(cudaMemsetAsync(s, 0, (size_t)K * Cout * 4, st));
+  }
   if (g_use_tc_gram && wc_tc_gram_ok(Cin, Cout) && wc_aligned16(x) && wc_aligned16(dy) && wc_aligned16(P) &&
       (!mean || wc_aligned16(mean)))
-    return wc_tc_gram_cross(x, dy, N, HW, Cin, mean, order, slot_of, P, s, st);
+    return wc_tc_gram_cross(x, dy, N, HW, Cin, mean, order, slot_of, cond ? K : 1, P, s, st);
   GramParams p{};
   p.A = x; p.B = dy; p.lda = Cin; p.ldb = Cout; p.ma = mean; p.mb = nullptr; p.nI = Cin; p.nJ = Cout;
   p.grouped = 0; p.g = Cin; p.tw = TI; p.tpg = 1;

@@ -107,6 +107,11 @@ __device__ __forceinline__ void tma_store_3d(const void* tmap, int c0, int c1, i
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0), "r"(c1),
                "r"(c2), "r"(smem_u32(smem_src)) : "memory");
 }
+// shared -> global box reduction (element-wise add performed by the L2); same completion mechanism as the store
+__device__ __forceinline__ void tma_reduce_add_3d(const void* tmap, int c0, int c1, int c2, uint32_t smem_src) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0),
+               "r"(c1), "r"(c2), "r"(smem_src) : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }

@@ -26,11 +26,16 @@ namespace {
 constexpr int KB = 32;                 // K elements per stage (64-byte bf16 rows, SWIZZLE_64B)
 constexpr int TILE_M = 128;
 constexpr int NCONV_WARPS = 8, NEPI_WARPS = 4;
-constexpr int W_PROD = 0, W_MMA = 1, W_EPI0 = 2, W_CONV0 = W_EPI0 + NEPI_WARPS;
-constexpr int NTHREADS = (W_CONV0 + NCONV_WARPS) * 32;
+constexpr int W_PROD = 0, W_MMA = 1, W_EPI0 = 2, W_CONV0 = W_EPI0 + NEPI_WARPS, W_BPROD = W_CONV0 + NCONV_WARPS;
+constexpr int NTHREADS = (W_BPROD + 1) * 32;
 constexpr int NCONV = NCONV_WARPS * 32, NEPI = NEPI_WARPS * 32;
 constexpr int STG_BYTES = TILE_M * KB * 4;   // one fp32 activation box: 16 KB
-constexpr int NSTG = 4, NAOP = 3, NBOP = 2, NEPIBUF = 2;
+constexpr int NEPIBUF = 2;
+// ring depths <activation staging, A operand, B operand>: the default and two alternatives kept for experiments
+// (wc_debug_set bits 2048 / 4096)
+struct Rings0 { static constexpr int NSTG = 5, NAOP = 2, NBOP = 2; };
+struct Rings1 { static constexpr int NSTG = 4, NAOP = 2, NBOP = 3; };
+struct Rings2 { static constexpr int NSTG = 6, NAOP = 2, NBOP = 2; };
 
 struct TcSeg {
   const float* mean;     // per-channel shift (nullable)
@@ -48,8 +53,9 @@ struct TcApplyParams {
   unsigned long long* dbg; int dbg_flags;   // debug marks / experiment switches (0 in normal use)
 };
 
-template <int C>
+template <int C, class R>
 struct Cfg {
+  static constexpr int NSTG = R::NSTG, NAOP = R::NAOP, NBOP = R::NBOP;
   static constexpr int N = C;
   static constexpr int NKB = C / KB;                       // K blocks per segment
   static constexpr int A_IMG = TILE_M * KB * 2;            // 8 KB: one bf16 split of an A tile
@@ -82,17 +88,17 @@ __device__ __forceinline__ TileInfo tile_info(const TcApplyParams& p, long long 
   return ti;
 }
 
-template <int C>
+template <int C, class R>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, const __grid_constant__ CUtensorMap tm_a0,
                                                                const __grid_constant__ CUtensorMap tm_a1,
                                                                const __grid_constant__ CUtensorMap tm_out) {
-  using cfg = Cfg<C>;
+  using cfg = Cfg<C, R>;
+  constexpr int NSTG = cfg::NSTG, NAOP = cfg::NAOP, NBOP = cfg::NBOP;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t stg_full[NSTG], stg_empty[NSTG], aop_full[NAOP], aop_empty[NAOP], bop_full[NBOP], bop_empty[NBOP],
       acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float smean[2][C];
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int total_kb = p.nseg * cfg::NKB;
@@ -106,10 +112,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
     tma_prefetch_desc(&tm_a0); tma_prefetch_desc(&tm_a1); tma_prefetch_desc(&tm_out);
   }
   if (warp == W_MMA) { tmem_alloc(&tmem_slot, cfg::TMEM_COLS); tmem_relinquish(); }
-  for (int i = t; i < 2 * C; i += NTHREADS) {
-    const int sg = i / C, ch = i % C;
-    smean[sg][ch] = (sg < p.nseg && p.seg[sg].mean) ? p.seg[sg].mean[ch] : 0.f;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -117,35 +119,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
   if (t == 0) wc_mark(p.dbg, 0);
 
   if (warp == W_PROD) {
-    // ------------------------------------------------------------------ producer
+    // ------------------------------------------------------------------ activation producer
+    // (its own thread: the staging ring runs NSTG boxes ahead of the converters, independent of the B ring)
     if (lane == 0) {
-      uint32_t ia = 0, ib = 0;
+      uint32_t ia = 0;
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileInfo ti = tile_info(p, tile);
-        for (int it = 0; it < total_kb; ++it) {
+        for (int it = 0; it < total_kb; ++it, ++ia) {
           const int sg = it / cfg::NKB, kb = it % cfg::NKB;
-          {
-            const int s = ia % NSTG;
-            mbar_wait(&stg_empty[s], ((ia / NSTG) & 1) ^ 1);
-            if (p.dbg_flags & 1024) mbar_arrive(&stg_full[s]);
-            else {
-              mbar_arrive_expect_tx(&stg_full[s], STG_BYTES);
-              tma_load_3d(smem + s * STG_BYTES, sg == 0 ? &tm_a0 : &tm_a1, kb * KB, ti.r0, ti.sample, &stg_full[s]);
-            }
-            ++ia;
+          const int s = ia % NSTG;
+          mbar_wait(&stg_empty[s], ((ia / NSTG) & 1) ^ 1);
+          if (p.dbg_flags & 1024) mbar_arrive(&stg_full[s]);
+          else {
+            mbar_arrive_expect_tx(&stg_full[s], STG_BYTES);
+            tma_load_3d(smem + s * STG_BYTES, sg == 0 ? &tm_a0 : &tm_a1, kb * KB, ti.r0, ti.sample, &stg_full[s]);
           }
-          {
-            const int s = ib % NBOP;
-            const uint8_t* src = p.seg[sg].Bp + (long long)ti.slot * p.seg[sg].slot_stride + (long long)kb * (2 * cfg::B_IMG);
-            mbar_wait(&bop_empty[s], ((ib / NBOP) & 1) ^ 1);
-            uint8_t* dst = smem + cfg::OFF_BOP + s * 2 * cfg::B_IMG;
-            if ((p.dbg_flags & 64) && ib >= NBOP) mbar_arrive(&bop_full[s]);
-            else {
-              mbar_arrive_expect_tx(&bop_full[s], 2 * cfg::B_IMG);
-              bulk_g2s(dst, src, cfg::B_IMG, &bop_full[s]);
-              bulk_g2s(dst + cfg::B_IMG, src + cfg::B_IMG, cfg::B_IMG, &bop_full[s]);
-            }
-            ++ib;
+        }
+      }
+    }
+  } else if (warp == W_BPROD) {
+    // ------------------------------------------------------------------ matrix-image producer (L2-resident source)
+    if (lane == 0) {
+      uint32_t ib = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileInfo ti = tile_info(p, tile);
+        for (int it = 0; it < total_kb; ++it, ++ib) {
+          const int sg = it / cfg::NKB, kb = it % cfg::NKB;
+          const int s = ib % NBOP;
+          const uint8_t* src = p.seg[sg].Bp + (long long)ti.slot * p.seg[sg].slot_stride + (long long)kb * (2 * cfg::B_IMG);
+          mbar_wait(&bop_empty[s], ((ib / NBOP) & 1) ^ 1);
+          uint8_t* dst = smem + cfg::OFF_BOP + s * 2 * cfg::B_IMG;
+          if ((p.dbg_flags & 64) && ib >= NBOP) mbar_arrive(&bop_full[s]);
+          else {
+            mbar_arrive_expect_tx(&bop_full[s], 2 * cfg::B_IMG);
+            bulk_g2s(dst, src, cfg::B_IMG, &bop_full[s]);
+            bulk_g2s(dst + cfg::B_IMG, src + cfg::B_IMG, cfg::B_IMG, &bop_full[s]);
           }
         }
       }
@@ -189,7 +197,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
         umma_commit(&acc_full[ab]);        // accumulator complete
       }
     }
-  } else if (warp < W_CONV0) {
+  } else if (warp >= W_EPI0 && warp < W_CONV0) {
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int te = t - W_EPI0 * 32;
     const int q = warp & 3;                // TMEM lanes 32q .. 32q+31 are the ones this warp may read
@@ -251,8 +259,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
       for (int it = 0; it < total_kb; ++it, ++ia) {
         const int sg = it / cfg::NKB, kb = it % cfg::NKB;
         const int s = ia % NSTG, sa = ia % NAOP;
-        const float4 m0 = *reinterpret_cast<const float4*>(&smean[sg][kb * KB + cch * 8]);
-        const float4 m1 = *reinterpret_cast<const float4*>(&smean[sg][kb * KB + cch * 8 + 4]);
+        float4 m0 = make_float4(0.f, 0.f, 0.f, 0.f), m1 = m0;       // per-channel shift: 64 bytes per stage, L1-resident
+        if (const float* mp = p.seg[sg].mean) {
+          m0 = __ldg(reinterpret_cast<const float4*>(mp + kb * KB + cch * 8));
+          m1 = __ldg(reinterpret_cast<const float4*>(mp + kb * KB + cch * 8 + 4));
+        }
         mbar_wait(&stg_full[s], (ia / NSTG) & 1);
         uint32_t hi[2][4], lo[2][4];
         const bool skipc = p.dbg_flags & 128;
@@ -345,16 +356,21 @@ EncodeTiledFn encode_tiled_fn() {
 
 // fp32 activations viewed as [N][HW][C]; box = 128 rows x 32 channels of one sample, SWIZZLE_128B
 int make_act_map(CUtensorMap* tm, const float* base, int N, int HW, int C) {
-  EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc) return WC_E_UNSUPPORTED;
-  const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)HW, (cuuint64_t)N};
-  const cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)HW * C * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)TILE_M, 1};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : WC_E_UNSUPPORTED;
+  return wc_make_f32_map3(tm, base, (uint64_t)C, (uint64_t)HW, (uint64_t)N, (uint64_t)C * 4, (uint64_t)HW * C * 4, KB, TILE_M);
+}
+
+template <int C, class R>
+int launch_tc_apply_r(const TcApplyParams& p, const CUtensorMap& tm_a0, const CUtensorMap& tm_a1, const CUtensorMap& tm_out,
+                      cudaStream_t st) {
+  static bool attr_set = false;   // idempotent; a race only repeats the same call
+  if (!attr_set) {
+    WC_CUDA(cudaFuncSetAttribute(tc_apply_kernel<C, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<C, R>::SMEM));
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)(p.total_tiles < WC_NUM_SMS ? p.total_tiles : WC_NUM_SMS);
+  tc_apply_kernel<C, R><<<grid, NTHREADS, Cfg<C, R>::SMEM, st>>>(p, tm_a0, tm_a1, tm_out);
+  WC_CHECK_LAUNCH();
+  return 0;
 }
 
 template <int C>
@@ -370,20 +386,30 @@ int launch_tc_apply(TcApplyParams& p, const float* a0, const float* a1, float* o
   if (!rc) rc = make_act_map(&tm_a1, a1 ? a1 : a0, N, HW, C);
   if (!rc) rc = make_act_map(&tm_out, out, N, HW, C);
   if (rc) return rc;
-  static bool attr_set = false;   // idempotent; a race only repeats the same call
-  if (!attr_set) {
-    WC_CUDA(cudaFuncSetAttribute(tc_apply_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<C>::SMEM));
-    attr_set = true;
-  }
-  const unsigned grid = (unsigned)(p.total_tiles < WC_NUM_SMS ? p.total_tiles : WC_NUM_SMS);
-  tc_apply_kernel<C><<<grid, NTHREADS, Cfg<C>::SMEM, st>>>(p, tm_a0, tm_a1, tm_out);
-  WC_CHECK_LAUNCH();
-  return 0;
+  if (p.dbg_flags & 2048) return launch_tc_apply_r<C, Rings1>(p, tm_a0, tm_a1, tm_out, st);
+  if (p.dbg_flags & 4096) return launch_tc_apply_r<C, Rings2>(p, tm_a0, tm_a1, tm_out, st);
+  return launch_tc_apply_r<C, Rings0>(p, tm_a0, tm_a1, tm_out, st);
 }
 
 bool tc_shape_ok(int Cin, int Cout) { return Cin == Cout && (Cin == 128 || Cin == 256); }
 
 }  // namespace
+
+// 3-D fp32 tensor map [d2][d1][d0] (d0 contiguous), box = box1 x box0 elements of one d2 index, SWIZZLE_128B
+// (box0 * 4 must be 128 bytes).  `tm` points at a 64-byte aligned CUtensorMap.
+int wc_make_f32_map3(void* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                     uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return WC_E_UNSUPPORTED;
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  const cuuint32_t box[3] = {box0, box1, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc((CUtensorMap*)tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : WC_E_UNSUPPORTED;
+}
 
 extern "C" size_t wc_pack_bytes(int C, int K, int nseg_shared) {
   if (!tc_shape_ok(C, C) || K <= 0) return 0;

@@ -19,6 +19,7 @@
 //   warp  17   MMA issuer (one thread), owns TMEM
 #include "wc_common.cuh"
 #include "wc_tc.cuh"
+#include <cuda.h>
 
 using namespace wctc;
 
@@ -42,6 +43,7 @@ struct TcGramParams {
   float* out; long long out_slot_stride;          // [slot][C][C]
   float* asum; float* bsum; long long sum_slot_stride;
   float* pivot_out;                     // self mode: the pivot every CTA used (written by CTA 0)
+  int nslots;                           // number of [C][C] accumulators behind `out`
   unsigned long long* dbg; int dbg_flags;   // debug marks (nullptr in normal use)
 };
 
@@ -53,7 +55,7 @@ struct GCfg {
   static constexpr int MH = C / 128;                       // M halves
   static constexpr int TMEM_COLS = MH * C;                 // 512 (C=256) / 128
   static constexpr int OPSTAGE = 4 * IMG;
-  static constexpr int NOPS = 3;
+  static constexpr int NOPS = (C == 128) ? 4 : 3;          // >= 64 KB: the flush borrows the idle ring (4 KB per warp)
   static constexpr int SMEM = NSLOTS * SLOT + NOPS * OPSTAGE + 1024;
   static constexpr int CQ = C / 4, RG = NCONV / CQ;        // pivot: threads per row, row groups
 };
@@ -98,7 +100,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 template <int C>
-__global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p) {
+__global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, const __grid_constant__ CUtensorMap tm_out) {
   using cfg = GCfg<C>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p) {
     mbar_init(&acc_full, 1);
     mbar_init(&acc_empty, NCONV_WARPS);
     mbar_fence_init();
+    tma_prefetch_desc(&tm_out);
   }
   if (warp == NCONV_WARPS + 1) { tmem_alloc(&tmem_slot, cfg::TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p) {
     // dy (operand B) of the same step; K1: the groups take alternate steps.  Within a group a warp owns 2 rows of the
     // slab; a lane owns the 4-channel quads {lane, lane+32} of a row (conflict-free ld.shared.v4 / st.shared.v2).
     const int grp = warp >> 3, wg = warp & 7;
+    const uint32_t stg_u32 = smem_u32(stg), ops_u32 = smem_u32(ops);
     constexpr int QPR = C / 128;              // quads per lane per row
     const int my_op = p.self ? 0 : grp;
     const bool want = my_op == 0 ? (p.asum != nullptr) : (p.bsum != nullptr);
@@ -239,7 +243,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p) {
         for (int j = 0; j < QPR; ++j) mean[j] = *reinterpret_cast<const float4*>(m + (lane + 32 * j) * 4);
       }
     }
-    const uint32_t stg_u32 = smem_u32(stg), ops_u32 = smem_u32(ops);
     const int r0 = wg * 2;                                        // this warp's rows of a slab: r0, r0 + 1
     const uint32_t ld_off = (uint32_t)r0 * (C * 4) + (uint32_t)lane * 16;
     // MN-major SWIZZLE_128B: quad qd of k-row r -> block qd/16, 16-byte chunk (qd%16)/2 XOR (r%8), half qd%2
@@ -259,6 +262,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p) {
       float* out = p.out + (long long)slot * p.out_slot_stride;
       // CTAs start at different chunks so that at any moment they add into different L2 lines
       const int nsteps = cfg::MH * NCH, rot = (int)(blockIdx.x % nsteps);
+      // The accumulator leaves as 32 x 32 boxes: tcgen05.ld -> swizzled 4 KB tile in this warp's slice of the (idle)
+      // operand ring -> one TMA reduce-add into the global matrix.  The L2 adds whole 128-byte lines instead of
+      // 16-byte vector reductions.  (experiment bit 16: the older red.global.add.v4 path)
+      const bool use_tma = !(p.dbg_flags & 16);
+      const uint32_t fbuf = ops_u32 + (uint32_t)warp * 4096u;
+      const uint32_t frow = fbuf + (uint32_t)lane * 128u;
 #pragma unroll 1
       for (int k = 0; k < nsteps; ++k) {
         const int kk = (k + rot) % nsteps;
@@ -269,14 +278,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p) {
         if (p.self) { clo = (i0 / p.g) * p.g; chi = min(((i0 + 31) / p.g + 1) * p.g, i0 + 32); }
         if (c0 >= chi || c0 + 32 <= clo) continue;   // warp-uniform
         float acc[32];
+        if (use_tma) {
+          if (lane == 0) bulk_wait_group_read<0>();   // the previous box has left the tile
+          __syncwarp();
+        }
         tmem_ld32(td + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * C + c0), acc);
-        float* dst = out + (long long)i * C + c0;
+        if (use_tma) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) if (!(p.dbg_flags & 2)) red_add_v4(dst + j, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(frow + ((j ^ (lane & 7)) << 4)), "f"(acc[4 * j]),
+                         "f"(acc[4 * j + 1]), "f"(acc[4 * j + 2]), "f"(acc[4 * j + 3]) : "memory");
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && !(p.dbg_flags & 2)) {
+            tma_reduce_add_3d(&tm_out, c0, i0, slot, fbuf);
+            bulk_commit_group();
+          }
+        } else {
+          float* dst = out + (long long)i * C + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) if (!(p.dbg_flags & 2)) red_add_v4(dst + j, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        }
+      }
+      if (use_tma) {
+        // the tiles live in the operand ring: nobody may refill it before every box has been read out
+        if (lane == 0) bulk_wait_group_read<0>();
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty);
+      if (use_tma) asm volatile("bar.sync 1, %0;" ::"n"(NCONV));
       // column sums: every warp holds partial sums of all channels of its operand
       for (int pass = 0; pass < 2; ++pass) {
         float* gsum = pass == 0 ? p.asum : p.bsum;
@@ -352,6 +384,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p) {
     }
     if (t == 0) wc_mark(p.dbg, 1);
     flush(cur_slot, nflush & 1);
+    if (lane == 0) bulk_wait_group<0>();     // the reduce-adds have been performed, not just read out
     if (t == 0) wc_mark(p.dbg, 2);
   }
   tc_fence_before();
@@ -372,7 +405,12 @@ int launch_tc_gram(TcGramParams& p, cudaStream_t st) {
     WC_CUDA(cudaFuncSetAttribute(tc_gram_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, GCfg<C>::SMEM));
     attr_set = true;
   }
-  tc_gram_kernel<C><<<(unsigned)ctas, NTHREADS, GCfg<C>::SMEM, st>>>(p);
+  // the accumulators as [slot][C][C], 32 x 32 boxes
+  alignas(64) CUtensorMap tm_out;
+  const long long sstride = p.out_slot_stride ? p.out_slot_stride : (long long)C * C;
+  int rc = wc_make_f32_map3(&tm_out, p.out, C, C, (uint64_t)(p.nslots > 0 ? p.nslots : 1), (uint64_t)C * 4, (uint64_t)sstride * 4, 32, 32);
+  if (rc) return rc;
+  tc_gram_kernel<C><<<(unsigned)ctas, NTHREADS, GCfg<C>::SMEM, st>>>(p, tm_out);
   WC_CHECK_LAUNCH();
   return 0;
 }
@@ -390,19 +428,19 @@ int wc_tc_gram_self(const float* x, long long M, int C, int g, float* pivot_out,
   p.order = nullptr; p.slot_of = nullptr;
   p.out = Sp; p.out_slot_stride = 0;
   p.asum = sums; p.bsum = nullptr; p.sum_slot_stride = 0;
-  p.pivot_out = pivot_out;
+  p.pivot_out = pivot_out; p.nslots = 1;
   return C == 256 ? launch_tc_gram<256>(p, st) : launch_tc_gram<128>(p, st);
 }
 
 // P (K,C,C) and s (K,C) must be zero on entry.
 int wc_tc_gram_cross(const float* x, const float* dy, int N, int HW, int C, const float* mean, const int32_t* order,
-                     const int32_t* slot_of, float* P, float* s, cudaStream_t st) {
+                     const int32_t* slot_of, int K, float* P, float* s, cudaStream_t st) {
   TcGramParams p{};
   p.A = x; p.B = dy; p.ma = mean; p.mb = nullptr; p.self = 0; p.g = C;
   p.N = N; p.HW = HW;
   p.order = order; p.slot_of = slot_of;
   p.out = P; p.out_slot_stride = (long long)C * C;
   p.asum = nullptr; p.bsum = s; p.sum_slot_stride = C;
-  p.pivot_out = nullptr;
+  p.pivot_out = nullptr; p.nslots = K;
   return C == 256 ? launch_tc_gram<256>(p, st) : launch_tc_gram<128>(p, st);
 }

@@ -26,6 +26,13 @@ tot = sum(sum(v) for v in agg.values()) / 10
 print(f'total device time per step {tot:.1f} us')
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     print(f'{sum(v)/10:8.1f} us/step  n/step={len(v)/10:4.1f}  avg={sum(v)/len(v):7.1f} us  {k[:90]}')
+evs_sorted = sorted(evs, key=lambda e: e.time_range.start)
+per = len(evs_sorted) // 10
+print('--- one step in launch order (start offset us, duration us)')
+t0 = evs_sorted[-per].time_range.start
+for e in evs_sorted[-per:]:
+    d = e.device_time if hasattr(e, 'device_time') else e.cuda_time
+    print(f'{(e.time_range.start - t0):9.1f} {d:7.1f}  {e.name[:100]}')
 import time
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for i in range(50): step(i)

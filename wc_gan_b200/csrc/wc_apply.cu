@@ -127,6 +127,7 @@ __device__ __forceinline__ void run_term(const Term& T, int slot, long long row_
 
 template <bool kVec>
 __global__ void __launch_bounds__(NT) apply_kernel(ApplyParams p) {
+  wc_pdl_wait();
   __shared__ __align__(16) float As[KC][TM + PAD];
   __shared__ __align__(16) float Bs[KC][TN + PAD];
   const int sample = blockIdx.x / p.tiles_per_sample;
@@ -181,7 +182,7 @@ int launch_apply(ApplyParams& p, bool vec, cudaStream_t st) {
   long long gx = (long long)p.N * p.tiles_per_sample;
   if (gx > INT32_MAX) return WC_E_UNSUPPORTED;
   dim3 grid((unsigned)gx, wc_cdiv(p.Nout, TN));
-  if (vec) apply_kernel<true><<<grid, NT, 0, st>>>(p); else apply_kernel<false><<<grid, NT, 0, st>>>(p);
+  if (vec) WC_CUDA(wc_launch(apply_kernel<true>, grid, NT, 0, st, p)); else WC_CUDA(wc_launch(apply_kernel<false>, grid, NT, 0, st, p));
   WC_CHECK_LAUNCH();
   return 0;
 }

@@ -137,6 +137,7 @@ __device__ __forceinline__ void tri_index(int t, int& a, int& b) {   // t -> (a,
 __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float* __restrict__ Ain, int g, float* __restrict__ Lout,
                                                                     float* __restrict__ Xout, float* __restrict__ Xpad,
                                                                     int32_t* info, int split_inverse) {
+  wc_pdl_wait();
   extern __shared__ __align__(16) float sm[];
   const int NB = (g + TB - 1) / TB, gp = NB * TB;
   float* tiles = sm;                                  // NB(NB+1)/2 tiles
@@ -356,6 +357,7 @@ __global__ void __launch_bounds__(NW * 32, 1) chol_inv_tiled_kernel(const float*
 constexpr int TI_COLS = 8, TI_THREADS = 32 * TI_COLS, TI_LP = 260, TI_DP = 33, TI_NPRE = 7;
 
 __global__ void __launch_bounds__(TI_THREADS) trinv_kernel(const float* __restrict__ L, int g, float* __restrict__ X, unsigned long long* dbg, int dflags) {
+  wc_pdl_wait();
   extern __shared__ __align__(16) float sm[];
   const int NB = g / TB;
   const int slabs = g / TI_COLS;
@@ -587,6 +589,7 @@ __device__ __forceinline__ void cta_fetch_tiles(const float* gt, int n, float* d
 __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
     chol_cluster_kernel(const float* __restrict__ Ain, int g, float* __restrict__ scratch, long long scratch_stride,
                         float* __restrict__ Lout, float* __restrict__ Xout, int32_t* info, int dbg) {
+  wc_pdl_wait();
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t flagA[CLN], flagB[CLN], flagD[CLN];
   __shared__ __align__(16) float rd_own[TB], rd_stage[TB], bcast[2 * TB];
@@ -805,7 +808,7 @@ int wc_chol_inv_launch(const float* Ain, int C, int g, float* Lout, float* Xout,
       WC_CUDA(cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
       cattr = true;
     }
-    chol_cluster_kernel<<<(C / g) * CLN, CLW * 32, csm, st>>>(Ain, g, Xpad, (long long)chol_cluster_scratch_floats(g), Lout, Xout, info, wc_debug_flags() & 1);
+    WC_CUDA(wc_launch(chol_cluster_kernel, (C / g) * CLN, CLW * 32, csm, st, Ain, g, Xpad, (long long)chol_cluster_scratch_floats(g), Lout, Xout, info, wc_debug_flags() & 1));
     WC_CHECK_LAUNCH();
     return 0;
   }
@@ -817,7 +820,7 @@ int wc_chol_inv_launch(const float* Ain, int C, int g, float* Lout, float* Xout,
   }
   // g >= 128 (multiple of 32): the off-diagonal blocks of the inverse are formed by trinv_kernel on g/8 CTAs per group
   const bool split = Xout && Lout && g >= 128 && (g % TB) == 0;
-  chol_inv_tiled_kernel<<<C / g, NW * 32, smem, st>>>(Ain, g, Lout, Xout, Xpad, info, split ? 1 : 0);
+  WC_CUDA(wc_launch(chol_inv_tiled_kernel, C / g, NW * 32, smem, st, Ain, g, Lout, Xout, Xpad, info, split ? 1 : 0));
   WC_CHECK_LAUNCH();
   if (split) {
     size_t tsm = ((size_t)TB * TI_LP + (size_t)TB * TI_DP + (size_t)TI_COLS * g + (size_t)TB * (TI_COLS + 1)) * sizeof(float);
@@ -826,7 +829,7 @@ int wc_chol_inv_launch(const float* Ain, int C, int g, float* Lout, float* Xout,
       WC_CUDA(cudaFuncSetAttribute(trinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
       tattr = tsm;
     }
-    trinv_kernel<<<(C / g) * (g / TI_COLS), TI_THREADS, tsm, st>>>(Lout, g, Xout, wc_debug_buf(), wc_debug_flags());
+    WC_CUDA(wc_launch(trinv_kernel, (C / g) * (g / TI_COLS), TI_THREADS, tsm, st, Lout, g, Xout, wc_debug_buf(), wc_debug_flags()));
     WC_CHECK_LAUNCH();
   }
   return 0;

@@ -22,6 +22,27 @@ void wc_count_launch();
     if (e__ != cudaSuccess) return (int)e__;                \
   } while (0)
 
+// ---- launches with programmatic dependent launch (PDL) ---------------------------------------------------
+// Every kernel of this library starts with wc_pdl_wait() before it touches global memory and is launched with the
+// programmatic-stream-serialization attribute: the grid may be scheduled (and run its prologue) while its predecessor
+// on the stream is still draining, and blocks in wc_pdl_wait() until that predecessor has completed and its writes are
+// visible.  A layer step is ~20 dependent launches; this hides their launch latency.  wc_debug_set bit 8192 turns it off.
+__device__ __forceinline__ void wc_pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool wc_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t wc_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = wc_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- debug-only instrumentation (not part of include/wc_b200.h) ---------------------------------------
 // wc_debug_set(flags): bit0 = kernels record globaltimer marks into a device buffer [block][slot] (allocated by
 // wc_debug_set, the only place this library allocates); other bits are kernel-specific experiment switches.
@@ -72,6 +93,16 @@ struct WcSmm {
   int tri;                     // 0 none, 1 keep lower (incl. diag) of C, 2 keep upper (incl. diag); others zeroed
 };
 int wc_smm_launch(const WcSmm& p, cudaStream_t st);
+
+// stage functions with the operand packing of the tcgen05 apply kernels folded in (wc_small.cu; used by wc_layer.cu)
+int wc_compose_fwd_impl(const float* Weff, int Cin, int Cout, int g, int K, const float* Wu, const float* bu,
+                        const float* Wc, const float* bc, int triangular, const float* class_matrix,
+                        const float* D, int E, const float* bf, float* ehat, float* Wk, float* T, float* b,
+                        void* Tp_fwd, void* Tp_bwd, cudaStream_t st);
+int wc_factor_bwd_impl(const float* dWeff, const float* gbar, const float* Weff, const float* Wm, const float* R,
+                       const float* U, const float* lam, const float* count_dev, double count_host, int C, int g,
+                       float eps, int decomposition, int renorm, float* A, float* cvec, float* workspace,
+                       size_t workspace_bytes, void* Tp_bwd, int pack_K, cudaStream_t st);
 
 // tensor-map encoder for the TMA kernels (wc_tc_apply.cu)
 int wc_make_f32_map3(void* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,

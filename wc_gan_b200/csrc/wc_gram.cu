@@ -76,6 +76,7 @@ __device__ __forceinline__ float4 load4(const float* base, long long row_off, in
 
 template <bool kVec>
 __global__ void __launch_bounds__(NT) gram_kernel(GramParams p) {
+  wc_pdl_wait();
   __shared__ __align__(16) float As[2][RK][TI];
   __shared__ __align__(16) float Bs[2][RK][TJ];
   __shared__ float red[RK][TI];
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(NT) gram_kernel(GramParams p) {
 // ---- K1 helpers ---------------------------------------------------------------------------
 // pivot[c] = mean of the first `rows` rows: a cheap shift that removes the E[xx^T]-mu mu^T cancellation
 __global__ void pivot_kernel(const float* __restrict__ x, int rows, int C, float* __restrict__ pivot) {
+  wc_pdl_wait();
   int c = blockIdx.x * 32 + (threadIdx.x & 31);
   int w = threadIdx.x >> 5;  // 8 warps stride over rows
   __shared__ float part[8][32];
@@ -232,6 +234,7 @@ __global__ void stats_finalize_kernel(const float* __restrict__ partS, const flo
                                       int nchunks, long long strideS, int C, int g, double M,
                                       const float* __restrict__ pivot, float* __restrict__ mean, float* __restrict__ S,
                                       int lower_only) {
+  wc_pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)C * g;
   if (idx >= total) return;
@@ -254,6 +257,7 @@ __global__ void stats_finalize_kernel(const float* __restrict__ partS, const flo
 // Chan merge of R shard records {mean[C], S[G g g], count}
 __global__ void stats_merge_kernel(const float* __restrict__ rec, int R, int C, int g,
                                    float* __restrict__ mean, float* __restrict__ S, float* __restrict__ count_total) {
+  wc_pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)C * g;
   if (idx >= total) return;
@@ -281,6 +285,7 @@ __global__ void stats_merge_kernel(const float* __restrict__ rec, int R, int C, 
 // ---- K4 helper: stable counting sort of samples by class (one CTA) -----------------------------
 __global__ void class_order_kernel(const int32_t* __restrict__ cls, int N, int K,
                                    int32_t* __restrict__ order, int32_t* __restrict__ slot_of) {
+  wc_pdl_wait();
   extern __shared__ int sh[];  // [K] starts
   int* start = sh;
   for (int k = threadIdx.x; k < K; k += blockDim.x) start[k] = 0;
@@ -357,12 +362,12 @@ extern "C" int wc_stats_fwd(const float* x, int64_t M, int C, int g, float* work
     int rc = wc_tc_gram_self(x, M, C, g, pivot, pS, psum, st);
     if (rc) return rc;
     long long tot = (long long)C * g;
-    stats_finalize_kernel<<<wc_cdiv(tot, 256), 256, 0, st>>>(pS, psum, 1, (long long)C * C, C, g, (double)M, pivot, mean, S, 1);
+    WC_CUDA(wc_launch(stats_finalize_kernel, wc_cdiv(tot, 256), 256, 0, st, pS, psum, 1, (long long)C * C, C, g, (double)M, pivot, mean, S, 1));
     WC_CHECK_LAUNCH();
     return 0;
   }
   int prow = (int)(M < 1024 ? M : 1024);
-  pivot_kernel<<<wc_cdiv(C, 32), 256, 0, st>>>(x, prow, C, pivot);
+  WC_CUDA(wc_launch(pivot_kernel, wc_cdiv(C, 32), 256, 0, st, x, prow, C, pivot));
   WC_CHECK_LAUNCH();
   GramParams p{};
   p.A = x; p.B = x; p.lda = C; p.ldb = C; p.ma = pivot; p.mb = pivot; p.nI = C; p.nJ = C;
@@ -373,10 +378,10 @@ extern "C" int wc_stats_fwd(const float* x, int64_t M, int C, int g, float* work
   p.asum = psum; p.bsum = nullptr; p.sum_slot_stride = C; p.atomic = 0;
   dim3 grid(pl.ntiles, pl.nchunks);
   bool vec = (C % 4 == 0) && (g % 4 == 0) && wc_aligned16(x);
-  if (vec) gram_kernel<true><<<grid, NT, 0, st>>>(p); else gram_kernel<false><<<grid, NT, 0, st>>>(p);
+  if (vec) WC_CUDA(wc_launch(gram_kernel<true>, grid, NT, 0, st, p)); else WC_CUDA(wc_launch(gram_kernel<false>, grid, NT, 0, st, p));
   WC_CHECK_LAUNCH();
   long long total = (long long)C * g;
-  stats_finalize_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(pS, psum, pl.nchunks, (long long)C * C, C, g, (double)M, pivot, mean, S, 0);
+  WC_CUDA(wc_launch(stats_finalize_kernel, wc_cdiv(total, 256), 256, 0, st, pS, psum, pl.nchunks, (long long)C * C, C, g, (double)M, pivot, mean, S, 0));
   WC_CHECK_LAUNCH();
   return 0;
 }
@@ -385,7 +390,7 @@ extern "C" int wc_stats_merge(const float* records, int R, int C, int g, float* 
                               wc_stream_t stream) {
   if (!records || !mean || !S || !count_total || R <= 0 || C <= 0 || g <= 0 || C % g) return WC_E_ARG;
   long long total = (long long)C * g;
-  stats_merge_kernel<<<wc_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(records, R, C, g, mean, S, count_total);
+  WC_CUDA(wc_launch(stats_merge_kernel, wc_cdiv(total, 256), 256, 0, (cudaStream_t)stream, records, R, C, g, mean, S, count_total));
   WC_CHECK_LAUNCH();
   return 0;
 }
@@ -409,7 +414,7 @@ extern "C" int wc_reduce_bwd(const float* x, const float* dy, int N, int HW, int
     if (K > 8192) return WC_E_UNSUPPORTED;
     order = reinterpret_cast<int32_t*>(workspace);
     slot_of = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + need / 2);
-    class_order_kernel<<<1, 1024, K * sizeof(int), st>>>(cls, N, K, order, slot_of);
+    WC_CUDA(wc_launch(class_order_kernel, 1, 1024, K * sizeof(int), st, cls, N, K, order, slot_of));
     WC_CHECK_LAUNCH();
   }
   if (s == P + (size_t)K * Cin * Cout) {   // P | s contiguous (wc_layer_bwd's workspace): one memset
@@ -440,7 +445,7 @@ extern "C" int wc_reduce_bwd(const float* x, const float* dy, int N, int HW, int
   p.asum = nullptr; p.bsum = s; p.sum_slot_stride = Cout; p.atomic = 1;
   dim3 grid(p.ntiles, p.nchunks);
   bool vec = (Cin % 4 == 0) && (Cout % 4 == 0) && wc_aligned16(x) && wc_aligned16(dy) && (!mean || wc_aligned16(mean));
-  if (vec) gram_kernel<true><<<grid, NT, 0, st>>>(p); else gram_kernel<false><<<grid, NT, 0, st>>>(p);
+  if (vec) WC_CUDA(wc_launch(gram_kernel<true>, grid, NT, 0, st, p)); else WC_CUDA(wc_launch(gram_kernel<false>, grid, NT, 0, st, p));
   WC_CHECK_LAUNCH();
   return 0;
 }

@@ -138,17 +138,12 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
     if (rc) return rc;
   }
   // identity coloring (after_norm == 'n', generator.py:79-80): W_k = I is written by the compose kernel from Wu == NULL
-  rc = wc_compose_fwd(at<float>(c.saved, L.Weff), c.Cin, c.Cout, c.whiten ? c.g : c.Cin, c.K, c.Wu, c.bu, c.Wc, c.bc,
-                      c.triangular, c.class_matrix, c.D, c.E, c.bf, at<float>(c.saved, L.ehat), at<float>(c.saved, L.Wk),
-                      at<float>(c.saved, L.T), at<float>(c.saved, L.b), stream);
-  if (rc) return rc;
   void* Tp = at<void>(c.saved, L.Tp_fwd);
-  if (Tp) {
-    rc = wc_pack_fwd(at<float>(c.saved, L.T), c.Cin, c.K, Tp, stream);
-    if (rc) return rc;
-    rc = wc_pack_bwd(at<float>(c.saved, L.T), nullptr, c.Cin, c.whiten ? c.g : c.Cin, c.K, at<void>(c.saved, L.Tp_bwd), stream);
-    if (rc) return rc;
-  }
+  rc = wc_compose_fwd_impl(at<float>(c.saved, L.Weff), c.Cin, c.Cout, c.whiten ? c.g : c.Cin, c.K, c.Wu, c.bu, c.Wc, c.bc,
+                           c.triangular, c.class_matrix, c.D, c.E, c.bf, at<float>(c.saved, L.ehat), at<float>(c.saved, L.Wk),
+                           at<float>(c.saved, L.T), at<float>(c.saved, L.b), Tp, Tp ? at<void>(c.saved, L.Tp_bwd) : nullptr,
+                           (cudaStream_t)stream);
+  if (rc) return rc;
   const int band = (c.whiten && !has_coloring(c) && c.g < c.Cin) ? c.g : 0;
   return wc_apply_fwd(c.x, c.N, c.HW, c.Cin, c.Cout, mean, at<float>(c.saved, L.T), Tp, at<float>(c.saved, L.b),
                       conditional(c) ? c.cls : nullptr, c.K, band, c.y, c.info, stream);
@@ -188,15 +183,12 @@ extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
   float *A = nullptr, *cvec = nullptr;
   if (stats_grad) {
     A = at<float>(c.saved, L.A); cvec = at<float>(c.saved, L.cvec);
-    rc = wc_factor_bwd(c.red, c.red + gg, at<float>(c.saved, L.Weff), at<float>(c.saved, L.Wm), at<float>(c.saved, L.R),
-                       at<float>(c.saved, L.U), at<float>(c.saved, L.lam), c.count_dev, c.count, c.Cin, g, c.eps, c.decomposition,
-                       c.renorm, A, cvec, at<float>(c.workspace, W.factor), W.factor_bytes, stream);
+    rc = wc_factor_bwd_impl(c.red, c.red + gg, at<float>(c.saved, L.Weff), at<float>(c.saved, L.Wm), at<float>(c.saved, L.R),
+                            at<float>(c.saved, L.U), at<float>(c.saved, L.lam), c.count_dev, c.count, c.Cin, g, c.eps,
+                            c.decomposition, c.renorm, A, cvec, at<float>(c.workspace, W.factor), W.factor_bytes,
+                            at<void>(c.saved, L.Tp_bwd), c.K, (cudaStream_t)stream);
     if (rc) return rc;
   }
   void* Tp = at<void>(c.saved, L.Tp_bwd);
-  if (Tp && A) {
-    rc = wc_pack_bwd(nullptr, A, c.Cin, g, c.K, Tp, stream);     // T's image was packed in forward; add A's
-    if (rc) return rc;
-  }
   return wc_apply_bwd(c.x, c.dy, c.N, c.HW, c.Cin, c.Cout, mean, at<float>(c.saved, L.T), A, Tp, cvec, g, cls, c.K, c.dx, stream);
 }

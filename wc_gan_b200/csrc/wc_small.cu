@@ -6,6 +6,7 @@
 // :993-1005 (per-class kernels), and TF autodiff of all of them.
 #include "wc_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 // =============================================================================================
 // generic batched small matmul
@@ -67,16 +68,41 @@ __device__ __forceinline__ void smm_store_panel(const float4 (&v)[SMM_NV], int k
   }
 }
 
+// Optional epilogues of a fast-path tile (the fused small-matrix launches):
+//   EPI_PACK_T  the tile also goes out as bf16 hi/lo operand images for the tcgen05 apply kernels: image 0 holds
+//               src(n,k) = C[k][n] (K3's T^T), image 1 src(n,k) = C[n][k] (K6's T); either may be NULL
+//   EPI_PSI     C is a lower-triangular product Z; what is stored is Psi = -(tril(Z) + tril(Z)^T - diag(Z))
+//               (both triangles; CTAs of strictly upper tiles do nothing)
+enum { EPI_NONE = 0, EPI_PACK = 1, EPI_PSI = 2 };
+struct SmmEpi {
+  int kind;
+  uint8_t* pk0; uint8_t* pk1;      // packed images (wc_pack_* layout), NULL = skip
+  long long pk_slot_stride;        // bytes between the images of consecutive b1 batches
+  int pkC;                         // channels of the packed matrix
+  int row_per_b2;                  // global row of the tile = b2 * row_per_b2 + local row (block-diagonal left factor)
+};
+
+__device__ __forceinline__ void smm_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+// byte offset of the 16-byte chunk (8 k's) `chunk` of row n in a K-major SWIZZLE_64B image with 32 k's per row
+__device__ __forceinline__ uint32_t smm_kmajor32_off(int n, int chunk) {
+  const uint32_t off = (uint32_t)n * 64u + (uint32_t)chunk * 16u;
+  return off ^ (((off >> 7) & 3u) << 4);
+}
+
 template <bool kAK, bool kBK>
-__global__ void __launch_bounds__(SMM_THREADS) smm_kernel(WcSmm p, SmmExtra ex) {
-  extern __shared__ __align__(16) float smm_sm[];
+__device__ __forceinline__ void smm_tile(const WcSmm& p, const SmmExtra& ex, const SmmEpi& ep, int bx, int by, int z, float* smm_sm) {
   float* As = smm_sm;                       // [k][SMM_P]
   float* Bs = smm_sm + SMM_KC * SMM_P;      // [k][SMM_P]
-  const int z = blockIdx.z, b1 = z / p.nb2, b2 = z % p.nb2;
+  if (ep.kind == EPI_PSI && by < bx) return;
+  const int b1 = z / p.nb2, b2 = z % p.nb2;
   const float* A = p.A + b1 * p.bA1 + b2 * p.bA2;
   const float* B = p.B + b1 * p.bB1 + b2 * p.bB2;
   float* C = p.C + b1 * p.bC1 + b2 * p.bC2;
-  const int i0 = blockIdx.y * SMM_T, j0 = blockIdx.x * SMM_T;
+  const int i0 = by * SMM_T, j0 = bx * SMM_T;
   const int t = threadIdx.x, kg = t >> 7, tt = t & 127, tx = tt & 15, ty = tt >> 4;
   const long long lda = kAK ? p.rsA : p.csA, ldb = kBK ? p.csB : p.rsB;
   float acc[4][2];
@@ -128,6 +154,20 @@ __global__ void __launch_bounds__(SMM_THREADS) smm_kernel(WcSmm p, SmmExtra ex) 
     float cnt = ex.count_dev ? ex.count_dev[0] : ex.count_host;
     alpha /= (ex.count_mode == 1 ? cnt : (cnt - 1.f));
   }
+  if (ep.kind == EPI_PSI) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int i = i0 + ty * 4 + a, j = j0 + tx * 2 + b;
+        if (j > i) continue;
+        const float v = -alpha * acc[a][b];
+        C[(long long)i * p.rsC + (long long)j * p.csC] = v;
+        if (j < i) C[(long long)j * p.rsC + (long long)i * p.csC] = v;
+      }
+    return;
+  }
+  float* tile = smm_sm + 4096;              // [32][33], clear of the reduction scratch
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -139,11 +179,119 @@ __global__ void __launch_bounds__(SMM_THREADS) smm_kernel(WcSmm p, SmmExtra ex) 
       if ((p.tri == 1 && j > i) || (p.tri == 2 && j < i)) v = 0.f;
       else if (p.beta != 0.f) v += p.beta * (*cp);
       *cp = v;
+      if (ep.kind == EPI_PACK) tile[(ty * 4 + a) * 33 + tx * 2 + b] = v;
     }
+  if (ep.kind != EPI_PACK) return;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  const int lane32 = tt & 31, ch = tt >> 5;            // one 16-byte chunk (8 k's) per thread and image
+  const int gi0 = b2 * ep.row_per_b2 + i0;             // global row of the tile's first row
+  const long long b_img = (long long)ep.pkC * 64;      // bytes of one bf16 image of a 32-wide k block
+  uint32_t hi[4], lo[4];
+  if (ep.pk0) {        // src(n,k) = C[k][n]: k block = the tile's rows, n = its columns
+#pragma unroll
+    for (int q = 0; q < 4; ++q) smm_split2(tile[(8 * ch + 2 * q) * 33 + lane32], tile[(8 * ch + 2 * q + 1) * 33 + lane32], hi[q], lo[q]);
+    uint8_t* dst = ep.pk0 + (long long)b1 * ep.pk_slot_stride + (long long)(gi0 >> 5) * (2 * b_img) + smm_kmajor32_off(j0 + lane32, ch);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst + b_img) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  if (ep.pk1) {        // src(n,k) = C[n][k]: k block = the tile's columns, n = its rows
+#pragma unroll
+    for (int q = 0; q < 4; ++q) smm_split2(tile[lane32 * 33 + 8 * ch + 2 * q], tile[lane32 * 33 + 8 * ch + 2 * q + 1], hi[q], lo[q]);
+    uint8_t* dst = ep.pk1 + (long long)b1 * ep.pk_slot_stride + (long long)(j0 >> 5) * (2 * b_img) + smm_kmajor32_off(gi0 + lane32, ch);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst + b_img) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+template <bool kAK, bool kBK>
+__global__ void __launch_bounds__(SMM_THREADS) smm_kernel(WcSmm p, SmmExtra ex) {
+  wc_pdl_wait();
+  extern __shared__ __align__(16) float smm_sm[];
+  SmmEpi ep{};
+  smm_tile<kAK, kBK>(p, ex, ep, blockIdx.x, blockIdx.y, blockIdx.z, smm_sm);
+}
+
+// ---- several independent products (and matrix-vector products) in ONE launch ---------------------------------------
+// The small-matrix stages are chains of 256^3-sized products whose cost is the launch, not the math; products that do
+// not depend on each other share a launch.
+struct SmmJob { WcSmm p; SmmExtra ex; SmmEpi ep; int ak, bk; int gx, gy, gz; int cta0; };
+// out[b][i] = scale * sum_q sum_k A_q[b](i,k) * x_q[b][k]   (x == NULL: ones)
+struct VecJob {
+  const float* A; const float* x; float* out;
+  int M, K; long long rsA, csA;
+  int nsum; long long sA, sx;
+  int nb; long long bA, bx, bo;
+  const float* count_dev; float count_host; int count_mode; float alpha;
+  int cta0, nctas;
+};
+constexpr int SMM_MAXJOBS = 3, SMM_MAXVEC = 2;
+struct SmmMulti { SmmJob job[SMM_MAXJOBS]; int njobs; VecJob vec[SMM_MAXVEC]; int nvec; };
+
+// one CTA = 32 outputs of one batch; 16 k-slices of 32 threads
+__device__ __forceinline__ void vec_job_run(const VecJob& v, int cta, float* sm) {
+  const int per_b = (v.M + 31) / 32;
+  const int b = cta / per_b, i0 = (cta % per_b) * 32;
+  const int t = threadIdx.x, io = t & 31, ks = t >> 5;       // 16 slices
+  const float* A = v.A + (long long)b * v.bA;
+  const float* x = v.x ? v.x + (long long)b * v.bx : nullptr;
+  float acc = 0.f;
+  if (v.rsA == 1) {
+    // consecutive outputs are contiguous: lanes walk i, slices walk k
+    const int i = i0 + io;
+    if (i < v.M)
+      for (int q = 0; q < v.nsum; ++q)
+        for (int k = ks; k < v.K; k += 16) acc = fmaf(A[(long long)q * v.sA + (long long)k * v.csA + i], x ? x[(long long)q * v.sx + k] : 1.f, acc);
+    sm[ks * 32 + io] = acc;
+    __syncthreads();
+    if (ks == 0) {
+#pragma unroll
+      for (int s2 = 1; s2 < 16; ++s2) acc += sm[s2 * 32 + io];
+    }
+  } else {
+    // rows of A are (near) contiguous in k: a warp walks k for two outputs
+    for (int h = 0; h < 2; ++h) {
+      const int i = i0 + ks * 2 + h;
+      float a = 0.f;
+      if (i < v.M)
+        for (int q = 0; q < v.nsum; ++q)
+          for (int k = io; k < v.K; k += 32) a = fmaf(A[(long long)q * v.sA + (long long)i * v.rsA + (long long)k * v.csA], x ? x[(long long)q * v.sx + k] : 1.f, a);
+      a = wc_warp_sum(a);
+      if (io == 0) sm[ks * 2 + h] = a;
+    }
+    __syncthreads();
+    acc = (t < 32) ? sm[t] : 0.f;
+  }
+  if (t < 32 && i0 + t < v.M) {
+    float scale = v.alpha;
+    if (v.count_mode) {
+      float cnt = v.count_dev ? v.count_dev[0] : v.count_host;
+      scale /= (v.count_mode == 1 ? cnt : (cnt - 1.f));
+    }
+    v.out[(long long)b * v.bo + i0 + t] = scale * acc;
+  }
+}
+
+__global__ void __launch_bounds__(SMM_THREADS) smm_multi_kernel(const __grid_constant__ SmmMulti mp) {
+  wc_pdl_wait();
+  extern __shared__ __align__(16) float smm_sm[];
+  const int cta = blockIdx.x;
+  for (int v = 0; v < mp.nvec; ++v)
+    if (cta >= mp.vec[v].cta0 && cta < mp.vec[v].cta0 + mp.vec[v].nctas) { vec_job_run(mp.vec[v], cta - mp.vec[v].cta0, smm_sm); return; }
+  int j = 0;
+  for (int q = 1; q < mp.njobs; ++q) if (cta >= mp.job[q].cta0) j = q;
+  const SmmJob& jb = mp.job[j];
+  const int l = cta - jb.cta0;
+  const int bx = l % jb.gx, by = (l / jb.gx) % jb.gy, z = l / (jb.gx * jb.gy);
+  if (jb.ak) {
+    if (jb.bk) smm_tile<true, true>(jb.p, jb.ex, jb.ep, bx, by, z, smm_sm); else smm_tile<true, false>(jb.p, jb.ex, jb.ep, bx, by, z, smm_sm);
+  } else {
+    if (jb.bk) smm_tile<false, true>(jb.p, jb.ex, jb.ep, bx, by, z, smm_sm); else smm_tile<false, false>(jb.p, jb.ex, jb.ep, bx, by, z, smm_sm);
+  }
 }
 
 // ---- generic path: any shape, any strides ------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) smm_generic_kernel(WcSmm p, SmmExtra ex) {
+  wc_pdl_wait();
   __shared__ float As[32][33];
   __shared__ float Bs[32][33];
   const int z = blockIdx.z, b1 = z / p.nb2, b2 = z % p.nb2;
@@ -220,7 +368,7 @@ int smm_fast_launch(const WcSmm& p, const SmmExtra& ex, dim3 grid, cudaStream_t 
     WC_CUDA(cudaFuncSetAttribute(smm_kernel<kAK, kBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMM_SMEM));
     attr_set = true;
   }
-  smm_kernel<kAK, kBK><<<grid, SMM_THREADS, SMM_SMEM, st>>>(p, ex);
+  WC_CUDA(wc_launch(smm_kernel<kAK, kBK>, grid, SMM_THREADS, SMM_SMEM, st, p, ex));
   WC_CHECK_LAUNCH();
   return 0;
 }
@@ -243,10 +391,56 @@ int smm(const WcSmm& p, cudaStream_t st, const float* count_dev = nullptr, float
     return bk ? smm_fast_launch<false, true>(p, ex, grid, st) : smm_fast_launch<false, false>(p, ex, grid, st);
   }
   dim3 grid(wc_cdiv(p.N, 32), wc_cdiv(p.M, 32), p.nb1 * p.nb2);
-  smm_generic_kernel<<<grid, 256, 0, st>>>(p, ex);
+  WC_CUDA(wc_launch(smm_generic_kernel, grid, 256, 0, st, p, ex));
   WC_CHECK_LAUNCH();
   return 0;
 }
+
+bool smm_is_fast(const WcSmm& p) {
+  const bool ak = p.csA == 1, bk = p.rsB == 1, ai = p.rsA == 1, bj = p.csB == 1;
+  const long long lda = ak ? p.rsA : p.csA, ldb = bk ? p.csB : p.rsB;
+  return p.M > 0 && p.N > 0 && (p.M % SMM_T == 0) && (p.N % SMM_T == 0) && (p.K % 4 == 0) && (ak || ai) && (bk || bj) &&
+         mult4(lda) && mult4(ldb) && wc_aligned16(p.A) && wc_aligned16(p.B) && mult4(p.bA1) && mult4(p.bA2) &&
+         mult4(p.bB1) && mult4(p.bB2) && mult4(p.sA) && mult4(p.sB);
+}
+
+// Builder for one fused launch.  add() refuses (returns false) a product the fast tile cannot do; the caller then
+// falls back to separate launches.
+struct MultiLaunch {
+  SmmMulti m{};
+  int ctas = 0;
+  bool add(const WcSmm& p, const SmmEpi& ep = SmmEpi{}, const float* count_dev = nullptr, float count_host = 0.f,
+           int count_mode = 0, float diag_scale = 1.f) {
+    if (m.njobs >= SMM_MAXJOBS || !smm_is_fast(p)) return false;
+    if (ep.kind == EPI_PACK && (ep.pkC % 32 || (ep.pk0 && !wc_aligned16(ep.pk0)) || (ep.pk1 && !wc_aligned16(ep.pk1)))) return false;
+    SmmJob& j = m.job[m.njobs++];
+    j.p = p; j.ex = SmmExtra{count_dev, count_host, count_mode, diag_scale}; j.ep = ep;
+    j.ak = p.csA == 1; j.bk = p.rsB == 1;
+    j.gx = p.N / SMM_T; j.gy = p.M / SMM_T; j.gz = p.nb1 * p.nb2;
+    j.cta0 = ctas;
+    ctas += j.gx * j.gy * j.gz;
+    return true;
+  }
+  bool add_vec(const VecJob& v0) {
+    if (m.nvec >= SMM_MAXVEC || v0.M <= 0 || v0.nb <= 0) return false;
+    VecJob& v = m.vec[m.nvec++];
+    v = v0;
+    v.cta0 = ctas; v.nctas = ((v.M + 31) / 32) * v.nb;
+    ctas += v.nctas;
+    return true;
+  }
+  int launch(cudaStream_t st) {
+    if (ctas == 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+      WC_CUDA(cudaFuncSetAttribute(smm_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMM_SMEM));
+      attr_set = true;
+    }
+    WC_CUDA(wc_launch(smm_multi_kernel, ctas, SMM_THREADS, SMM_SMEM, st, m));
+    WC_CHECK_LAUNCH();
+    return 0;
+  }
+};
 
 WcSmm smm_init() {
   WcSmm p{};
@@ -288,6 +482,7 @@ __global__ void factor_prep_kernel(const float* __restrict__ mean, const float* 
                                    const float* count_dev, float count_host, int C, int g, float eps, float extra_eps,
                                    float momentum, int training, float* moving_mean, float* moving_cov,
                                    float* __restrict__ Ashr) {
+  wc_pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)C * g;
   if (idx >= total) return;
@@ -315,6 +510,7 @@ __global__ void factor_prep_kernel(const float* __restrict__ mean, const float* 
 // resident, only this CTA touches its slice).  A warp owns one column pair per step.
 __global__ void __launch_bounds__(1024) jacobi_kernel(const float* __restrict__ L, int g, float* __restrict__ Bm,
                                                       float* __restrict__ U, float* __restrict__ lam, int32_t* info) {
+  wc_pdl_wait();
   __shared__ int pairs[2][256];      // round-robin tournament positions (g <= 512)
   __shared__ int rotated;
   const int grp = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
@@ -390,6 +586,7 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(const float* __restrict__ 
 // Us = U * diag(lam^power)  (row-major (G,g,g))
 __global__ void scale_cols_kernel(const float* __restrict__ U, const float* __restrict__ lam, int C, int g, float power,
                                   float* __restrict__ out) {
+  wc_pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)C * g) return;
   int grp = (int)(idx / ((long long)g * g));
@@ -399,6 +596,7 @@ __global__ void scale_cols_kernel(const float* __restrict__ U, const float* __re
 
 // Y[i,j] *= -1 / (r_i r_j (r_i + r_j)),  r = sqrt(lam)      (Daleckii-Krein for lam^-1/2)
 __global__ void zca_mulF_kernel(float* __restrict__ Y, const float* __restrict__ lam, int C, int g) {
+  wc_pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)C * g) return;
   int grp = (int)(idx / ((long long)g * g));
@@ -410,6 +608,7 @@ __global__ void zca_mulF_kernel(float* __restrict__ Y, const float* __restrict__
 // out = alpha * (X + X^T) per group; alpha optionally divided by (count - 1)
 __global__ void sym_scale_kernel(const float* __restrict__ X, float alpha, const float* count_dev, float count_host,
                                  int use_count, int C, int g, float* __restrict__ out) {
+  wc_pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)C * g) return;
   long long base = idx - idx % ((long long)g * g);
@@ -427,6 +626,7 @@ __global__ void build_wk_kernel(int Cin, int Cout, int K, const float* __restric
                                 const float* __restrict__ cm, const float* __restrict__ D, int E,
                                 const float* __restrict__ bf, float* __restrict__ ehat, float* __restrict__ Wk,
                                 float* __restrict__ b, int identity) {
+  wc_pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long per = (long long)Cin * Cout;
   if (idx >= per * K) return;
@@ -454,6 +654,7 @@ __global__ void build_wk_kernel(int Cin, int Cout, int K, const float* __restric
 // K5a helpers
 // =============================================================================================
 __global__ void sum_over_k_kernel(const float* __restrict__ X, long long per, int K, float* __restrict__ out) {
+  wc_pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= per) return;
   float s = 0.f;
@@ -462,6 +663,7 @@ __global__ void sum_over_k_kernel(const float* __restrict__ X, long long per, in
 }
 
 __global__ void triu_copy_kernel(const float* __restrict__ X, int Cin, int Cout, long long total, float* __restrict__ out) {
+  wc_pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   long long ij = idx % ((long long)Cin * Cout);
@@ -472,6 +674,7 @@ __global__ void triu_copy_kernel(const float* __restrict__ X, int Cin, int Cout,
 // de[k,e] = <Q_k, D_e>, one CTA per (k,e)
 __global__ void __launch_bounds__(256) class_dot_kernel(const float* __restrict__ Q, const float* __restrict__ D, long long per, int E,
                                                         float* __restrict__ de) {
+  wc_pdl_wait();
   __shared__ float part[8];
   int k = blockIdx.x / E, e = blockIdx.x % E;
   const float* q = Q + (long long)k * per;
@@ -491,6 +694,7 @@ __global__ void __launch_bounds__(256) class_dot_kernel(const float* __restrict_
 // backward of tf.nn.l2_normalize (conditional_layers.py:994): one thread per class
 __global__ void l2norm_bwd_kernel(const float* __restrict__ cm, const float* __restrict__ ehat, const float* __restrict__ de,
                                   int K, int E, float* __restrict__ dcm) {
+  wc_pdl_wait();
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   float sq = 0.f, dot = 0.f;
@@ -528,14 +732,14 @@ int factor_matrix(const float* Ashr, int C, int g, int decomposition, float* Wm,
   if (decomposition == WC_DECOMP_CHOLESKY) return wc_chol_inv_launch(Ashr, C, g, sqrt_out, Wm, Xpad, info, st);   // L only on request
   int rcc = wc_chol_inv_launch(Ashr, C, g, L, nullptr, Xpad, info, st);
   if (rcc) return rcc;
-  jacobi_kernel<<<G, 1024, 0, st>>>(L, g, Bm, U, lam, info);
+  WC_CUDA(wc_launch(jacobi_kernel, G, 1024, 0, st, L, g, Bm, U, lam, info));
   WC_CHECK_LAUNCH();
-  scale_cols_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(U, lam, C, g, -0.25f, Us);
+  WC_CUDA(wc_launch(scale_cols_kernel, wc_cdiv(total, 256), 256, 0, st, U, lam, C, g, -0.25f, Us));
   WC_CHECK_LAUNCH();
   int rc = smm(smm_gg(Us, false, Us, true, Wm, g, G), st);
   if (rc) return rc;
   if (sqrt_out) {
-    scale_cols_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(U, lam, C, g, 0.25f, Us);
+    WC_CUDA(wc_launch(scale_cols_kernel, wc_cdiv(total, 256), 256, 0, st, U, lam, C, g, 0.25f, Us));
     WC_CHECK_LAUNCH();
     rc = smm(smm_gg(Us, false, Us, true, sqrt_out, g, G), st);
     if (rc) return rc;
@@ -571,8 +775,8 @@ extern "C" int wc_factor_fwd(const float* mean, const float* S, const float* cou
   int rc;
   if (!training) {
     // test phase (:702-704): factor the moving covariance; U/lam scratch if the caller gave none
-    factor_prep_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(nullptr, nullptr, nullptr, 0.f, C, g, eps, extra, momentum, 0,
-                                                            moving_mean, moving_cov, Ashr);
+    WC_CUDA(wc_launch(factor_prep_kernel, wc_cdiv(total, 256), 256, 0, st, nullptr, nullptr, nullptr, 0.f, C, g, eps, extra, momentum, 0,
+                                                            moving_mean, moving_cov, Ashr));
     WC_CHECK_LAUNCH();
     if (zca && (!U || !lam)) return WC_E_ARG;   // eigenvector / eigenvalue scratch is required in every phase
     return factor_matrix(Ashr, C, g, decomposition, Weff, nullptr, U, lam, L, Bm, Us, Xpad, info, st);
@@ -582,15 +786,15 @@ extern "C" int wc_factor_fwd(const float* mean, const float* S, const float* cou
     Amov = reinterpret_cast<float*>(ws + off); Wmov = reinterpret_cast<float*>(ws + off + gb);
     Lb = reinterpret_cast<float*>(ws + off + 2 * gb); Umov = reinterpret_cast<float*>(ws + off + 3 * gb);
     // moving covariance as it is BEFORE this step's update (:695-696)
-    factor_prep_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(nullptr, nullptr, nullptr, 0.f, C, g, eps, extra, momentum, 0,
-                                                            moving_mean, moving_cov, Amov);
+    WC_CUDA(wc_launch(factor_prep_kernel, wc_cdiv(total, 256), 256, 0, st, nullptr, nullptr, nullptr, 0.f, C, g, eps, extra, momentum, 0,
+                                                            moving_mean, moving_cov, Amov));
     WC_CHECK_LAUNCH();
     // lam scratch for the moving factor: reuse R's first C floats (R is written afterwards)
     rc = factor_matrix(Amov, C, g, decomposition, Wmov, nullptr, Umov, R, L, Bm, Us, Xpad, info, st);
     if (rc) return rc;
   }
-  factor_prep_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(mean, S, count_dev, (float)count_host, C, g, eps, extra, momentum, 1,
-                                                          moving_mean, moving_cov, Ashr);
+  WC_CUDA(wc_launch(factor_prep_kernel, wc_cdiv(total, 256), 256, 0, st, mean, S, count_dev, (float)count_host, C, g, eps, extra, momentum, 1,
+                                                          moving_mean, moving_cov, Ashr));
   WC_CHECK_LAUNCH();
   rc = factor_matrix(Ashr, C, g, decomposition, Wm, renorm ? Lb : nullptr, U, lam, L, Bm, Us, Xpad, info, st);
   if (rc) return rc;
@@ -608,23 +812,50 @@ extern "C" int wc_factor_fwd(const float* mean, const float* S, const float* cou
 // =============================================================================================
 // K2b entry point
 // =============================================================================================
+int wc_compose_fwd_impl(const float* Weff, int Cin, int Cout, int g, int K, const float* Wu, const float* bu,
+                        const float* Wc, const float* bc, int triangular, const float* class_matrix,
+                        const float* D, int E, const float* bf, float* ehat, float* Wk, float* T, float* b,
+                        void* Tp_fwd, void* Tp_bwd, cudaStream_t st) {
+  if (Cin <= 0 || Cout <= 0 || K <= 0 || !Wk || !T) return WC_E_ARG;
+  if (Weff && (g <= 0 || Cin % g)) return WC_E_ARG;
+  if (class_matrix && (!D || E <= 0 || !ehat)) return WC_E_ARG;
+  long long per = (long long)Cin * Cout;
+  WC_CUDA(wc_launch(build_wk_kernel, wc_cdiv(per * K, 256), 256, 0, st, Cin, Cout, K, Wu, bu, Wc, bc, triangular, class_matrix, D, E, bf,
+                                                         ehat, Wk, b, (!Wu && !Wc && !D) ? 1 : 0));
+  WC_CHECK_LAUNCH();
+  int rc = 0;
+  bool packed = false;
+  if (!Weff) {
+    if (T != Wk) WC_CUDA(cudaMemcpyAsync(T, Wk, (size_t)per * K * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    const WcSmm p = smm_blockdiag_left(Weff, true, Wk, T, g, Cin / g, Cout, Cout, K, per);
+    MultiLaunch ml;
+    SmmEpi ep{};
+    if (Tp_fwd || Tp_bwd) {   // T leaves the product tile as fp32 and as the bf16 operand images of K3 / K6
+      ep.kind = EPI_PACK; ep.pk0 = (uint8_t*)Tp_fwd; ep.pk1 = (uint8_t*)Tp_bwd;
+      ep.pk_slot_stride = (long long)Cin * Cout * 4; ep.pkC = Cin; ep.row_per_b2 = g;
+    }
+    if (Cin == Cout && ml.add(p, ep)) {
+      rc = ml.launch(st);
+      packed = true;
+    } else {
+      rc = smm(p, st);
+    }
+    if (rc) return rc;
+  }
+  if (!packed) {
+    if (Tp_fwd) { rc = wc_pack_fwd(T, Cin, K, Tp_fwd, (wc_stream_t)st); if (rc) return rc; }
+    if (Tp_bwd) { rc = wc_pack_bwd(T, nullptr, Cin, Weff ? g : Cin, K, Tp_bwd, (wc_stream_t)st); if (rc) return rc; }
+  }
+  return 0;
+}
+
 extern "C" int wc_compose_fwd(const float* Weff, int Cin, int Cout, int g, int K, const float* Wu, const float* bu,
                               const float* Wc, const float* bc, int triangular, const float* class_matrix,
                               const float* D, int E, const float* bf, float* ehat, float* Wk, float* T, float* b,
                               wc_stream_t stream) {
-  if (Cin <= 0 || Cout <= 0 || K <= 0 || !Wk || !T) return WC_E_ARG;
-  if (Weff && (g <= 0 || Cin % g)) return WC_E_ARG;
-  if (class_matrix && (!D || E <= 0 || !ehat)) return WC_E_ARG;
-  cudaStream_t st = (cudaStream_t)stream;
-  long long per = (long long)Cin * Cout;
-  build_wk_kernel<<<wc_cdiv(per * K, 256), 256, 0, st>>>(Cin, Cout, K, Wu, bu, Wc, bc, triangular, class_matrix, D, E, bf,
-                                                         ehat, Wk, b, (!Wu && !Wc && !D) ? 1 : 0);
-  WC_CHECK_LAUNCH();
-  if (!Weff) {
-    if (T != Wk) WC_CUDA(cudaMemcpyAsync(T, Wk, (size_t)per * K * 4, cudaMemcpyDeviceToDevice, st));
-    return 0;
-  }
-  return smm(smm_blockdiag_left(Weff, true, Wk, T, g, Cin / g, Cout, Cout, K, per), st);
+  return wc_compose_fwd_impl(Weff, Cin, Cout, g, K, Wu, bu, Wc, bc, triangular, class_matrix, D, E, bf, ehat, Wk, T, b,
+                             nullptr, nullptr, (cudaStream_t)stream);
 }
 
 // =============================================================================================
@@ -651,22 +882,51 @@ extern "C" int wc_color_bwd(const float* P, const float* s, const float* Weff, c
   int rc;
   const bool need_q = dWu || dWc || dD || dclass_matrix;
   const float* Q = P;
+  // The products that only need P, s and the saved matrices share one launch: Q_k = Weff P_k (= x_hat^T dy per class),
+  // dWeff = sum_k Wk P_k^T, gbar = sum_k Wk s_k, dbu = sum_k s_k.  Whatever the fast tile cannot take runs separately.
+  MultiLaunch ml;
+  bool q_done = false, dweff_done = false, gbar_done = false, dbu_done = false;
+  float* Qdst = Qws;
+  if (dWc && !triangular) Qdst = dWc;
+  else if (K == 1 && dWu) Qdst = dWu;
+  WcSmm pq = smm_init(), pw = smm_init();
   if (need_q && Weff) {
-    // Q_k = Weff P_k  ( = x_hat^T dy per class )
-    float* Qdst = Qws;
-    if (dWc && !triangular) Qdst = dWc;
-    else if (K == 1 && dWu) Qdst = dWu;
-    rc = smm(smm_blockdiag_left(Weff, false, P, Qdst, g, Cin / g, Cout, Cout, K, per), st);
-    if (rc) return rc;
+    pq = smm_blockdiag_left(Weff, false, P, Qdst, g, Cin / g, Cout, Cout, K, per);
+    q_done = ml.add(pq);
     Q = Qdst;
   }
+  if (dWeff) {
+    if (!Weff) return WC_E_ARG;
+    // dWeff[grp] = sum_k Wk[k][grp rows,:] . P[k][grp rows,:]^T
+    pw.A = Wk; pw.B = P; pw.C = dWeff; pw.M = g; pw.N = g; pw.K = Cout;
+    pw.rsA = Cout; pw.csA = 1; pw.rsB = 1; pw.csB = Cout; pw.rsC = g; pw.csC = 1;
+    pw.nb1 = 1; pw.nb2 = Cin / g;
+    pw.bA2 = (long long)g * Cout; pw.bB2 = (long long)g * Cout; pw.bC2 = (long long)g * g;
+    pw.nsum = K; pw.sA = per; pw.sB = per;
+    dweff_done = ml.add(pw);
+  }
+  if (gbar) {
+    VecJob v{};
+    v.A = Wk; v.x = s; v.out = gbar; v.M = Cin; v.K = Cout; v.rsA = Cout; v.csA = 1;
+    v.nsum = K; v.sA = per; v.sx = Cout; v.nb = 1; v.alpha = 1.f;
+    gbar_done = ml.add_vec(v);
+  }
+  if (dbu) {
+    VecJob v{};
+    v.A = s; v.x = nullptr; v.out = dbu; v.M = Cout; v.K = K; v.rsA = 1; v.csA = Cout;
+    v.nsum = 1; v.nb = 1; v.alpha = 1.f;
+    dbu_done = ml.add_vec(v);
+  }
+  rc = ml.launch(st);
+  if (rc) return rc;
+  if (need_q && Weff && !q_done) { rc = smm(pq, st); if (rc) return rc; }
   if (dWu && Q != dWu) {
     if (K == 1) WC_CUDA(cudaMemcpyAsync(dWu, Q, (size_t)per * 4, cudaMemcpyDeviceToDevice, st));
-    else { sum_over_k_kernel<<<wc_cdiv(per, 256), 256, 0, st>>>(Q, per, K, dWu); WC_CHECK_LAUNCH(); }
+    else { WC_CUDA(wc_launch(sum_over_k_kernel, wc_cdiv(per, 256), 256, 0, st, Q, per, K, dWu)); WC_CHECK_LAUNCH(); }
   }
-  if (dbu) { sum_over_k_kernel<<<wc_cdiv(Cout, 256), 256, 0, st>>>(s, Cout, K, dbu); WC_CHECK_LAUNCH(); }
+  if (dbu && !dbu_done) { WC_CUDA(wc_launch(sum_over_k_kernel, wc_cdiv(Cout, 256), 256, 0, st, s, Cout, K, dbu)); WC_CHECK_LAUNCH(); }
   if (dWc && Q != dWc) {
-    if (triangular) { triu_copy_kernel<<<wc_cdiv(per * K, 256), 256, 0, st>>>(Q, Cin, Cout, per * K, dWc); WC_CHECK_LAUNCH(); }
+    if (triangular) { WC_CUDA(wc_launch(triu_copy_kernel, wc_cdiv(per * K, 256), 256, 0, st, Q, Cin, Cout, per * K, dWc)); WC_CHECK_LAUNCH(); }
     else WC_CUDA(cudaMemcpyAsync(dWc, Q, (size_t)per * K * 4, cudaMemcpyDeviceToDevice, st));
   }
   if (dbc) WC_CUDA(cudaMemcpyAsync(dbc, s, (size_t)K * Cout * 4, cudaMemcpyDeviceToDevice, st));
@@ -680,24 +940,13 @@ extern "C" int wc_color_bwd(const float* P, const float* s, const float* Weff, c
     if (rc) return rc;
   }
   if (dclass_matrix) {
-    class_dot_kernel<<<K * E, 256, 0, st>>>(Q, D, per, E, de);
+    WC_CUDA(wc_launch(class_dot_kernel, K * E, 256, 0, st, Q, D, per, E, de));
     WC_CHECK_LAUNCH();
-    l2norm_bwd_kernel<<<wc_cdiv(K, 128), 128, 0, st>>>(class_matrix, ehat, de, K, E, dclass_matrix);
+    WC_CUDA(wc_launch(l2norm_bwd_kernel, wc_cdiv(K, 128), 128, 0, st, class_matrix, ehat, de, K, E, dclass_matrix));
     WC_CHECK_LAUNCH();
   }
-  if (dWeff) {
-    if (!Weff) return WC_E_ARG;
-    // dWeff[grp] = sum_k Wk[k][grp rows,:] . P[k][grp rows,:]^T
-    WcSmm p = smm_init();
-    p.A = Wk; p.B = P; p.C = dWeff; p.M = g; p.N = g; p.K = Cout;
-    p.rsA = Cout; p.csA = 1; p.rsB = 1; p.csB = Cout; p.rsC = g; p.csC = 1;
-    p.nb1 = 1; p.nb2 = Cin / g;
-    p.bA2 = (long long)g * Cout; p.bB2 = (long long)g * Cout; p.bC2 = (long long)g * g;
-    p.nsum = K; p.sA = per; p.sB = per;
-    rc = smm(p, st);
-    if (rc) return rc;
-  }
-  if (gbar) {
+  if (dWeff && !dweff_done) { rc = smm(pw, st); if (rc) return rc; }
+  if (gbar && !gbar_done) {
     // gbar = sum_k Wk[k] s[k]
     WcSmm p = smm_init();
     p.A = Wk; p.B = s; p.C = gbar; p.M = Cin; p.N = 1; p.K = Cout;
@@ -717,15 +966,15 @@ extern "C" size_t wc_factor_bwd_workspace_bytes(int C, int g, int decomposition,
   return 3 * gg_bytes(C, g);
 }
 
-extern "C" int wc_factor_bwd(const float* dWeff, const float* gbar, const float* Weff, const float* Wm, const float* R,
-                             const float* U, const float* lam, const float* count_dev, double count_host, int C, int g,
-                             float eps, int decomposition, int renorm, float* A, float* cvec, float* workspace,
-                             size_t workspace_bytes, wc_stream_t stream) {
+int wc_factor_bwd_impl(const float* dWeff, const float* gbar, const float* Weff, const float* Wm, const float* R,
+                       const float* U, const float* lam, const float* count_dev, double count_host, int C, int g,
+                       float eps, int decomposition, int renorm, float* A, float* cvec, float* workspace,
+                       size_t workspace_bytes, void* Tp_bwd, int pack_K, cudaStream_t st) {
+  // Tp_bwd (nullable): K6's packed operand buffer [pack_K images of T | image of A]; A's image is refreshed here
   if (!dWeff || !gbar || !Weff || !Wm || !A || !cvec || C <= 0 || g <= 0 || C % g) return WC_E_ARG;
   if (renorm && !R) return WC_E_ARG;
   if (decomposition == WC_DECOMP_ZCA && (!U || !lam)) return WC_E_ARG;
   if (!workspace || workspace_bytes < wc_factor_bwd_workspace_bytes(C, g, decomposition, renorm)) return WC_E_WORKSPACE;
-  cudaStream_t st = (cudaStream_t)stream;
   const int G = C / g;
   const size_t gb = gg_bytes(C, g);
   char* ws = reinterpret_cast<char*>(workspace);
@@ -741,27 +990,56 @@ extern "C" int wc_factor_bwd(const float* dWeff, const float* gbar, const float*
     if (rc) return rc;
     dWm = W2;
   }
+  // cvec = Weff^T gbar / count
+  VecJob vc{};
+  vc.A = Weff; vc.x = gbar; vc.out = cvec; vc.M = g; vc.K = g; vc.rsA = 1; vc.csA = g;
+  vc.nsum = 1; vc.nb = G; vc.bA = (long long)g * g; vc.bx = g; vc.bo = g;
+  vc.count_dev = count_dev; vc.count_host = ch; vc.count_mode = 1; vc.alpha = 1.f;
+  bool cvec_done = false, packed = false;
   if (decomposition == WC_DECOMP_CHOLESKY) {
-    // Phi = -(tril(Z) - diag(Z)/2),  Z = dWm Wm^T
-    WcSmm p = smm_gg(dWm, false, Wm, true, W0, g, G);
-    p.alpha = -1.f; p.tri = 1;
-    rc = smm(p, st, nullptr, 0.f, 0, 0.5f);
-    if (rc) return rc;
-    rc = smm(smm_gg(W0, false, Wm, false, W1, g, G), st);     // Y = Phi Wm
-    if (rc) return rc;
-    rc = smm(smm_gg(Wm, true, W1, false, W0, g, G), st);      // Qs = Wm^T Y
-    if (rc) return rc;
-    // A = (1-eps) (Qs + Qs^T) / (count-1)
-    sym_scale_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(W0, 1.f - eps, count_dev, ch, 1, C, g, A);
-    WC_CHECK_LAUNCH();
+    // Z = dWm Wm^T;  Phi = -(tril(Z) - diag(Z)/2);  dSigma' = sym(Wm^T Phi Wm)
+    const WcSmm pz = smm_gg(dWm, false, Wm, true, W0, g, G);
+    const WcSmm py = smm_gg(W0, false, Wm, false, W1, g, G);
+    WcSmm pa = smm_gg(Wm, true, W1, false, A, g, G);
+    if (smm_is_fast(pz) && smm_is_fast(py) && smm_is_fast(pa)) {
+      // three launches: Psi = Phi + Phi^T straight from the lower tiles of Z (+ cvec);  Y = Psi Wm;
+      // A = (1-eps)/(count-1) Wm^T Y, which also leaves as the bf16 operand image of K6
+      MultiLaunch m1, m2, m3;
+      SmmEpi e1{}; e1.kind = EPI_PSI;
+      m1.add(pz, e1);
+      cvec_done = m1.add_vec(vc);
+      rc = m1.launch(st); if (rc) return rc;
+      m2.add(py);
+      rc = m2.launch(st); if (rc) return rc;
+      pa.alpha = 1.f - eps;
+      SmmEpi e3{};
+      if (Tp_bwd && g == C) {
+        e3.kind = EPI_PACK; e3.pk0 = (uint8_t*)Tp_bwd + (size_t)pack_K * C * C * 4; e3.pkC = C;
+        packed = true;
+      }
+      if (!m3.add(pa, e3, count_dev, ch, 2, 1.f)) return WC_E_UNSUPPORTED;
+      rc = m3.launch(st); if (rc) return rc;
+    } else {
+      WcSmm p = pz;
+      p.alpha = -1.f; p.tri = 1;
+      rc = smm(p, st, nullptr, 0.f, 0, 0.5f);
+      if (rc) return rc;
+      rc = smm(py, st);     // Y = Phi Wm
+      if (rc) return rc;
+      rc = smm(smm_gg(Wm, true, W1, false, W0, g, G), st);      // Qs = Wm^T Y
+      if (rc) return rc;
+      // A = (1-eps) (Qs + Qs^T) / (count-1)
+      WC_CUDA(wc_launch(sym_scale_kernel, wc_cdiv(total, 256), 256, 0, st, W0, 1.f - eps, count_dev, ch, 1, C, g, A));
+      WC_CHECK_LAUNCH();
+    }
   } else {
-    sym_scale_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(dWm, 0.5f, nullptr, 0.f, 0, C, g, W0);   // sym(dWm)
+    WC_CUDA(wc_launch(sym_scale_kernel, wc_cdiv(total, 256), 256, 0, st, dWm, 0.5f, nullptr, 0.f, 0, C, g, W0));   // sym(dWm)
     WC_CHECK_LAUNCH();
     rc = smm(smm_gg(U, true, W0, false, W1, g, G), st);       // U^T sym
     if (rc) return rc;
     rc = smm(smm_gg(W1, false, U, false, W0, g, G), st);      // (U^T sym) U
     if (rc) return rc;
-    zca_mulF_kernel<<<wc_cdiv(total, 256), 256, 0, st>>>(W0, lam, C, g);
+    WC_CUDA(wc_launch(zca_mulF_kernel, wc_cdiv(total, 256), 256, 0, st, W0, lam, C, g));
     WC_CHECK_LAUNCH();
     rc = smm(smm_gg(U, false, W0, false, W1, g, G), st);      // U (.)
     if (rc) return rc;
@@ -770,12 +1048,25 @@ extern "C" int wc_factor_bwd(const float* dWeff, const float* gbar, const float*
     rc = smm(p, st, count_dev, ch, 2, 1.f);
     if (rc) return rc;
   }
-  // cvec = Weff^T gbar / count
-  WcSmm p = smm_init();
-  p.A = Weff; p.B = gbar; p.C = cvec; p.M = g; p.N = 1; p.K = g;
-  p.rsA = 1; p.csA = g; p.rsB = 1; p.csB = 0; p.rsC = 1; p.csC = 1;
-  p.nb1 = 1; p.nb2 = G; p.bA2 = (long long)g * g; p.bB2 = g; p.bC2 = g;
-  return smm(p, st, count_dev, ch, 1, 1.f);
+  if (!cvec_done) {
+    MultiLaunch mv;
+    mv.add_vec(vc);
+    rc = mv.launch(st);
+    if (rc) return rc;
+  }
+  if (Tp_bwd && !packed) {
+    rc = wc_pack_bwd(nullptr, A, C, g, pack_K, Tp_bwd, (wc_stream_t)st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int wc_factor_bwd(const float* dWeff, const float* gbar, const float* Weff, const float* Wm, const float* R,
+                             const float* U, const float* lam, const float* count_dev, double count_host, int C, int g,
+                             float eps, int decomposition, int renorm, float* A, float* cvec, float* workspace,
+                             size_t workspace_bytes, wc_stream_t stream) {
+  return wc_factor_bwd_impl(dWeff, gbar, Weff, Wm, R, U, lam, count_dev, count_host, C, g, eps, decomposition, renorm, A, cvec,
+                            workspace, workspace_bytes, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" int wc_version(void) { return WC_B200_VERSION; }
@@ -789,6 +1080,10 @@ extern "C" long long wc_launch_count(void) { return g_launches.load(std::memory_
 static int g_dbg_flags = 0;
 static unsigned long long* g_dbg_buf = nullptr;
 int wc_debug_flags() { return g_dbg_flags; }
+bool wc_pdl_enabled() {
+  static const bool env_off = getenv("WC_B200_NO_PDL") != nullptr;    // A/B measurements
+  return !env_off && !(g_dbg_flags & 8192);
+}
 unsigned long long* wc_debug_buf() { return (g_dbg_flags & 1) ? g_dbg_buf : nullptr; }
 extern "C" int wc_debug_set(int flags) {
   g_dbg_flags = flags;

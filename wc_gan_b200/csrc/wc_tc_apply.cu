@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
   __syncthreads();
   tc_fence_after();
   const uint32_t td = tmem_slot;
+  wc_pdl_wait();      // barriers, tensor maps and TMEM were set up while the previous kernel drained
   if (t == 0) wc_mark(p.dbg, 0);
 
   if (warp == W_PROD) {
@@ -306,6 +307,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
 // mode 2: src(n,k) = blockdiag(A (G,g,g))[k][n]  (K6 term 2).
 __global__ void __launch_bounds__(256) pack_b_kernel(const float* __restrict__ M, int C, int nslots, long long slot_stride_in,
                                                      int mode, int g, uint8_t* __restrict__ out, long long slot_stride_out) {
+  wc_pdl_wait();
   const int nkb = C / KB;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long per_slot = (long long)C * nkb * 4;        // chunks per slot
@@ -368,7 +370,7 @@ int launch_tc_apply_r(const TcApplyParams& p, const CUtensorMap& tm_a0, const CU
     attr_set = true;
   }
   const unsigned grid = (unsigned)(p.total_tiles < WC_NUM_SMS ? p.total_tiles : WC_NUM_SMS);
-  tc_apply_kernel<C, R><<<grid, NTHREADS, Cfg<C, R>::SMEM, st>>>(p, tm_a0, tm_a1, tm_out);
+  WC_CUDA(wc_launch(tc_apply_kernel<C, R>, grid, NTHREADS, Cfg<C, R>::SMEM, st, p, tm_a0, tm_a1, tm_out));
   WC_CHECK_LAUNCH();
   return 0;
 }
@@ -420,8 +422,8 @@ extern "C" int wc_pack_fwd(const float* T, int C, int K, void* packed, wc_stream
   if (!T || !packed || K <= 0) return WC_E_ARG;
   if (!tc_shape_ok(C, C)) return WC_E_UNSUPPORTED;
   long long chunks = (long long)K * C * (C / KB) * 4;
-  pack_b_kernel<<<wc_cdiv(chunks, 256), 256, 0, (cudaStream_t)stream>>>(T, C, K, (long long)C * C, 0, C, (uint8_t*)packed,
-                                                                       (long long)C * C * 4);
+  WC_CUDA(wc_launch(pack_b_kernel, wc_cdiv(chunks, 256), 256, 0, (cudaStream_t)stream, T, C, K, (long long)C * C, 0, C, (uint8_t*)packed,
+                                                                       (long long)C * C * 4));
   WC_CHECK_LAUNCH();
   return 0;
 }
@@ -433,12 +435,12 @@ extern "C" int wc_pack_bwd(const float* T, const float* A, int C, int g, int K, 
   cudaStream_t st = (cudaStream_t)stream;
   long long chunks = (long long)K * C * (C / KB) * 4;
   if (T) {    // T == NULL: T's image is already in place (packed once in forward), only A's is refreshed
-    pack_b_kernel<<<wc_cdiv(chunks, 256), 256, 0, st>>>(T, C, K, (long long)C * C, 1, C, (uint8_t*)packed, (long long)C * C * 4);
+    WC_CUDA(wc_launch(pack_b_kernel, wc_cdiv(chunks, 256), 256, 0, st, T, C, K, (long long)C * C, 1, C, (uint8_t*)packed, (long long)C * C * 4));
     WC_CHECK_LAUNCH();
   }
   if (A) {
     chunks = (long long)C * (C / KB) * 4;
-    pack_b_kernel<<<wc_cdiv(chunks, 256), 256, 0, st>>>(A, C, 1, 0, 2, g, (uint8_t*)packed + (size_t)K * C * C * 4, 0);
+    WC_CUDA(wc_launch(pack_b_kernel, wc_cdiv(chunks, 256), 256, 0, st, A, C, 1, 0, 2, g, (uint8_t*)packed + (size_t)K * C * C * 4, 0));
     WC_CHECK_LAUNCH();
   }
   return 0;

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
   tc_fence_after();
   const uint32_t td = tmem_slot;
   const int nops = p.self ? 1 : 2;
+  wc_pdl_wait();      // barriers, tensor map and TMEM were set up while the previous kernel drained
   if (t == 0) wc_mark(p.dbg, 0);
 
   if (warp == NCONV_WARPS) {
@@ -410,7 +411,7 @@ int launch_tc_gram(TcGramParams& p, cudaStream_t st) {
   const long long sstride = p.out_slot_stride ? p.out_slot_stride : (long long)C * C;
   int rc = wc_make_f32_map3(&tm_out, p.out, C, C, (uint64_t)(p.nslots > 0 ? p.nslots : 1), (uint64_t)C * 4, (uint64_t)sstride * 4, 32, 32);
   if (rc) return rc;
-  tc_gram_kernel<C><<<(unsigned)ctas, NTHREADS, GCfg<C>::SMEM, st>>>(p, tm_out);
+  WC_CUDA(wc_launch(tc_gram_kernel<C>, (unsigned)ctas, NTHREADS, GCfg<C>::SMEM, st, p, tm_out));
   WC_CHECK_LAUNCH();
   return 0;
 }

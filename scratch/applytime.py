@@ -1,0 +1,39 @@
+"""debug: K3 / K6 alone with per-CTA globaltimer marks (start of main loop, end)"""
+import sys, ctypes, torch
+sys.path.insert(0, '/root/repo')
+import wc_gan_b200 as W  # noqa: F401
+from wc_gan_b200._lib import lib, ptr
+N, HW, C = 256, 256, 256
+M = N * HW
+dev = torch.device('cuda')
+NB = 4
+xs = [torch.randn(M, C, device=dev) + 1 for _ in range(NB)]
+dys = [torch.randn(M, C, device=dev) for _ in range(NB)]
+outs = [torch.empty(M, C, device=dev) for _ in range(2)]
+mean = torch.zeros(C, device=dev)
+T = torch.randn(C, C, device=dev) / 16; A = torch.randn(C, C, device=dev) / 1e4; b = torch.randn(C, device=dev)
+st = torch.cuda.current_stream().cuda_stream
+lib.wc_debug_set.argtypes = [ctypes.c_int]; lib.wc_debug_marks.argtypes = [ctypes.c_void_p]
+pf = torch.empty(lib.wc_pack_bytes(C, 1, 0) // 4, device=dev); pb = torch.empty(lib.wc_pack_bytes(C, 1, 1) // 4, device=dev)
+assert lib.wc_pack_fwd(ptr(T), C, 1, ptr(pf), st) == 0
+assert lib.wc_pack_bwd(ptr(T), ptr(A), C, C, 1, ptr(pb), st) == 0
+info = torch.zeros(4, dtype=torch.int32, device=dev)
+k3 = lambda i: lib.wc_apply_fwd(ptr(xs[i % NB]), N, HW, C, C, ptr(mean), ptr(T), ptr(pf), ptr(b), None, 1, 0, ptr(outs[i % 2]), ptr(info), st)
+k6 = lambda i: lib.wc_apply_bwd(ptr(xs[i % NB]), ptr(dys[i % NB]), N, HW, C, C, ptr(mean), ptr(T), ptr(A), ptr(pb), ptr(b), C, None, 1, ptr(outs[i % 2]), st)
+def marks(tag):
+    buf = (ctypes.c_ulonglong * (160 * 8))()
+    lib.wc_debug_marks(buf)
+    rows = [[buf[bb * 8 + k] for k in range(2)] for bb in range(148) if buf[bb * 8]]
+    t0 = min(r[0] for r in rows)
+    ends = [(r[1] - t0) / 1e3 for r in rows]
+    starts = [(r[0] - t0) / 1e3 for r in rows]
+    e4 = ends[:68]; e3 = ends[68:]
+    print(f'{tag}: start spread {max(starts):.2f} us | CTAs 0-67 (4 tiles) end avg {sum(e4)/len(e4):.1f} max {max(e4):.1f} | CTAs 68-147 (3 tiles) end avg {sum(e3)/max(1,len(e3)):.1f} max {max(e3) if e3 else 0:.1f}')
+for flags in (1, 1 | 256, 1 | 128 | 256, 1 | 64 | 128 | 256):
+    lib.wc_debug_set(flags)
+    for nm, fn in (('K3', k3), ('K6', k6)):
+        for i in range(3): fn(i)
+        torch.cuda.synchronize()
+        fn(3); torch.cuda.synchronize()
+        marks(f'flags {flags:4d} {nm}')
+lib.wc_debug_set(0)

@@ -364,3 +364,13 @@ def test_tensor_core_ragged_tiles(shape):
     run_case('n', 'ucconv', shape, K=3)
     if shape[0] * shape[1] * shape[2] > shape[3] + 1:
         run_case('d', 'ufconv', shape, K=3, E=2)
+
+
+@pytest.mark.parametrize('shape', [(3, 8, 8, 128), (5, 10, 10, 128), (37, 8, 8, 256), (150, 16, 16, 128)])
+def test_tensor_core_unconditional_tiling(shape):
+    """Unconditional layers view all samples as one run of rows: last tile partial (rows not a multiple of 128),
+    fewer tiles than SMs, and several tiles per CTA."""
+    from wc_gan_b200 import _lib
+    assert _lib.lib.wc_path_for(shape[0] * shape[1] * shape[2], shape[3], shape[3], shape[3]) & 1
+    run_case('d', 'uconv', shape)
+    run_case('n', 'uconv', shape)

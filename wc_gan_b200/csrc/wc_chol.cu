@@ -467,6 +467,21 @@ __device__ __forceinline__ void cl_wait(uint64_t* bar) {   // each flag is used 
       "bra CL_WAIT;\n\t"
       "CL_DONE:\n\t}" ::"r"(a) : "memory");
 }
+__device__ __forceinline__ uint32_t cl_map(uint32_t local_addr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  return ra;
+}
+__device__ __forceinline__ float4 cl_ld4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float cl_ld1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 // acc(4x8 per lane) += A(32x32, k-major, pitch PA) * B(32x32, k-major, pitch PB); GA / GB: operand lives in the global
@@ -537,26 +552,34 @@ __device__ void warp_potrf32_bc(float* T, float* rdiag, float* bc, int lane, int
 #pragma unroll
   for (int c = 0; c < 32; ++c) a[c] = T[c * TP + lane];
   float dg = T[lane * TP + lane];
+  // The serial chain per column is  pivot -> rsqrt -> l_k -> (diagonal of lane k+1, element (.,k+1)) -> next pivot.
+  // Both hand-overs to column k+1 go through shuffles; only the columns k+2.. take the (slower) broadcast through
+  // shared memory, which is off the chain.
+  float piv = __shfl_sync(FULL, dg, 0);
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
-    float piv = __shfl_sync(FULL, dg, k);
     if (!(piv > 0.f)) { if (!bad) bad = k + 1; piv = 1e-30f; }
     const float rs = rsqrt_approx(piv);
     const float lk = (lane == k) ? piv * rs : a[k] * rs;
     a[k] = lk;
-    dg = fmaf(-lk, lk, dg);
     if (lane == k) rdiag[k] = rs;
     if (k < 31) {
-      float* b = bc + (k & 1) * 32;
-      b[lane] = lk;
-      __syncwarp();
+      dg = fmaf(-lk, lk, dg);
+      piv = __shfl_sync(FULL, dg, k + 1);                  // lane k+1's diagonal is final after column k
+      const float lnext = __shfl_sync(FULL, lk, k + 1);    // L[k+1][k]
+      a[k + 1] = fmaf(-lk, lnext, a[k + 1]);
+      if (k < 30) {
+        float* b = bc + (k & 1) * 32;
+        b[lane] = lk;
+        __syncwarp();
 #pragma unroll
-      for (int q = (k + 1) / 4; q < 8; ++q) {
-        const float4 l = *reinterpret_cast<const float4*>(b + 4 * q);
-        if (4 * q + 0 > k) a[4 * q + 0] = fmaf(-lk, l.x, a[4 * q + 0]);
-        if (4 * q + 1 > k) a[4 * q + 1] = fmaf(-lk, l.y, a[4 * q + 1]);
-        if (4 * q + 2 > k) a[4 * q + 2] = fmaf(-lk, l.z, a[4 * q + 2]);
-        if (4 * q + 3 > k) a[4 * q + 3] = fmaf(-lk, l.w, a[4 * q + 3]);
+        for (int q = (k + 2) / 4; q < 8; ++q) {
+          const float4 l = *reinterpret_cast<const float4*>(b + 4 * q);
+          if (4 * q + 0 > k + 1) a[4 * q + 0] = fmaf(-lk, l.x, a[4 * q + 0]);
+          if (4 * q + 1 > k + 1) a[4 * q + 1] = fmaf(-lk, l.y, a[4 * q + 1]);
+          if (4 * q + 2 > k + 1) a[4 * q + 2] = fmaf(-lk, l.z, a[4 * q + 2]);
+          if (4 * q + 3 > k + 1) a[4 * q + 3] = fmaf(-lk, l.w, a[4 * q + 3]);
+        }
       }
     }
   }
@@ -670,8 +693,18 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
         if (J == r - 1) CL_MARK(2);
         cl_wait(&flagB[J]);
         if (J == r - 1) CL_MARK(3);
-        fetch_tile_warp(gtile(J, J), ljj, lane);
-        rd_stage[lane] = __ldcg(gR + J * TB + lane);
+        {   // L_JJ and 1/diag straight out of CTA J's shared memory (same offsets in every CTA of the cluster)
+          const int cq = lane >> 3, q8 = lane & 7;
+          const uint32_t rt = cl_map((uint32_t)__cvta_generic_to_shared(own + J * TS), (uint32_t)J);
+          const uint32_t rr = cl_map((uint32_t)__cvta_generic_to_shared(rd_own), (uint32_t)J);
+          float4 v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = cl_ld4(rt + (uint32_t)(((4 * e + cq) * TP + 4 * q8) * 4));
+          const float rdv = cl_ld1(rr + (uint32_t)lane * 4u);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) *reinterpret_cast<float4*>(ljj + (4 * e + cq) * TP + 4 * q8) = v[e];
+          rd_stage[lane] = rdv;
+        }
         __syncwarp();
         float x[32];
 #pragma unroll
@@ -713,9 +746,7 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
       CL_MARK(7);
       if (bad && lane == 0 && info) atomicCAS(&info[WC_INFO_NOT_PD], 0, grp * g + r * TB + bad);
       __syncwarp();
-      publish_tile(T, gtile(r, r), lane);
-      gR[r * TB + lane] = rd_own[lane];
-      cl_fence();
+      cl_fence();         // the tile and 1/diag stay in this CTA's shared memory; the peers read them there
       __syncwarp();
       if (lane < NB && lane != r) cl_arrive_remote(&flagB[r], lane);
       CL_MARK(8);

@@ -254,6 +254,35 @@ __global__ void stats_finalize_kernel(const float* __restrict__ partS, const flo
   if (rem % g == rem / g) mean[i] = (float)((double)pivot[i] + ddi);
 }
 
+// Tensor-core path, single process: finalize and the K2 prep step (covariance scaling, moving averages, shrinkage;
+// see factor_prep_kernel in wc_small.cu) in one launch.  The scatter is read from its lower triangle, so S and the
+// covariance are exactly symmetric.
+__global__ void stats_finalize_prep_kernel(const float* __restrict__ partS, const float* __restrict__ partSum, int C, int g,
+                                           double M, const float* __restrict__ pivot, float* __restrict__ mean,
+                                           float* __restrict__ S, WcPrepFuse f) {
+  wc_pdl_wait();
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)C * g;
+  if (idx >= total) return;
+  int grp = (int)(idx / ((long long)g * g));
+  int rem = (int)(idx % ((long long)g * g));
+  int r = rem / g, c = rem % g;
+  int i = grp * g + r, j = grp * g + c;
+  const float s = partS[(long long)max(i, j) * C + min(i, j)];
+  const float di = partSum[i], dj = partSum[j];
+  const double ddi = (double)di / M, ddj = (double)dj / M;
+  const float sv = (float)((double)s - M * ddi * ddj);
+  S[idx] = sv;
+  const float cov = sv / ((float)M - 1.f);
+  f.moving_cov[idx] = f.moving_cov[idx] * f.momentum + cov * (1.f - f.momentum);        // conditional_layers.py:687-689
+  if (r == c) {
+    const float mu = (float)((double)pivot[i] + ddi);
+    mean[i] = mu;
+    f.moving_mean[i] = f.moving_mean[i] * f.momentum + mu * (1.f - f.momentum);          // :684-686
+  }
+  f.Ashr[idx] = (1.f - f.eps) * cov + (r == c ? f.eps + f.extra_eps : 0.f);              // :691 (+ :671 for ZCA)
+}
+
 // Chan merge of R shard records {mean[C], S[G g g], count}
 __global__ void stats_merge_kernel(const float* __restrict__ rec, int R, int C, int g,
                                    float* __restrict__ mean, float* __restrict__ S, float* __restrict__ count_total) {
@@ -344,6 +373,14 @@ extern "C" size_t wc_stats_workspace_bytes(int64_t M, int C, int g) {
 
 extern "C" int wc_stats_fwd(const float* x, int64_t M, int C, int g, float* workspace, size_t workspace_bytes,
                             float* mean, float* S, wc_stream_t stream) {
+  return wc_stats_fwd_impl(x, M, C, g, workspace, workspace_bytes, mean, S, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+// fuse (nullable): also run the prep step of wc_factor_fwd when the tensor-core path is taken; *fused reports whether
+// that happened (the caller then tells wc_factor_fwd_impl to skip its own prep launch)
+int wc_stats_fwd_impl(const float* x, int64_t M, int C, int g, float* workspace, size_t workspace_bytes,
+                      float* mean, float* S, const WcPrepFuse* fuse, int* fused, cudaStream_t stream) {
+  if (fused) *fused = 0;
   if (!x || !workspace || !mean || !S || M <= 0 || C <= 0 || g <= 0 || C % g) return WC_E_ARG;
   if (M > (int64_t)INT32_MAX) return WC_E_UNSUPPORTED;
   StatsPlan pl = plan_stats(M, C, g);
@@ -362,6 +399,12 @@ extern "C" int wc_stats_fwd(const float* x, int64_t M, int C, int g, float* work
     int rc = wc_tc_gram_self(x, M, C, g, pivot, pS, psum, st);
     if (rc) return rc;
     long long tot = (long long)C * g;
+    if (fuse) {
+      WC_CUDA(wc_launch(stats_finalize_prep_kernel, wc_cdiv(tot, 256), 256, 0, st, pS, psum, C, g, (double)M, pivot, mean, S, *fuse));
+      WC_CHECK_LAUNCH();
+      if (fused) *fused = 1;
+      return 0;
+    }
     WC_CUDA(wc_launch(stats_finalize_kernel, wc_cdiv(tot, 256), 256, 0, st, pS, psum, 1, (long long)C * C, C, g, (double)M, pivot, mean, S, 1));
     WC_CHECK_LAUNCH();
     return 0;

@@ -16,6 +16,9 @@ struct Carver {
 
 inline bool conditional(const WcLayerCall& c) { return c.K > 1 && c.cls != nullptr; }
 inline bool has_coloring(const WcLayerCall& c) { return c.Wu || c.Wc || c.D; }
+// only the unconditional kernel, one class: the per-class matrix IS Wu and the bias IS bu (nothing to build or to save;
+// the caller keeps both alive and unmodified between the two directions: they are autograd-saved tensors)
+inline bool plain_u(const WcLayerCall& c) { return c.K == 1 && c.Wu && !c.Wc && !c.D && !c.class_matrix && !c.bc && !c.bf; }
 inline bool use_tc(const WcLayerCall& c) {
   return c.use_tensor_cores && (wc_path_for((int64_t)c.N * c.HW, c.Cin, c.Cout, c.g) & 1);
 }
@@ -112,9 +115,15 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
   const bool train_w = c.whiten && c.training;
   if (c.whiten && (!c.moving_mean || !c.moving_cov)) return WC_E_ARG;
 
+  int prep_done = 0;
   if ((c.phases & WC_PHASE_STATS) && train_w) {
-    rc = wc_stats_fwd(c.x, M, c.Cin, c.g, at<float>(c.workspace, W.stats), W.stats_bytes, at<float>(c.saved, L.mean),
-                      at<float>(c.saved, L.S), stream);
+    // single process, no renorm: the finalize kernel of the statistics also scales / shrinks the covariance and
+    // updates the moving averages (K2's prep step), one launch less on the serial path
+    const bool can_fuse = (c.phases & WC_PHASE_APPLY) && c.y && !c.renorm && !c.mean_ext && !c.S_ext && !c.count_dev;
+    WcPrepFuse f{c.eps, c.decomposition == WC_DECOMP_ZCA ? c.eps : 0.f, c.momentum, c.moving_mean, c.moving_cov,
+                 at<float>(c.workspace, W.factor)};
+    rc = wc_stats_fwd_impl(c.x, M, c.Cin, c.g, at<float>(c.workspace, W.stats), W.stats_bytes, at<float>(c.saved, L.mean),
+                           at<float>(c.saved, L.S), can_fuse ? &f : nullptr, &prep_done, (cudaStream_t)stream);
     if (rc) return rc;
   }
   if (!(c.phases & WC_PHASE_APPLY)) return 0;
@@ -131,10 +140,11 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
     } else {
       mean = c.moving_mean;
     }
-    rc = wc_factor_fwd(train_w ? mean : nullptr, S, c.count_dev, c.count, c.Cin, c.g, c.eps, c.momentum, c.decomposition,
-                       c.renorm, c.training, c.moving_mean, c.moving_cov, at<float>(c.saved, L.Weff),
-                       at<float>(c.saved, train_w ? L.Wm : L.Weff), at<float>(c.saved, L.R), at<float>(c.saved, L.U),
-                       at<float>(c.saved, L.lam), c.info, at<float>(c.workspace, W.factor), W.factor_bytes, stream);
+    rc = wc_factor_fwd_impl(train_w ? mean : nullptr, S, c.count_dev, c.count, c.Cin, c.g, c.eps, c.momentum, c.decomposition,
+                            c.renorm, c.training, c.moving_mean, c.moving_cov, at<float>(c.saved, L.Weff),
+                            at<float>(c.saved, train_w ? L.Wm : L.Weff), at<float>(c.saved, L.R), at<float>(c.saved, L.U),
+                            at<float>(c.saved, L.lam), c.info, at<float>(c.workspace, W.factor), W.factor_bytes, prep_done,
+                            (cudaStream_t)stream);
     if (rc) return rc;
   }
   // identity coloring (after_norm == 'n', generator.py:79-80): W_k = I is written by the compose kernel from Wu == NULL
@@ -142,10 +152,10 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
   rc = wc_compose_fwd_impl(at<float>(c.saved, L.Weff), c.Cin, c.Cout, c.whiten ? c.g : c.Cin, c.K, c.Wu, c.bu, c.Wc, c.bc,
                            c.triangular, c.class_matrix, c.D, c.E, c.bf, at<float>(c.saved, L.ehat), at<float>(c.saved, L.Wk),
                            at<float>(c.saved, L.T), at<float>(c.saved, L.b), Tp, Tp ? at<void>(c.saved, L.Tp_bwd) : nullptr,
-                           (cudaStream_t)stream);
+                           plain_u(c) ? c.Wu : nullptr, (cudaStream_t)stream);
   if (rc) return rc;
   const int band = (c.whiten && !has_coloring(c) && c.g < c.Cin) ? c.g : 0;
-  return wc_apply_fwd(c.x, c.N, c.HW, c.Cin, c.Cout, mean, at<float>(c.saved, L.T), Tp, at<float>(c.saved, L.b),
+  return wc_apply_fwd(c.x, c.N, c.HW, c.Cin, c.Cout, mean, at<float>(c.saved, L.T), Tp, plain_u(c) ? c.bu : at<float>(c.saved, L.b),
                       conditional(c) ? c.cls : nullptr, c.K, band, c.y, c.info, stream);
 }
 
@@ -173,7 +183,7 @@ extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
     rc = wc_reduce_bwd(c.x, c.dy, c.N, c.HW, c.Cin, c.Cout, mean, cls, c.K, P, s, at<float>(c.workspace, W.reduce),
                        W.reduce_bytes, stream);
     if (rc) return rc;
-    rc = wc_color_bwd(P, s, at<float>(c.saved, L.Weff), at<float>(c.saved, L.Wk), c.Cin, c.Cout, g, c.K, c.dWu, c.dbu, c.dWc,
+    rc = wc_color_bwd(P, s, at<float>(c.saved, L.Weff), plain_u(c) ? c.Wu : at<float>(c.saved, L.Wk), c.Cin, c.Cout, g, c.K, c.dWu, c.dbu, c.dWc,
                       c.dbc, c.triangular, c.class_matrix, at<float>(c.saved, L.ehat), c.D, c.E, c.dD, c.dclass_matrix, c.dbf,
                       stats_grad ? c.red : nullptr, stats_grad ? c.red + gg : nullptr, at<float>(c.workspace, W.color),
                       W.color_bytes, stream);

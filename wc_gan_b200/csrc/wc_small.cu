@@ -752,6 +752,17 @@ extern "C" int wc_factor_fwd(const float* mean, const float* S, const float* cou
                              float eps, float momentum, int decomposition, int renorm, int training,
                              float* moving_mean, float* moving_cov, float* Weff, float* Wm, float* R, float* U,
                              float* lam, int32_t* info, float* workspace, size_t workspace_bytes, wc_stream_t stream) {
+  return wc_factor_fwd_impl(mean, S, count_dev, count_host, C, g, eps, momentum, decomposition, renorm, training, moving_mean,
+                            moving_cov, Weff, Wm, R, U, lam, info, workspace, workspace_bytes, 0, (cudaStream_t)stream);
+}
+
+// prep_done: the shrunk covariance is already at the start of `workspace` and the moving averages are updated
+// (stats_finalize_prep_kernel); only valid for training without renorm
+int wc_factor_fwd_impl(const float* mean, const float* S, const float* count_dev, double count_host, int C, int g,
+                       float eps, float momentum, int decomposition, int renorm, int training,
+                       float* moving_mean, float* moving_cov, float* Weff, float* Wm, float* R, float* U,
+                       float* lam, int32_t* info, float* workspace, size_t workspace_bytes, int prep_done, cudaStream_t stream) {
+  if (prep_done && (!training || renorm)) return WC_E_ARG;
   if (C <= 0 || g <= 0 || C % g || !moving_cov || !Weff || !workspace) return WC_E_ARG;
   if (training && (!mean || !S || !moving_mean || !Wm)) return WC_E_ARG;
   if (decomposition != WC_DECOMP_CHOLESKY && decomposition != WC_DECOMP_ZCA) return WC_E_ARG;
@@ -793,9 +804,11 @@ extern "C" int wc_factor_fwd(const float* mean, const float* S, const float* cou
     rc = factor_matrix(Amov, C, g, decomposition, Wmov, nullptr, Umov, R, L, Bm, Us, Xpad, info, st);
     if (rc) return rc;
   }
-  WC_CUDA(wc_launch(factor_prep_kernel, wc_cdiv(total, 256), 256, 0, st, mean, S, count_dev, (float)count_host, C, g, eps, extra, momentum, 1,
-                                                          moving_mean, moving_cov, Ashr));
-  WC_CHECK_LAUNCH();
+  if (!prep_done) {
+    WC_CUDA(wc_launch(factor_prep_kernel, wc_cdiv(total, 256), 256, 0, st, mean, S, count_dev, (float)count_host, C, g, eps, extra, momentum, 1,
+                                                            moving_mean, moving_cov, Ashr));
+    WC_CHECK_LAUNCH();
+  }
   rc = factor_matrix(Ashr, C, g, decomposition, Wm, renorm ? Lb : nullptr, U, lam, L, Bm, Us, Xpad, info, st);
   if (rc) return rc;
   if (renorm) {
@@ -815,20 +828,25 @@ extern "C" int wc_factor_fwd(const float* mean, const float* S, const float* cou
 int wc_compose_fwd_impl(const float* Weff, int Cin, int Cout, int g, int K, const float* Wu, const float* bu,
                         const float* Wc, const float* bc, int triangular, const float* class_matrix,
                         const float* D, int E, const float* bf, float* ehat, float* Wk, float* T, float* b,
-                        void* Tp_fwd, void* Tp_bwd, cudaStream_t st) {
-  if (Cin <= 0 || Cout <= 0 || K <= 0 || !Wk || !T) return WC_E_ARG;
+                        void* Tp_fwd, void* Tp_bwd, const float* Wk_ready, cudaStream_t st) {
+  // Wk_ready (nullable): the per-class matrix already exists (K == 1 with only the unconditional kernel: it IS Wu, and the
+  // bias is bu); nothing is built and `Wk` / `b` are not written
+  if (Cin <= 0 || Cout <= 0 || K <= 0 || (!Wk && !Wk_ready) || !T) return WC_E_ARG;
   if (Weff && (g <= 0 || Cin % g)) return WC_E_ARG;
   if (class_matrix && (!D || E <= 0 || !ehat)) return WC_E_ARG;
   long long per = (long long)Cin * Cout;
-  WC_CUDA(wc_launch(build_wk_kernel, wc_cdiv(per * K, 256), 256, 0, st, Cin, Cout, K, Wu, bu, Wc, bc, triangular, class_matrix, D, E, bf,
-                                                         ehat, Wk, b, (!Wu && !Wc && !D) ? 1 : 0));
-  WC_CHECK_LAUNCH();
+  if (!Wk_ready) {
+    WC_CUDA(wc_launch(build_wk_kernel, wc_cdiv(per * K, 256), 256, 0, st, Cin, Cout, K, Wu, bu, Wc, bc, triangular, class_matrix, D, E, bf,
+                                                           ehat, Wk, b, (!Wu && !Wc && !D) ? 1 : 0));
+    WC_CHECK_LAUNCH();
+  }
+  const float* Wsrc = Wk_ready ? Wk_ready : Wk;
   int rc = 0;
   bool packed = false;
   if (!Weff) {
-    if (T != Wk) WC_CUDA(cudaMemcpyAsync(T, Wk, (size_t)per * K * 4, cudaMemcpyDeviceToDevice, st));
+    if (T != Wsrc) WC_CUDA(cudaMemcpyAsync(T, Wsrc, (size_t)per * K * 4, cudaMemcpyDeviceToDevice, st));
   } else {
-    const WcSmm p = smm_blockdiag_left(Weff, true, Wk, T, g, Cin / g, Cout, Cout, K, per);
+    const WcSmm p = smm_blockdiag_left(Weff, true, Wsrc, T, g, Cin / g, Cout, Cout, K, per);
     MultiLaunch ml;
     SmmEpi ep{};
     if (Tp_fwd || Tp_bwd) {   // T leaves the product tile as fp32 and as the bf16 operand images of K3 / K6
@@ -855,7 +873,7 @@ extern "C" int wc_compose_fwd(const float* Weff, int Cin, int Cout, int g, int K
                               const float* D, int E, const float* bf, float* ehat, float* Wk, float* T, float* b,
                               wc_stream_t stream) {
   return wc_compose_fwd_impl(Weff, Cin, Cout, g, K, Wu, bu, Wc, bc, triangular, class_matrix, D, E, bf, ehat, Wk, T, b,
-                             nullptr, nullptr, (cudaStream_t)stream);
+                             nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 // =============================================================================================

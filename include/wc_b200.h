@@ -215,6 +215,14 @@ typedef struct WcLayerCall {
   /* caller-owned memory */
   void* saved;     size_t saved_bytes;
   void* workspace; size_t workspace_bytes;
+  /* synchronised-batch statistics over peer memory (one node, NVLink P2P): every rank maps a symmetric buffer of
+     wc_exchange_bytes() zero-initialised bytes; xchg_peers is a DEVICE array of xchg_world pointers to those buffers in
+     rank order, xchg_state 16 zero-initialised device bytes owned by this rank.  With these set, training calls with
+     both phases exchange the shard records (forward) and the adjoint `red` (backward) inside the call; count is this
+     shard's row count.  NULL: single process, or the host runs the collectives between the phases. */
+  void* const* xchg_peers;
+  void* xchg_state;
+  int32_t xchg_rank, xchg_world;
 } WcLayerCall;
 
 /* byte offsets into `saved` ((size_t)-1 when the piece does not exist for this configuration) */
@@ -223,6 +231,8 @@ typedef struct WcSavedLayout {
   size_t Weff, Wm, R, U, lam, Wk, T, b, ehat, Tp_fwd, Tp_bwd, A, cvec, total;
 } WcSavedLayout;
 
+/* bytes of the symmetric exchange buffer for one (C, g) on `world` ranks (0: unsupported) */
+size_t wc_exchange_bytes(int C, int g, int world);
 int wc_layer_saved_layout(const WcLayerCall* c, WcSavedLayout* out);
 size_t wc_layer_saved_bytes(const WcLayerCall* c);
 size_t wc_layer_workspace_bytes(const WcLayerCall* c, int backward);

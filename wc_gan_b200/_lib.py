@@ -42,7 +42,8 @@ class WcLayerCall(ctypes.Structure):
                 [(n, c_void_p) for n in ('count_dev', 'Wu', 'bu', 'Wc', 'bc', 'class_matrix', 'D', 'bf', 'moving_mean',
                                          'moving_cov', 'cls', 'info', 'x', 'y', 'mean_ext', 'S_ext', 'dy', 'dx', 'dWu',
                                          'dbu', 'dWc', 'dbc', 'dclass_matrix', 'dD', 'dbf', 'red')] +
-                [('saved', c_void_p), ('saved_bytes', c_size_t), ('workspace', c_void_p), ('workspace_bytes', c_size_t)])
+                [('saved', c_void_p), ('saved_bytes', c_size_t), ('workspace', c_void_p), ('workspace_bytes', c_size_t)] +
+                [('xchg_peers', c_void_p), ('xchg_state', c_void_p), ('xchg_rank', c_int32), ('xchg_world', c_int32)])
 
 
 class WcSavedLayout(ctypes.Structure):
@@ -77,6 +78,7 @@ _SIGS = {
     'wc_factor_bwd': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_double, c_int, c_int, c_float, c_int, c_int,
                               _P, _P, _P, c_size_t, _P]),
     'wc_apply_bwd': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, c_int, _P, _P]),
+    'wc_exchange_bytes': (c_size_t, [c_int, c_int, c_int]),
     'wc_layer_saved_layout': (c_int, [ctypes.POINTER(WcLayerCall), ctypes.POINTER(WcSavedLayout)]),
     'wc_layer_saved_bytes': (c_size_t, [ctypes.POINTER(WcLayerCall)]),
     'wc_layer_workspace_bytes': (c_size_t, [ctypes.POINTER(WcLayerCall), c_int]),

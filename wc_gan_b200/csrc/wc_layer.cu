@@ -19,6 +19,15 @@ inline bool has_coloring(const WcLayerCall& c) { return c.Wu || c.Wc || c.D; }
 // only the unconditional kernel, one class: the per-class matrix IS Wu and the bias IS bu (nothing to build or to save;
 // the caller keeps both alive and unmodified between the two directions: they are autograd-saved tensors)
 inline bool plain_u(const WcLayerCall& c) { return c.K == 1 && c.Wu && !c.Wc && !c.D && !c.class_matrix && !c.bc && !c.bf; }
+// statistics and adjoint exchanged over peer memory inside the call (training, whole call, more than one rank)
+inline bool xchg_fwd(const WcLayerCall& c) {
+  return c.xchg_peers && c.xchg_state && c.xchg_world > 1 && c.whiten && c.training && !c.renorm &&
+         (c.phases & WC_PHASE_STATS) && (c.phases & WC_PHASE_APPLY);
+}
+inline bool xchg_bwd(const WcLayerCall& c) {
+  return c.xchg_peers && c.xchg_state && c.xchg_world > 1 && c.whiten && c.training && !c.renorm && c.dx &&
+         (c.phases & WC_PHASE_REDUCE) && (c.phases & WC_PHASE_DX);
+}
 inline bool use_tc(const WcLayerCall& c) {
   return c.use_tensor_cores && (wc_path_for((int64_t)c.N * c.HW, c.Cin, c.Cout, c.g) & 1);
 }
@@ -119,7 +128,7 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
   if ((c.phases & WC_PHASE_STATS) && train_w) {
     // single process, no renorm: the finalize kernel of the statistics also scales / shrinks the covariance and
     // updates the moving averages (K2's prep step), one launch less on the serial path
-    const bool can_fuse = (c.phases & WC_PHASE_APPLY) && c.y && !c.renorm && !c.mean_ext && !c.S_ext && !c.count_dev;
+    const bool can_fuse = (c.phases & WC_PHASE_APPLY) && c.y && !c.renorm && !c.mean_ext && !c.S_ext && !c.count_dev && !xchg_fwd(c);
     WcPrepFuse f{c.eps, c.decomposition == WC_DECOMP_ZCA ? c.eps : 0.f, c.momentum, c.moving_mean, c.moving_cov,
                  at<float>(c.workspace, W.factor)};
     rc = wc_stats_fwd_impl(c.x, M, c.Cin, c.g, at<float>(c.workspace, W.stats), W.stats_bytes, at<float>(c.saved, L.mean),
@@ -128,6 +137,16 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
   }
   if (!(c.phases & WC_PHASE_APPLY)) return 0;
   if (!c.y) return WC_E_ARG;
+  const float* count_dev = c.count_dev;
+  if (xchg_fwd(c)) {
+    // shard record -> every rank; Chan merge + prep from the complete set; saved mean | S | count become global
+    rc = wc_stats_exchange(at<float>(c.saved, L.rec), (float)c.count, c.Cin, c.g, c.xchg_peers, c.xchg_state, c.xchg_rank,
+                           c.xchg_world, c.eps, c.decomposition == WC_DECOMP_ZCA ? c.eps : 0.f, c.momentum, c.moving_mean,
+                           c.moving_cov, at<float>(c.workspace, W.factor), (cudaStream_t)stream);
+    if (rc) return rc;
+    prep_done = 1;
+    count_dev = at<float>(c.saved, L.rec_count);
+  }
   const float* mean = nullptr;
   if (c.whiten) {
     const float* S = nullptr;
@@ -140,7 +159,7 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
     } else {
       mean = c.moving_mean;
     }
-    rc = wc_factor_fwd_impl(train_w ? mean : nullptr, S, c.count_dev, c.count, c.Cin, c.g, c.eps, c.momentum, c.decomposition,
+    rc = wc_factor_fwd_impl(train_w ? mean : nullptr, S, count_dev, c.count, c.Cin, c.g, c.eps, c.momentum, c.decomposition,
                             c.renorm, c.training, c.moving_mean, c.moving_cov, at<float>(c.saved, L.Weff),
                             at<float>(c.saved, train_w ? L.Wm : L.Weff), at<float>(c.saved, L.R), at<float>(c.saved, L.U),
                             at<float>(c.saved, L.lam), c.info, at<float>(c.workspace, W.factor), W.factor_bytes, prep_done,
@@ -191,10 +210,16 @@ extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
   }
   if (!(c.phases & WC_PHASE_DX) || !c.dx) return 0;
   float *A = nullptr, *cvec = nullptr;
+  const float* count_dev = c.count_dev;
+  if (stats_grad && xchg_bwd(c)) {
+    rc = wc_adjoint_exchange(c.red, c.Cin, g, c.xchg_peers, c.xchg_state, c.xchg_rank, c.xchg_world, (cudaStream_t)stream);
+    if (rc) return rc;
+    count_dev = at<float>(c.saved, L.rec_count);       // global row count, left there by the forward exchange
+  }
   if (stats_grad) {
     A = at<float>(c.saved, L.A); cvec = at<float>(c.saved, L.cvec);
     rc = wc_factor_bwd_impl(c.red, c.red + gg, at<float>(c.saved, L.Weff), at<float>(c.saved, L.Wm), at<float>(c.saved, L.R),
-                            at<float>(c.saved, L.U), at<float>(c.saved, L.lam), c.count_dev, c.count, c.Cin, g, c.eps,
+                            at<float>(c.saved, L.U), at<float>(c.saved, L.lam), count_dev, c.count, c.Cin, g, c.eps,
                             c.decomposition, c.renorm, A, cvec, at<float>(c.workspace, W.factor), W.factor_bytes,
                             at<void>(c.saved, L.Tp_bwd), c.K, (cudaStream_t)stream);
     if (rc) return rc;

@@ -171,7 +171,15 @@ class WhiteningColoringFn(torch.autograd.Function):
         c.saved, c.saved_bytes = ptr(saved), saved_bytes
         c.workspace, c.workspace_bytes = ptr(ws), ws.numel() * 4
         keep = [saved]
-        if do_sync:
+        xch = sync.peer_exchange(group, Cin, g, dev) if (do_sync and not spec.renorm) else None
+        if xch is not None:
+            # statistics exchanged over peer memory inside the call: one foreign call, no host collective
+            c.xchg_peers, c.xchg_state = xch.peers_dev, ptr(xch.state)
+            c.xchg_rank, c.xchg_world = xch.rank, xch.world
+            c.phases = PHASE_STATS | PHASE_APPLY
+            _call('wc_layer_fwd', ctypes.byref(c), st)
+            keep.append(xch)
+        elif do_sync:
             # phase 1: this shard's record {mean, S, count}; all-gather; Chan merge; phase 2 with the global statistics
             c.phases = PHASE_STATS
             _call('wc_layer_fwd', ctypes.byref(c), st)
@@ -189,7 +197,7 @@ class WhiteningColoringFn(torch.autograd.Function):
             c.phases = PHASE_STATS | PHASE_APPLY
             _call('wc_layer_fwd', ctypes.byref(c), st)
 
-        ctx.call, ctx.keep, ctx.group, ctx.sync = c, keep, group, do_sync
+        ctx.call, ctx.keep, ctx.group, ctx.sync = c, keep, group, (do_sync and xch is None)
         ctx.dims = (N, H, W_, Cin, Cout, g, K, E, bws)
         ctx.has = has
         ctx.stats_train = bool(spec.whiten and training)

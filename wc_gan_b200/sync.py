@@ -7,10 +7,16 @@ backward: the adjoint of the whitening matrix and of the mean, {dWeff[G*g*g], gb
           the factorisation adjoint, so A and cvec are global; coloring-parameter gradients stay local, as with
           torch.nn.SyncBatchNorm (DDP averages them).
 
-Only the collectives live here (device-agnostic torch.distributed calls, NCCL on GPUs, gloo in the CPU tests);
-the arithmetic on either side of them runs in the CUDA library.
+Two transports.  On one node with peer access the exchanges run INSIDE the library's kernels over a symmetric
+buffer (`peer_exchange`: torch's symmetric memory only allocates and maps the buffer; wc_exchange.cu pushes, signals,
+waits and merges -- no NCCL call, no host round trip, one foreign call per direction).  Otherwise the host issues the
+collectives between the two phases of each direction (device-agnostic torch.distributed calls: NCCL on GPUs, gloo in
+the CPU tests); the arithmetic on either side of them runs in the CUDA library.
 """
 from __future__ import annotations
+
+import os
+import warnings
 
 import torch
 import torch.distributed as dist
@@ -60,3 +66,56 @@ def merge_records_reference(recs: torch.Tensor, C: int, g: int):
     d = (mean_r - mean).reshape(-1, G, g)
     S = (S_r.reshape(-1, G, g, g) + n_r.reshape(-1, 1, 1, 1) * d[:, :, :, None] * d[:, :, None, :]).sum(0)
     return mean, S, n
+
+
+class PeerExchange:
+    """A symmetric exchange buffer mapped on every rank of `group`, plus this rank's epoch counters."""
+
+    def __init__(self, buf, handle, state, rank, world):
+        self.buf, self.handle, self.state, self.rank, self.world = buf, handle, state, rank, world
+        self.peers_dev = int(handle.buffer_ptrs_dev)      # device array of `world` buffer pointers, rank order
+
+
+_EXCHANGES = {}
+_WARNED = False
+
+
+def peer_exchange(group, C: int, g: int, device):
+    """The peer-memory transport for layers of shape (C, g) on `group`, or None (then the host runs NCCL collectives).
+    Collective on first use per (group, C, g): every rank reaches it at the same layer.  Layers of the same shape share
+    one buffer: exchanges are stream-ordered and happen in the same order on every rank.
+    WC_B200_SYNC=nccl forces the host-collective path."""
+    global _WARNED
+    if os.environ.get('WC_B200_SYNC', '').lower() == 'nccl' or device.type != 'cuda':
+        return None
+    pg = group if group is not None else dist.group.WORLD
+    key = (id(pg), C, g, device.index)
+    if key in _EXCHANGES:
+        return _EXCHANGES[key]
+    xch = None
+    try:
+        import torch.distributed._symmetric_memory as symm
+        from ._lib import lib
+        world, rank = dist.get_world_size(pg), dist.get_rank(pg)
+        nbytes = int(lib.wc_exchange_bytes(C, g, world))
+        if nbytes == 0:
+            raise RuntimeError(f'no peer exchange for C={C}, g={g}, world={world}')
+        buf = symm.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+        buf.zero_()
+        handle = symm.rendezvous(buf, pg)
+        state = torch.zeros(4, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=pg)              # every buffer is zeroed before anyone's first push can land in it
+        xch = PeerExchange(buf, handle, state, rank, world)
+    except Exception as e:                  # no P2P / symmetric memory here: the NCCL path is always available
+        if not _WARNED:
+            warnings.warn(f'wc_gan_b200: peer-memory exchange unavailable ({e!r}); using NCCL collectives')
+            _WARNED = True
+        xch = None
+    # all ranks must agree, or one would wait in a kernel for pushes that never come
+    ok = torch.tensor([1 if xch is not None else 0], device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=pg)
+    if int(ok.item()) == 0:
+        xch = None
+    _EXCHANGES[key] = xch
+    return xch

@@ -4,10 +4,17 @@ import sys, torch
 sys.path.insert(0, '/root/repo')
 import bench, wc_gan_b200 as W
 from torch.profiler import profile, ProfilerActivity
-dev = torch.device('cuda', 0)
+import os
+import torch.distributed as dist
+rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
+torch.cuda.set_device(dev)
+group = None
+if world > 1:
+    dist.init_process_group('nccl', device_id=dev); group = dist.group.WORLD
 shape = bench.SHAPE
-xs, dys = bench.make_inputs(torch, shape, 2, dev, 1)
-stack = bench.build_stack(W, torch, 'd', 'uconv', shape[-1], dev)
+xs, dys = bench.make_inputs(torch, shape, 2, dev, 1 + rank)
+stack = bench.build_stack(W, torch, 'd', 'uconv', shape[-1], dev, group=group)
 params = list(stack.parameters())
 def step(i):
     x = xs[i % 2].requires_grad_(True)
@@ -30,7 +37,11 @@ half = len(evs) // 2
 evs = evs[half:]           # second step of the replay (warm)
 prev = evs[0].time_range.start
 t0 = prev
-print(f'{"end us":>9s} {"adds us":>8s} {"own us":>8s}  kernel')
+if rank == 0: print(f'{"end us":>9s} {"adds us":>8s} {"own us":>8s}  kernel')
 for e in evs:
-    print(f'{e.time_range.end - t0:9.1f} {e.time_range.end - prev:8.1f} {e.time_range.end - e.time_range.start:8.1f}  {e.name[:90]}')
+    if rank == 0: print(f'{e.time_range.end - t0:9.1f} {e.time_range.end - prev:8.1f} {e.time_range.end - e.time_range.start:8.1f}  {e.name[:90]}')
     prev = e.time_range.end
+
+if world > 1:
+    del g
+    torch.cuda.synchronize(); dist.barrier(); os._exit(0)

@@ -78,14 +78,15 @@ __device__ __forceinline__ uint32_t xch_push_wait(const XchParams& p, const floa
       }
     }
   }
-  __threadfence_system();
+  // release pattern: the CTA barrier orders every thread's stores before the signalling threads' release-RMW at
+  // system scope (release is cumulative over what the barrier made visible); no per-thread system fence is needed
   __syncthreads();
   const size_t flag_off = ((size_t)p.dir * 2 + slot) * XCH_MAXR * 4;
   if (t < p.R) red_release_sys_add(reinterpret_cast<uint32_t*>(p.peers[t] + flag_off) + p.rank, 1u);
   const uint32_t target = gridDim.x * (e / 2u + 1u);
   if (t < p.R) {
     const uint32_t* f = reinterpret_cast<const uint32_t*>(p.peers[p.rank] + flag_off) + t;
-    while ((int32_t)(ld_acquire_sys(f) - target) < 0) { __nanosleep(64); }
+    while ((int32_t)(ld_acquire_sys(f) - target) < 0) { }
   }
   __syncthreads();
   return e;

@@ -4,8 +4,11 @@ import sys, torch
 sys.path.insert(0, '/root/repo')
 import bench, wc_gan_b200 as W
 from torch.profiler import profile, ProfilerActivity
-import os
+import os, ctypes
 import torch.distributed as dist
+from wc_gan_b200._lib import lib as _l
+_l.wc_debug_set.argtypes=[ctypes.c_int]
+if os.environ.get('WC_DBG'): _l.wc_debug_set(int(os.environ['WC_DBG']))
 rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
 dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
 torch.cuda.set_device(dev)

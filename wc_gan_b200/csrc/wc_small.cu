@@ -415,6 +415,7 @@ struct MultiLaunch {
     if (ep.kind == EPI_PACK && (ep.pkC % 32 || (ep.pk0 && !wc_aligned16(ep.pk0)) || (ep.pk1 && !wc_aligned16(ep.pk1)))) return false;
     SmmJob& j = m.job[m.njobs++];
     j.p = p; j.ex = SmmExtra{count_dev, count_host, count_mode, diag_scale}; j.ep = ep;
+    if (wc_debug_flags() & 16384) j.ep.kind = EPI_NONE;     // experiment: what does the packing epilogue cost (wrong results)
     j.ak = p.csA == 1; j.bk = p.rsB == 1;
     j.gx = p.N / SMM_T; j.gy = p.M / SMM_T; j.gz = p.nb1 * p.nb2;
     j.cta0 = ctas;

@@ -547,44 +547,80 @@ __device__ __forceinline__ void fetch_tile_warp(const float* gt, float* T, int l
 // shared memory (one store + 128-bit broadcast loads) instead of 31-k shuffles; the pivot chain per column is
 // shfl -> rsqrt -> mul -> fma.  rsqrt.approx is accurate to 2^-22.4 relative (PTX ISA), i.e. a few ulp of the fp32 result.
 // bc: 64 floats of shared memory.
-__device__ void warp_potrf32_bc(float* T, float* rdiag, float* bc, int lane, int& bad) {
+__device__ __forceinline__ void cta_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void cta_mbar_wait0(uint64_t* bar) {     // one-shot barriers: phase 0
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "CB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n\t"
+      "@P1 bra CB_DONE;\n\t"
+      "bra CB_WAIT;\n\t"
+      "CB_DONE:\n\t}" ::"r"(a) : "memory");
+}
+
+// in-place lower Cholesky of a 32x32 tile by one warp (lane = row).  Column k of the factor is written to the tile as
+// soon as it is final -- it is at once the broadcast buffer for the trailing update of this warp (128-bit broadcast loads)
+// and, announced on colbar[k], the input of the warp that builds the inverse one column behind (warp_inverse_follow).
+// The serial chain per column is  pivot -> rsqrt -> l_k -> (diagonal of lane k+1, element (.,k+1)) -> next pivot; both
+// hand-overs to column k+1 go through shuffles.  rsqrt.approx is accurate to 2^-22.4 relative (PTX ISA).
+__device__ void warp_potrf32_bc(float* T, float* rdiag, uint64_t* colbar, int lane, int& bad) {
   float a[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) a[c] = T[c * TP + lane];
   float dg = T[lane * TP + lane];
-  // The serial chain per column is  pivot -> rsqrt -> l_k -> (diagonal of lane k+1, element (.,k+1)) -> next pivot.
-  // Both hand-overs to column k+1 go through shuffles; only the columns k+2.. take the (slower) broadcast through
-  // shared memory, which is off the chain.
+  __syncwarp();                                   // every lane holds its row before columns are overwritten
   float piv = __shfl_sync(FULL, dg, 0);
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
     if (!(piv > 0.f)) { if (!bad) bad = k + 1; piv = 1e-30f; }
     const float rs = rsqrt_approx(piv);
     const float lk = (lane == k) ? piv * rs : a[k] * rs;
-    a[k] = lk;
     if (lane == k) rdiag[k] = rs;
+    T[k * TP + lane] = (lane >= k) ? lk : 0.f;    // final column k (zero above the diagonal)
     if (k < 31) {
       dg = fmaf(-lk, lk, dg);
       piv = __shfl_sync(FULL, dg, k + 1);                  // lane k+1's diagonal is final after column k
       const float lnext = __shfl_sync(FULL, lk, k + 1);    // L[k+1][k]
       a[k + 1] = fmaf(-lk, lnext, a[k + 1]);
-      if (k < 30) {
-        float* b = bc + (k & 1) * 32;
-        b[lane] = lk;
-        __syncwarp();
+    }
+    __syncwarp();
+    if (lane == 0) cta_mbar_arrive(&colbar[k]);
+    if (k < 30) {
+      const float* b = T + k * TP;
 #pragma unroll
-        for (int q = (k + 2) / 4; q < 8; ++q) {
-          const float4 l = *reinterpret_cast<const float4*>(b + 4 * q);
-          if (4 * q + 0 > k + 1) a[4 * q + 0] = fmaf(-lk, l.x, a[4 * q + 0]);
-          if (4 * q + 1 > k + 1) a[4 * q + 1] = fmaf(-lk, l.y, a[4 * q + 1]);
-          if (4 * q + 2 > k + 1) a[4 * q + 2] = fmaf(-lk, l.z, a[4 * q + 2]);
-          if (4 * q + 3 > k + 1) a[4 * q + 3] = fmaf(-lk, l.w, a[4 * q + 3]);
-        }
+      for (int q = (k + 2) / 4; q < 8; ++q) {
+        const float4 l = *reinterpret_cast<const float4*>(b + 4 * q);
+        if (4 * q + 0 > k + 1) a[4 * q + 0] = fmaf(-lk, l.x, a[4 * q + 0]);
+        if (4 * q + 1 > k + 1) a[4 * q + 1] = fmaf(-lk, l.y, a[4 * q + 1]);
+        if (4 * q + 2 > k + 1) a[4 * q + 2] = fmaf(-lk, l.z, a[4 * q + 2]);
+        if (4 * q + 3 > k + 1) a[4 * q + 3] = fmaf(-lk, l.w, a[4 * q + 3]);
       }
     }
   }
+}
+
+// one warp, one column behind warp_potrf32_bc: x (row `lane` of L^-T = column `lane` of L^-1) by right-looking
+// substitution; step m needs column m of L and 1/L[m][m], which colbar[m] announces
+__device__ void warp_inverse_follow(float (&x)[32], const float* T, const float* rdiag, uint64_t* colbar, int lane) {
 #pragma unroll
-  for (int c = 0; c < 32; ++c) T[c * TP + lane] = (c <= lane) ? a[c] : 0.f;
+  for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.f : 0.f;
+#pragma unroll
+  for (int m = 0; m < 32; ++m) {
+    cta_mbar_wait0(&colbar[m]);
+    x[m] *= rdiag[m];
+    const float xm = x[m];
+#pragma unroll
+    for (int q = (m + 1) / 4; q < 8; ++q) {
+      const float4 l = *reinterpret_cast<const float4*>(T + m * TP + 4 * q);   // L[4q..4q+3][m]
+      if (4 * q + 0 > m) x[4 * q + 0] = fmaf(-xm, l.x, x[4 * q + 0]);
+      if (4 * q + 1 > m) x[4 * q + 1] = fmaf(-xm, l.y, x[4 * q + 1]);
+      if (4 * q + 2 > m) x[4 * q + 2] = fmaf(-xm, l.z, x[4 * q + 2]);
+      if (4 * q + 3 > m) x[4 * q + 3] = fmaf(-xm, l.w, x[4 * q + 3]);
+    }
+  }
 }
 
 // all 256 threads: acc(2x2 per thread: rows 2tr+i, cols 2tc+j) += A(32x32, k-major, pitch TP) * B(32x32, k-major, pitch TP)
@@ -614,8 +650,8 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
                         float* __restrict__ Lout, float* __restrict__ Xout, int32_t* info, int dbg) {
   wc_pdl_wait();
   extern __shared__ __align__(16) float sm[];
-  __shared__ uint64_t flagA[CLN], flagB[CLN], flagD[CLN];
-  __shared__ __align__(16) float rd_own[TB], rd_stage[TB], bcast[2 * TB];
+  __shared__ uint64_t flagA[CLN], flagB[CLN], flagD[CLN], colbar[TB];
+  __shared__ __align__(16) float rd_own[TB];
   const int NB = g / TB;
   const int grp = blockIdx.x / CLN;
   const int r = (int)cl_rank();
@@ -626,6 +662,7 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
   float* ljj = xcol + CLN * TS;          // staged L_JJ / inv(L_II), column-major
   float* stile = ljj + TS;               // S tile, row-major; also inv(L_rr) column-major
   float* stg = stile + TS;               // CLN staged tiles of another block row
+  float* dinv = stg + CLN * TS;          // inv(L_rr), column-major: what the rows below multiply their tiles with
   const float* Ag = Ain + (long long)grp * g * g;
   float* gs = scratch + (long long)grp * scratch_stride;
   float* gD = gs + (NB * (NB + 1) / 2) * GT;       // NB tiles inv(L_JJ)
@@ -643,6 +680,8 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(d) : "memory");
     }
+    for (int j = 0; j < TB; ++j)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&colbar[j])) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // load block row r: column c of the column-major tile (r,J) is a contiguous piece of ROW J*32+c of the symmetric input
@@ -689,38 +728,34 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
         }
         __syncthreads();
       }
-      if (warp == 0) {
+      {
+        // L_rJ = T inv(L_JJ)^T as a tile product by the whole CTA; inv(L_JJ) comes straight out of CTA J's shared memory
+        // (it was built one column behind J's factorisation, so it is there as soon as L_JJ is)
         if (J == r - 1) CL_MARK(2);
         cl_wait(&flagB[J]);
         if (J == r - 1) CL_MARK(3);
-        {   // L_JJ and 1/diag straight out of CTA J's shared memory (same offsets in every CTA of the cluster)
-          const int cq = lane >> 3, q8 = lane & 7;
-          const uint32_t rt = cl_map((uint32_t)__cvta_generic_to_shared(own + J * TS), (uint32_t)J);
-          const uint32_t rr = cl_map((uint32_t)__cvta_generic_to_shared(rd_own), (uint32_t)J);
-          float4 v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = cl_ld4(rt + (uint32_t)(((4 * e + cq) * TP + 4 * q8) * 4));
-          const float rdv = cl_ld1(rr + (uint32_t)lane * 4u);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) *reinterpret_cast<float4*>(ljj + (4 * e + cq) * TP + 4 * q8) = v[e];
-          rd_stage[lane] = rdv;
+        {
+          const int col = t >> 3, q8 = t & 7;
+          const uint32_t rt = cl_map((uint32_t)__cvta_generic_to_shared(dinv), (uint32_t)J);
+          const float4 v = cl_ld4(rt + (uint32_t)((col * TP + 4 * q8) * 4));
+          *reinterpret_cast<float4*>(ljj + col * TP + 4 * q8) = v;
         }
-        __syncwarp();
-        float x[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) x[c] = T[c * TP + lane];
-        warp_trsm_row(x, ljj, rd_stage);
+        __syncthreads();
+        float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        cta_tile_mac(acc, T, ljj, tr, tc);       // (row 2tr+i, col 2tc+j) = sum_k T(row,k) inv(L_JJ)(col,k)
+        __syncthreads();                         // everyone has read T
         float* gt = gtile(r, J);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) { T[c * TP + lane] = x[c]; gt[c * TB + lane] = x[c]; }
-        if (J == r - 1) {                     // all off-diagonal tiles of row r are published
-          cl_fence();
-          __syncwarp();
-          if (lane < NB && lane != r) cl_arrive_remote(&flagA[r], lane);
+        for (int j = 0; j < 2; ++j) {
+          const float2 v = make_float2(acc[0][j], acc[1][j]);
+          *reinterpret_cast<float2*>(T + (2 * tc + j) * TP + 2 * tr) = v;
+          *reinterpret_cast<float2*>(gt + (2 * tc + j) * TB + 2 * tr) = v;
         }
+        if (J == r - 1) cl_fence();              // all off-diagonal tiles of row r are published
+        __syncthreads();
+        if (J == r - 1 && t < NB && t != r) cl_arrive_remote(&flagA[r], t);
         if (J == r - 1) CL_MARK(4);
       }
-      __syncthreads();
       {   // right-looking update of the diagonal tile: T_rr -= L_rJ L_rJ^T
         float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
         cta_tile_mac(acc, T, T, tr, tc);
@@ -738,35 +773,34 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
     __syncthreads();
     CL_MARK(5);
     // ------------------------------------------------------------------ diagonal tile
+    // warp 0 factors it column by column; warp 1 follows one column behind with the inverse, so inv(L_rr) exists
+    // (almost) as soon as L_rr does and the rows below never run a triangular solve
     if (warp == 0) {
       float* T = own + r * TS;
       CL_MARK(6);
       int bad = 0;
-      warp_potrf32_bc(T, rd_own, bcast, lane, bad);
+      warp_potrf32_bc(T, rd_own, colbar, lane, bad);
       CL_MARK(7);
       if (bad && lane == 0 && info) atomicCAS(&info[WC_INFO_NOT_PD], 0, grp * g + r * TB + bad);
       __syncwarp();
-      cl_fence();         // the tile and 1/diag stay in this CTA's shared memory; the peers read them there
+      if (Lg) store_tile_rowmajor(T, Lg + (long long)(r * TB) * g + r * TB, g, lane);
+    } else if (warp == 1) {
+      const float* T = own + r * TS;
+      float x[32];
+      warp_inverse_follow(x, T, rd_own, colbar, lane);
+      float* Xr = xcol + r * TS;              // row-major
+#pragma unroll
+      for (int c = 0; c < 32; ++c) { dinv[lane * TP + c] = x[c]; Xr[c * TP + lane] = x[c]; }   // dinv: element (row c, col lane)
+      cl_fence();
       __syncwarp();
       if (lane < NB && lane != r) cl_arrive_remote(&flagB[r], lane);
       CL_MARK(8);
-      // inv(L_rr): row `lane` of L^-T = column `lane` of L^-1
-      float x[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.f : 0.f;
-      warp_trsm_row(x, T, rd_own);
-      float* D = stile;                       // column-major: element (row c, col lane)
-      float* Xr = xcol + r * TS;              // row-major
-#pragma unroll
-      for (int c = 0; c < 32; ++c) { D[lane * TP + c] = x[c]; Xr[c * TP + lane] = x[c]; }
-      __syncwarp();
-      publish_tile(D, gD + r * GT, lane);
+      publish_tile(dinv, gD + r * GT, lane);
       cl_fence();
       __syncwarp();
       if (lane < NB && lane != r) cl_arrive_remote(&flagD[r], lane);
       CL_MARK(9);
-      store_tile_rowmajor(D, Xg + (long long)(r * TB) * g + r * TB, g, lane);
-      if (Lg) store_tile_rowmajor(T, Lg + (long long)(r * TB) * g + r * TB, g, lane);
+      store_tile_rowmajor(dinv, Xg + (long long)(r * TB) * g + r * TB, g, lane);
     }
     __syncthreads();
     CL_MARK(10);
@@ -833,7 +867,7 @@ int wc_chol_inv_launch(const float* Ain, int C, int g, float* Lout, float* Xout,
   const int NB = (g + TB - 1) / TB;
   if (chol_cluster_ok(g, Xout) && !(wc_debug_flags() & 2048)) {
     if (!Xpad) return WC_E_ARG;
-    const size_t csm = (size_t)(2 * CLN + 2 + CLW) * TS * sizeof(float);
+    const size_t csm = (size_t)(2 * CLN + 3 + CLW) * TS * sizeof(float);
     static bool cattr = false;
     if (!cattr) {
       WC_CUDA(cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));

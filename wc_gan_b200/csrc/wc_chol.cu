@@ -663,6 +663,7 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
   float* stile = ljj + TS;               // S tile, row-major; also inv(L_rr) column-major
   float* stg = stile + TS;               // CLN staged tiles of another block row
   float* dinv = stg + CLN * TS;          // inv(L_rr), column-major: what the rows below multiply their tiles with
+  float* dnext = dinv + TS;              // inv(L_{r-1,r-1}), pushed here by CTA r-1 (the hand-over on the critical path)
   const float* Ag = Ain + (long long)grp * g * g;
   float* gs = scratch + (long long)grp * scratch_stride;
   float* gD = gs + (NB * (NB + 1) / 2) * GT;       // NB tiles inv(L_JJ)
@@ -734,15 +735,17 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
         if (J == r - 1) CL_MARK(2);
         cl_wait(&flagB[J]);
         if (J == r - 1) CL_MARK(3);
-        {
+        const float* Dj = dnext;                 // J == r-1: CTA J pushed its inverse into our shared memory
+        if (J < r - 1) {
           const int col = t >> 3, q8 = t & 7;
           const uint32_t rt = cl_map((uint32_t)__cvta_generic_to_shared(dinv), (uint32_t)J);
           const float4 v = cl_ld4(rt + (uint32_t)((col * TP + 4 * q8) * 4));
           *reinterpret_cast<float4*>(ljj + col * TP + 4 * q8) = v;
+          Dj = ljj;
+          __syncthreads();
         }
-        __syncthreads();
         float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-        cta_tile_mac(acc, T, ljj, tr, tc);       // (row 2tr+i, col 2tc+j) = sum_k T(row,k) inv(L_JJ)(col,k)
+        cta_tile_mac(acc, T, Dj, tr, tc);        // (row 2tr+i, col 2tc+j) = sum_k T(row,k) inv(L_JJ)(col,k)
         __syncthreads();                         // everyone has read T
         float* gt = gtile(r, J);
 #pragma unroll
@@ -751,10 +754,9 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
           *reinterpret_cast<float2*>(T + (2 * tc + j) * TP + 2 * tr) = v;
           *reinterpret_cast<float2*>(gt + (2 * tc + j) * TB + 2 * tr) = v;
         }
-        if (J == r - 1) cl_fence();              // all off-diagonal tiles of row r are published
         __syncthreads();
-        if (J == r - 1 && t < NB && t != r) cl_arrive_remote(&flagA[r], t);
         if (J == r - 1) CL_MARK(4);
+        // (row r is announced to the other CTAs from the diagonal phase below: they have a whole factorisation of slack)
       }
       {   // right-looking update of the diagonal tile: T_rr -= L_rJ L_rJ^T
         float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
@@ -788,19 +790,35 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
       const float* T = own + r * TS;
       float x[32];
       warp_inverse_follow(x, T, rd_own, colbar, lane);
-      float* Xr = xcol + r * TS;              // row-major
+      // dinv: element (row c, col lane).  The next CTA gets its copy pushed (it needs it first, on the critical path).
+      if (r + 1 < NB) {
+        const uint32_t rn = cl_map((uint32_t)__cvta_generic_to_shared(dnext), (uint32_t)(r + 1)) + (uint32_t)(lane * TP * 4);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) { dinv[lane * TP + c] = x[c]; Xr[c * TP + lane] = x[c]; }   // dinv: element (row c, col lane)
-      cl_fence();
+        for (int c = 0; c < 32; c += 4)
+          asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rn + c * 4), "f"(x[c]), "f"(x[c + 1]), "f"(x[c + 2]), "f"(x[c + 3]) : "memory");
+      }
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(dinv + lane * TP + c) = make_float4(x[c], x[c + 1], x[c + 2], x[c + 3]);
+      // the arrivals are release operations at cluster scope and cumulative over what __syncwarp ordered before them:
+      // no separate fence on this (critical) hand-over
       __syncwarp();
       if (lane < NB && lane != r) cl_arrive_remote(&flagB[r], lane);
       CL_MARK(8);
+      float* Xr = xcol + r * TS;              // row-major
+#pragma unroll
+      for (int c = 0; c < 32; ++c) Xr[c * TP + lane] = x[c];
+      __syncwarp();
       publish_tile(dinv, gD + r * GT, lane);
       cl_fence();
       __syncwarp();
       if (lane < NB && lane != r) cl_arrive_remote(&flagD[r], lane);
       CL_MARK(9);
       store_tile_rowmajor(dinv, Xg + (long long)(r * TB) * g + r * TB, g, lane);
+    } else if (warp == 2 && r > 0) {
+      // all off-diagonal tiles of row r are in the scratch (written before the barrier above): announce them
+      cl_fence();
+      __syncwarp();
+      if (lane < NB && lane != r) cl_arrive_remote(&flagA[r], lane);
     }
     __syncthreads();
     CL_MARK(10);
@@ -867,7 +885,7 @@ int wc_chol_inv_launch(const float* Ain, int C, int g, float* Lout, float* Xout,
   const int NB = (g + TB - 1) / TB;
   if (chol_cluster_ok(g, Xout) && !(wc_debug_flags() & 2048)) {
     if (!Xpad) return WC_E_ARG;
-    const size_t csm = (size_t)(2 * CLN + 3 + CLW) * TS * sizeof(float);
+    const size_t csm = (size_t)(2 * CLN + 4 + CLW) * TS * sizeof(float);
     static bool cattr = false;
     if (!cattr) {
       WC_CUDA(cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));

@@ -858,7 +858,9 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
     }
   }
   CL_MARK(14);
-  cl_sync();      // nobody leaves while a peer may still arrive on its flags
+  // nobody leaves while a peer may still arrive on its flags or read its shared memory; no data is handed over here, so
+  // the arrival does not have to wait for this CTA's global stores (relaxed)
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
   CL_MARK(15);
 }
 

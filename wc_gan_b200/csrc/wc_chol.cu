@@ -808,10 +808,6 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
 #pragma unroll
       for (int c = 0; c < 32; ++c) Xr[c * TP + lane] = x[c];
       __syncwarp();
-      publish_tile(dinv, gD + r * GT, lane);
-      cl_fence();
-      __syncwarp();
-      if (lane < NB && lane != r) cl_arrive_remote(&flagD[r], lane);
       CL_MARK(9);
       store_tile_rowmajor(dinv, Xg + (long long)(r * TB) * g + r * TB, g, lane);
     } else if (warp == 2 && r > 0) {
@@ -837,9 +833,14 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
           *reinterpret_cast<float2*>(stile + (2 * tr + i) * TP + 2 * tc) = make_float2(acc[i][0], acc[i][1]);
       }
       if (I == NB - 1) CL_MARK(12);
-      cl_wait(&flagD[I]);
+      cl_wait(&flagB[I]);                            // inv(L_II) is in CTA I's shared memory (column-major)
       if (I == NB - 1) CL_MARK(13);
-      cta_fetch_tiles(gD + I * GT, 1, ljj, t);       // inv(L_II), column-major
+      {
+        const int col = t >> 3, q8 = t & 7;
+        const uint32_t rt = cl_map((uint32_t)__cvta_generic_to_shared(dinv), (uint32_t)I);
+        const float4 v = cl_ld4(rt + (uint32_t)((col * TP + 4 * q8) * 4));
+        *reinterpret_cast<float4*>(ljj + col * TP + 4 * q8) = v;
+      }
       __syncthreads();
       {   // X_Ir = -inv(L_II) S
         float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};

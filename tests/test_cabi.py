@@ -37,6 +37,11 @@ def test_argument_errors_without_device():
     assert L.wc_reduce_bwd(None, None, 1, 1, 1, 1, None, None, 1, None, None, None, 0, None) == -1
     assert L.wc_factor_fwd(None, None, None, 1.0, 8, 3, 1e-3, 0.99, 0, 0, 1, None, None, None, None, None, None, None,
                            None, None, 0, None) == -1
+    # peer-memory exchange buffer: flags + 2 slots x world x (record + adjoint); 1..16 ranks
+    n1, n8 = L.wc_exchange_bytes(256, 256, 1), L.wc_exchange_bytes(256, 256, 8)
+    assert n1 >= 1024 + 2 * 4 * (2 * 256 * 256 + 2 * 256 + 1) and n8 > 7 * (n1 - 1024)
+    assert L.wc_exchange_bytes(256, 256, 17) == 0 and L.wc_exchange_bytes(256, 7, 2) == 0
+    assert ctypes.sizeof(_lib.WcLayerCall) % 8 == 0
     with pytest.raises(ValueError):
         _lib.check(-1, 'x')
     with pytest.raises(_lib.WcError):

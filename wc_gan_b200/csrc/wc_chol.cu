@@ -477,11 +477,6 @@ __device__ __forceinline__ float4 cl_ld4(uint32_t addr) {
   asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
-__device__ __forceinline__ float cl_ld1(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-  return v;
-}
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 // acc(4x8 per lane) += A(32x32, k-major, pitch PA) * B(32x32, k-major, pitch PB); GA / GB: operand lives in the global
@@ -502,45 +497,6 @@ __device__ __forceinline__ void cl_tile_fma(float (&acc)[4][8], const float* At,
 #pragma unroll
       for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
   }
-}
-__device__ __forceinline__ void acc_zero(float (&acc)[4][8]) {
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
-}
-// accumulator -> column-major tile (pitch TP): element (4ly+r, 8lx+c)
-__device__ __forceinline__ void acc_store_colmajor(const float (&acc)[4][8], float* T, int ly, int lx) {
-#pragma unroll
-  for (int c = 0; c < 8; ++c)
-    *reinterpret_cast<float4*>(T + (8 * lx + c) * TP + 4 * ly) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
-}
-// accumulator -> row-major tile (pitch TP)
-__device__ __forceinline__ void acc_store_rowmajor(const float (&acc)[4][8], float* T, int ly, int lx, float sign) {
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    float* d = T + (4 * ly + r) * TP + 8 * lx;
-    *reinterpret_cast<float4*>(d) = make_float4(sign * acc[r][0], sign * acc[r][1], sign * acc[r][2], sign * acc[r][3]);
-    *reinterpret_cast<float4*>(d + 4) = make_float4(sign * acc[r][4], sign * acc[r][5], sign * acc[r][6], sign * acc[r][7]);
-  }
-}
-// one warp: column-major smem tile (pitch TP) -> published tile (pitch 32), 128-bit coalesced
-__device__ __forceinline__ void publish_tile(const float* T, float* gt, int lane) {
-  const int cq = lane >> 3, q8 = lane & 7;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int col = 4 * e + cq;
-    *reinterpret_cast<float4*>(gt + col * TB + 4 * q8) = *reinterpret_cast<const float4*>(T + col * TP + 4 * q8);
-  }
-}
-// one warp: published tile -> column-major smem tile (pitch TP)
-__device__ __forceinline__ void fetch_tile_warp(const float* gt, float* T, int lane) {
-  const int cq = lane >> 3, q8 = lane & 7;
-  float4 v[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) v[e] = ldcg4(gt + (4 * e + cq) * TB + 4 * q8);
-#pragma unroll
-  for (int e = 0; e < 8; ++e) *reinterpret_cast<float4*>(T + (4 * e + cq) * TP + 4 * q8) = v[e];
 }
 
 // in-place lower Cholesky of a 32x32 tile by one warp (lane = row).  Column k of the factor is broadcast through
@@ -650,7 +606,7 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
                         float* __restrict__ Lout, float* __restrict__ Xout, int32_t* info, int dbg) {
   wc_pdl_wait();
   extern __shared__ __align__(16) float sm[];
-  __shared__ uint64_t flagA[CLN], flagB[CLN], flagD[CLN], colbar[TB];
+  __shared__ uint64_t flagA[CLN], flagB[CLN], colbar[TB];
   __shared__ __align__(16) float rd_own[TB];
   const int NB = g / TB;
   const int grp = blockIdx.x / CLN;
@@ -666,8 +622,6 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
   float* dnext = dinv + TS;              // inv(L_{r-1,r-1}), pushed here by CTA r-1 (the hand-over on the critical path)
   const float* Ag = Ain + (long long)grp * g * g;
   float* gs = scratch + (long long)grp * scratch_stride;
-  float* gD = gs + (NB * (NB + 1) / 2) * GT;       // NB tiles inv(L_JJ)
-  float* gR = gD + NB * GT;                        // NB x 32 reciprocal diagonals
   float* Lg = Lout ? Lout + (long long)grp * g * g : nullptr;
   float* Xg = Xout + (long long)grp * g * g;
   auto gtile = [&](int I, int J) { return gs + (I * (I + 1) / 2 + J) * GT; };
@@ -675,11 +629,9 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
   CL_MARK(0);
   if (t == 0) {
     for (int j = 0; j < CLN; ++j) {
-      const uint32_t a = (uint32_t)__cvta_generic_to_shared(&flagA[j]), b = (uint32_t)__cvta_generic_to_shared(&flagB[j]),
-                     d = (uint32_t)__cvta_generic_to_shared(&flagD[j]);
+      const uint32_t a = (uint32_t)__cvta_generic_to_shared(&flagA[j]), b = (uint32_t)__cvta_generic_to_shared(&flagB[j]);
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(d) : "memory");
     }
     for (int j = 0; j < TB; ++j)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&colbar[j])) : "memory");

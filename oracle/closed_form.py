@@ -213,3 +213,61 @@ def backward(x: Tensor, dy: Tensor, fwd: dict, params: dict, *, norm='d', after_
     grads['x'] = dX.reshape(n, h, w, c)
     grads['_inter'] = inter
     return grads
+
+
+# ---------------------------------------------------------------------------------------------
+# Restatements of the exact algebra the fused small-matrix kernels use (checked against the
+# forms above / torch.linalg in tests/test_closed_form.py)
+# ---------------------------------------------------------------------------------------------
+def cholesky_adjoint_psi(dWm: Tensor, Wm: Tensor, eps: float, Mtot: float) -> Tensor:
+    """A = 2(1-eps) dSigma' / (M-1) as the three launches M2 / M3 / M4 of wc_small.cu compute it
+    (wc_factor_bwd_impl): Z = dWm Wm^T; Psi = Phi + Phi^T built from the LOWER tiles of Z only
+    (Psi_ij = -Z_max(i,j),min(i,j)); Y = Psi Wm; A = (1-eps)/(M-1) Wm^T Y.  No symmetrisation pass."""
+    Z = dWm @ Wm.transpose(-1, -2)
+    L = torch.tril(Z, -1)
+    Psi = -(L + L.transpose(-1, -2) + torch.diag_embed(torch.diagonal(Z, dim1=-2, dim2=-1)))
+    Y = Psi @ Wm
+    return (1.0 - eps) / (Mtot - 1.0) * (Wm.transpose(-1, -2) @ Y)
+
+
+def cluster_cholesky_inverse(A: Tensor, tb: int = 32):
+    """L = chol(A) and X = L^-1 by the schedule of chol_cluster_kernel (wc_chol.cu), in plain loops:
+    block row r of L left-looking, every panel as a PRODUCT with the inverse of the diagonal tile
+    (L_rJ = T inv(L_JJ)^T, no triangular solve), the inverse of a diagonal tile by right-looking
+    substitution on the identity, then block column r of X as X_Ir = -inv(L_II) sum_K L_IK X_Kr."""
+    n = A.shape[-1]
+    assert n % tb == 0
+    nb = n // tb
+    blk = lambda M, i, j: M[i * tb:(i + 1) * tb, j * tb:(j + 1) * tb]
+    L = torch.zeros_like(A)
+    X = torch.zeros_like(A)
+    Dinv = []
+    for r in range(nb):
+        for J in range(r):
+            T = blk(A, r, J).clone()
+            for K in range(J):
+                T -= blk(L, r, K) @ blk(L, J, K).transpose(0, 1)
+            blk(L, r, J).copy_(T @ Dinv[J].transpose(0, 1))
+        Td = blk(A, r, r).clone()
+        for J in range(r):
+            Td -= blk(L, r, J) @ blk(L, r, J).transpose(0, 1)
+        # potrf of the tile, column by column; the inverse follows one column behind
+        Lt = torch.zeros_like(Td)
+        W = Td.clone()
+        xinv = torch.eye(tb, dtype=A.dtype)            # row i = row i of L^-T (column i of L^-1)
+        for k in range(tb):
+            rs = 1.0 / torch.sqrt(W[k, k])
+            Lt[k:, k] = W[k:, k] * rs
+            W[k + 1:, k + 1:] -= torch.outer(Lt[k + 1:, k], Lt[k + 1:, k])
+            xinv[:, k] *= rs
+            xinv[:, k + 1:] -= torch.outer(xinv[:, k], Lt[k + 1:, k])
+        blk(L, r, r).copy_(Lt)
+        Dinv.append(xinv.transpose(0, 1).contiguous())   # inv(L_rr)
+        blk(X, r, r).copy_(Dinv[r])
+    for r in range(nb):
+        for I in range(r + 1, nb):
+            S = torch.zeros(tb, tb, dtype=A.dtype)
+            for K in range(r, I):
+                S += blk(L, I, K) @ blk(X, K, r)
+            blk(X, I, r).copy_(-Dinv[I] @ S)
+    return L, X

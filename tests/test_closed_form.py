@@ -107,3 +107,33 @@ def test_sync_batch_emulation():
         S = S + Sr + nr * d[:, :, None] * d[:, None, :]
     ys = [CF.forward(sh, None, params, group_size=g, stats_override=(n, mu, S))['y'] for sh in shards]
     assert torch.allclose(torch.cat(ys), full['y'], rtol=1e-10, atol=1e-10)
+
+
+def test_psi_form_of_the_cholesky_adjoint():
+    """The M2 / M3 / M4 launches build A from Psi = Phi + Phi^T (lower tiles of Z only); same A as sym(Wm^T Phi Wm)."""
+    torch.manual_seed(0)
+    G, g, eps, M = 3, 8, 1e-3, 77.0
+    S = torch.randn(G, g, 2 * g, dtype=torch.float64)
+    cov = S @ S.transpose(1, 2) / (2 * g) + 0.1 * torch.eye(g, dtype=torch.float64)
+    Wm = torch.linalg.inv(torch.linalg.cholesky(cov))
+    dWm = torch.randn(G, g, g, dtype=torch.float64)
+    Z = dWm @ Wm.transpose(1, 2)
+    Phi = -(torch.tril(Z) - 0.5 * torch.diag_embed(torch.diagonal(Z, dim1=1, dim2=2)))
+    Qs = Wm.transpose(1, 2) @ Phi @ Wm
+    ref = 2.0 * (1 - eps) * 0.5 * (Qs + Qs.transpose(1, 2)) / (M - 1.0)
+    got = CF.cholesky_adjoint_psi(dWm, Wm, eps, M)
+    assert float((got - ref).abs().max()) < 1e-12 * float(ref.abs().max()) + 1e-15
+
+
+@pytest.mark.parametrize('n', [128, 256])
+def test_cluster_cholesky_schedule(n):
+    """The cluster kernel's schedule (panels as products with the inverse of the diagonal tile, inverse one column
+    behind the factorisation, block columns of L^-1) gives L and L^-1."""
+    torch.manual_seed(1)
+    S = torch.randn(n, 2 * n, dtype=torch.float64)
+    A = S @ S.t() / (2 * n) + 1e-3 * torch.eye(n, dtype=torch.float64)
+    L, X = CF.cluster_cholesky_inverse(A)
+    Lr = torch.linalg.cholesky(A)
+    assert float((L - Lr).abs().max()) < 1e-10 * float(Lr.abs().max())
+    assert float((X @ Lr - torch.eye(n, dtype=torch.float64)).abs().max()) < 1e-8
+    assert float(torch.triu(X, 1).abs().max()) == 0.0

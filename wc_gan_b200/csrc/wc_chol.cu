@@ -543,7 +543,7 @@ __device__ void warp_potrf32_bc(float* T, float* rdiag, uint64_t* colbar, int la
       a[k + 1] = fmaf(-lk, lnext, a[k + 1]);
     }
     __syncwarp();
-    if (lane == 0) cta_mbar_arrive(&colbar[k]);
+    if (colbar && lane == 0) cta_mbar_arrive(&colbar[k]);
     if (k < 30) {
       const float* b = T + k * TP;
 #pragma unroll
@@ -565,7 +565,7 @@ __device__ void warp_inverse_follow(float (&x)[32], const float* T, const float*
   for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.f : 0.f;
 #pragma unroll
   for (int m = 0; m < 32; ++m) {
-    cta_mbar_wait0(&colbar[m]);
+    if (colbar) cta_mbar_wait0(&colbar[m]);
     x[m] *= rdiag[m];
     const float xm = x[m];
 #pragma unroll
@@ -607,7 +607,7 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
   wc_pdl_wait();
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t flagA[CLN], flagB[CLN], colbar[TB];
-  __shared__ __align__(16) float rd_own[TB];
+  __shared__ __align__(16) float rd_own[TB], rd_warm[2 * TB];
   const int NB = g / TB;
   const int grp = blockIdx.x / CLN;
   const int r = (int)cl_rank();
@@ -662,6 +662,13 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
   CL_MARK(1);
 
   if (r < NB) {
+    // The factorisation of a diagonal tile and the inverse that follows it are ~75 KB of unrolled straight-line code
+    // that a CTA runs exactly once, on the critical path; cold, they are bound by instruction fetch.  Rows below the first
+    // wait ~4 us for CTA 0 anyway: in "phase 0" two otherwise idle warps run THE SAME code (one call site, this loop is
+    // not unrolled) on scratch tiles, so that phase 1 -- the real thing -- finds it in the SM's instruction cache.
+#pragma unroll 1
+    for (int phase = (r > 0) ? 0 : 1; phase < 2; ++phase) {
+    if (phase == 1) {
     // ------------------------------------------------------------------ block row r of L
     for (int J = 0; J < r; ++J) {
       float* T = own + J * TS;
@@ -726,22 +733,28 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
     }
     __syncthreads();
     CL_MARK(5);
+    }   // phase 1
     // ------------------------------------------------------------------ diagonal tile
-    // warp 0 factors it column by column; warp 1 follows one column behind with the inverse, so inv(L_rr) exists
+    // one warp factors it column by column; another follows one column behind with the inverse, so inv(L_rr) exists
     // (almost) as soon as L_rr does and the rows below never run a triangular solve
-    if (warp == 0) {
-      float* T = own + r * TS;
+    const int w_fac = phase ? 0 : CLW - 1, w_inv = phase ? 1 : CLW - 2;
+    float* Tt = phase ? own + r * TS : stg;                    // phase 0: scratch tiles, values irrelevant
+    float* rdv = phase ? rd_own : rd_warm;
+    uint64_t* cb = phase ? colbar : nullptr;
+    if (warp == w_fac) {
       CL_MARK(6);
       int bad = 0;
-      warp_potrf32_bc(T, rd_own, colbar, lane, bad);
+      warp_potrf32_bc(Tt, rdv, cb, lane, bad);
       CL_MARK(7);
-      if (bad && lane == 0 && info) atomicCAS(&info[WC_INFO_NOT_PD], 0, grp * g + r * TB + bad);
-      __syncwarp();
-      if (Lg) store_tile_rowmajor(T, Lg + (long long)(r * TB) * g + r * TB, g, lane);
-    } else if (warp == 1) {
-      const float* T = own + r * TS;
+      if (phase) {
+        if (bad && lane == 0 && info) atomicCAS(&info[WC_INFO_NOT_PD], 0, grp * g + r * TB + bad);
+        __syncwarp();
+        if (Lg) store_tile_rowmajor(Tt, Lg + (long long)(r * TB) * g + r * TB, g, lane);
+      }
+    } else if (warp == w_inv) {
       float x[32];
-      warp_inverse_follow(x, T, rd_own, colbar, lane);
+      warp_inverse_follow(x, phase ? Tt : stg + TS, phase ? rdv : rd_warm + TB, cb, lane);
+      if (phase) {
       // dinv: element (row c, col lane).  The next CTA gets its copy pushed (it needs it first, on the critical path).
       if (r + 1 < NB) {
         const uint32_t rn = cl_map((uint32_t)__cvta_generic_to_shared(dnext), (uint32_t)(r + 1)) + (uint32_t)(lane * TP * 4);
@@ -762,14 +775,23 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
       __syncwarp();
       CL_MARK(9);
       store_tile_rowmajor(dinv, Xg + (long long)(r * TB) * g + r * TB, g, lane);
-    } else if (warp == 2 && r > 0) {
+      } else {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc += x[c];
+        rd_warm[TB + lane] = acc;              // keeps the warm-up alive
+      }
+    } else if (phase && warp == 2 && r > 0) {
       // all off-diagonal tiles of row r are in the scratch (written before the barrier above): announce them
       cl_fence();
       __syncwarp();
       if (lane < NB && lane != r) cl_arrive_remote(&flagA[r], lane);
     }
-    __syncthreads();
-    CL_MARK(10);
+    if (phase) {
+      __syncthreads();
+      CL_MARK(10);
+    }
+    }   // phase loop
     // ------------------------------------------------------------------ block column r of X
     for (int I = r + 1; I < NB; ++I) {
       cl_wait(&flagA[I]);

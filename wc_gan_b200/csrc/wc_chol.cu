@@ -606,7 +606,7 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
                         float* __restrict__ Lout, float* __restrict__ Xout, int32_t* info, int dbg) {
   wc_pdl_wait();
   extern __shared__ __align__(16) float sm[];
-  __shared__ uint64_t flagA[CLN], flagB[CLN], colbar[TB];
+  __shared__ uint64_t flagA[CLN], flagA2[CLN], flagB[CLN], colbar[TB];
   __shared__ __align__(16) float rd_own[TB], rd_warm[2 * TB];
   const int NB = g / TB;
   const int grp = blockIdx.x / CLN;
@@ -629,9 +629,11 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
   CL_MARK(0);
   if (t == 0) {
     for (int j = 0; j < CLN; ++j) {
-      const uint32_t a = (uint32_t)__cvta_generic_to_shared(&flagA[j]), b = (uint32_t)__cvta_generic_to_shared(&flagB[j]);
+      const uint32_t a = (uint32_t)__cvta_generic_to_shared(&flagA[j]), b = (uint32_t)__cvta_generic_to_shared(&flagB[j]),
+                     a2 = (uint32_t)__cvta_generic_to_shared(&flagA2[j]);
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a2) : "memory");
     }
     for (int j = 0; j < TB; ++j)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&colbar[j])) : "memory");
@@ -673,12 +675,20 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
     for (int J = 0; J < r; ++J) {
       float* T = own + J * TS;
       if (J > 0) {
-        // T -= sum_{K<J} L_rK L_JK^T  (row J's tiles come from the scratch; this runs while CTA J factors its diagonal tile)
-        cl_wait(&flagA[J]);
-        cta_fetch_tiles(gtile(J, 0), J, stg, t);
-        __syncthreads();
+        // T -= sum_{K<J} L_rK L_JK^T  (row J's tiles come from the scratch; this runs while CTA J factors its diagonal tile).
+        // Row J is announced in two parts: its tiles 0..J-2 one block step early (flagA2), the last one (J,J-1) with
+        // flagA -- only that one fetch and one tile product sit between CTA J's last panel and our turn.
         float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-        for (int K = 0; K < J; ++K) cta_tile_mac(acc, own + K * TS, stg + K * TS, tr, tc);
+        if (J > 1) {
+          cl_wait(&flagA2[J]);
+          cta_fetch_tiles(gtile(J, 0), J - 1, stg, t);
+          __syncthreads();
+          for (int K = 0; K < J - 1; ++K) cta_tile_mac(acc, own + K * TS, stg + K * TS, tr, tc);
+        }
+        cl_wait(&flagA[J]);
+        cta_fetch_tiles(gtile(J, J - 1), 1, stg + (J - 1) * TS, t);
+        __syncthreads();
+        cta_tile_mac(acc, own + (J - 1) * TS, stg + (J - 1) * TS, tr, tc);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           float2* p = reinterpret_cast<float2*>(T + (2 * tc + j) * TP + 2 * tr);
@@ -716,6 +726,12 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
         __syncthreads();
         if (J == r - 1) CL_MARK(4);
         // (row r is announced to the other CTAs from the diagonal phase below: they have a whole factorisation of slack)
+        if (J == r - 2 && warp == 3) {
+          // tiles (r, 0..r-2) are in the scratch (stored before the barrier above): the early part of row r
+          cl_fence();
+          __syncwarp();
+          if (lane < NB && lane > r) cl_arrive_remote(&flagA2[r], lane);
+        }
       }
       {   // right-looking update of the diagonal tile: T_rr -= L_rJ L_rJ^T
         float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};

@@ -225,7 +225,10 @@ struct VecJob {
   int cta0, nctas;
 };
 constexpr int SMM_MAXJOBS = 3, SMM_MAXVEC = 2;
-struct SmmMulti { SmmJob job[SMM_MAXJOBS]; int njobs; VecJob vec[SMM_MAXVEC]; int nvec; };
+// lead: CTAs [0, lead) exit at once.  The tile code is ~1500 straight-line instructions per operand-layout variant and a
+// launch runs it once per SM: ~2.7 us slower when that SM's instruction cache last held another variant.  CTA i of
+// consecutive launches lands on the same SM, so a launch can be shifted onto the SMs that just ran its variant.
+struct SmmMulti { SmmJob job[SMM_MAXJOBS]; int njobs; VecJob vec[SMM_MAXVEC]; int nvec; int lead; };
 
 // one CTA = 32 outputs of one batch; 16 k-slices of 32 threads
 __device__ __forceinline__ void vec_job_run(const VecJob& v, int cta, float* sm) {
@@ -274,7 +277,8 @@ __device__ __forceinline__ void vec_job_run(const VecJob& v, int cta, float* sm)
 __global__ void __launch_bounds__(SMM_THREADS) smm_multi_kernel(const __grid_constant__ SmmMulti mp) {
   wc_pdl_wait();
   extern __shared__ __align__(16) float smm_sm[];
-  const int cta = blockIdx.x;
+  const int cta = (int)blockIdx.x - mp.lead;
+  if (cta < 0) return;
   for (int v = 0; v < mp.nvec; ++v)
     if (cta >= mp.vec[v].cta0 && cta < mp.vec[v].cta0 + mp.vec[v].nctas) { vec_job_run(mp.vec[v], cta - mp.vec[v].cta0, smm_sm); return; }
   int j = 0;
@@ -437,7 +441,7 @@ struct MultiLaunch {
       WC_CUDA(cudaFuncSetAttribute(smm_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMM_SMEM));
       attr_set = true;
     }
-    WC_CUDA(wc_launch(smm_multi_kernel, ctas, SMM_THREADS, SMM_SMEM, st, m));
+    WC_CUDA(wc_launch(smm_multi_kernel, ctas + m.lead, SMM_THREADS, SMM_SMEM, st, m));
     WC_CHECK_LAUNCH();
     return 0;
   }
@@ -1018,8 +1022,14 @@ int wc_factor_bwd_impl(const float* dWeff, const float* gbar, const float* Weff,
   if (decomposition == WC_DECOMP_CHOLESKY) {
     // Z = dWm Wm^T;  Phi = -(tril(Z) - diag(Z)/2);  dSigma' = sym(Wm^T Phi Wm)
     const WcSmm pz = smm_gg(dWm, false, Wm, true, W0, g, G);
-    const WcSmm py = smm_gg(W0, false, Wm, false, W1, g, G);
-    WcSmm pa = smm_gg(Wm, true, W1, false, A, g, G);
+    // Y = Psi Wm is stored TRANSPOSED (W1 = Y^T) and A = Wm^T Y computed as (Y^T Wm)^T with transposed output strides:
+    // the same products in the same order, but both launches use the row-panel / row-panel operand variant of M1's
+    // first job, whose code is still in the instruction cache of the SMs they run on (experiment bit 65536: read the
+    // symmetric Psi transposed instead, the k-major variant)
+    WcSmm py = smm_gg(W0, (wc_debug_flags() & 65536) != 0, Wm, false, W1, g, G);
+    py.rsC = 1; py.csC = g;
+    WcSmm pa = smm_gg(W1, false, Wm, false, A, g, G);
+    pa.rsC = 1; pa.csC = g;
     if (smm_is_fast(pz) && smm_is_fast(py) && smm_is_fast(pa)) {
       // three launches: Psi = Phi + Phi^T straight from the lower tiles of Z (+ cvec);  Y = Psi Wm;
       // A = (1-eps)/(count-1) Wm^T Y, which also leaves as the bf16 operand image of K6
@@ -1027,13 +1037,16 @@ int wc_factor_bwd_impl(const float* dWeff, const float* gbar, const float* Weff,
       SmmEpi e1{}; e1.kind = EPI_PSI;
       m1.add(pz, e1);
       cvec_done = m1.add_vec(vc);
+      // (experiment bit 131072: shift this launch by one job's worth of CTAs, onto the SMs that ran M1's second job --
+      // the same operand variant; measured: no gain, this launch is not bound by instruction fetch)
+      if ((wc_debug_flags() & 131072) && m1.ctas + (g / SMM_T) * (g / SMM_T) * G <= WC_NUM_SMS) m1.m.lead = (g / SMM_T) * (g / SMM_T) * G;
       rc = m1.launch(st); if (rc) return rc;
       m2.add(py);
       rc = m2.launch(st); if (rc) return rc;
       pa.alpha = 1.f - eps;
       SmmEpi e3{};
-      if (Tp_bwd && g == C) {
-        e3.kind = EPI_PACK; e3.pk0 = (uint8_t*)Tp_bwd + (size_t)pack_K * C * C * 4; e3.pkC = C;
+      if (Tp_bwd && g == C) {   // the tile holds A^T: image src(n,k) = A[k][n] = tile[n][k], the second packing form
+        e3.kind = EPI_PACK; e3.pk1 = (uint8_t*)Tp_bwd + (size_t)pack_K * C * C * 4; e3.pkC = C;
         packed = true;
       }
       if (!m3.add(pa, e3, count_dev, ch, 2, 1.f)) return WC_E_UNSUPPORTED;
@@ -1043,7 +1056,7 @@ int wc_factor_bwd_impl(const float* dWeff, const float* gbar, const float* Weff,
       p.alpha = -1.f; p.tri = 1;
       rc = smm(p, st, nullptr, 0.f, 0, 0.5f);
       if (rc) return rc;
-      rc = smm(py, st);     // Y = Phi Wm
+      rc = smm(smm_gg(W0, false, Wm, false, W1, g, G), st);     // Y = Phi Wm
       if (rc) return rc;
       rc = smm(smm_gg(Wm, true, W1, false, W0, g, G), st);      // Qs = Wm^T Y
       if (rc) return rc;

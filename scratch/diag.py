@@ -47,7 +47,7 @@ for flags in (0, 16, 2, 4, 8, 2 | 4, 4 | 8, 2 | 4 | 8):
     lib.wc_debug_set(flags)
     print(f'  flags {flags:5d}  K1 {timeit(k1):6.1f} us   K4 {timeit(k4):6.1f} us', flush=True)
 print('apply kernels: 64 no B reload, 128 no convert, 256 no MMA, 512 no store, 1024 no A load')
-for flags in (0, 2048, 4096, 64, 128, 256, 512, 1024, 64 | 256, 64 | 128 | 256, 64 | 128 | 256 | 512, 64 | 128 | 256 | 1024, 64 | 128 | 256 | 512 | 1024,
+for flags in (0, 32768, 4096, 64, 128, 256, 512, 1024, 64 | 256, 64 | 128 | 256, 64 | 128 | 256 | 512, 64 | 128 | 256 | 1024, 64 | 128 | 256 | 512 | 1024,
               128 | 256 | 512 | 1024):
     lib.wc_debug_set(flags)
     print(f'  flags {flags:5d}  K3 {timeit(k3):6.1f} us   K6 {timeit(k6):6.1f} us', flush=True)

@@ -60,3 +60,14 @@ def test_label_validation(stubbed):
         stack(x, torch.zeros(3, 1, dtype=torch.int32))       # one label per sample
     with pytest.raises(ValueError):
         W.DecorelationNormalization(group_size=3)(x)         # channels not divisible by the group size
+
+
+def test_peer_exchange_is_only_offered_on_cuda(monkeypatch):
+    """The peer-memory transport is never chosen for CPU tensors or when WC_B200_SYNC=nccl asks for host collectives;
+    neither case touches torch.distributed."""
+    import torch
+    from wc_gan_b200 import sync
+    assert sync.peer_exchange(None, 8, 8, torch.device('cpu')) is None
+    monkeypatch.setenv('WC_B200_SYNC', 'nccl')
+    assert sync.peer_exchange(None, 256, 256, torch.device('cuda', 0)) is None
+    assert sync.record_numel(8, 4) == 8 + 2 * 16 + 1

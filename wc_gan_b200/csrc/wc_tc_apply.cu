@@ -28,7 +28,7 @@ constexpr int TILE_M = 128;
 constexpr int NCONV_WARPS = 8, NEPI_WARPS = 4;
 constexpr int W_PROD = 0, W_MMA = 1, W_EPI0 = 2, W_CONV0 = W_EPI0 + NEPI_WARPS, W_BPROD = W_CONV0 + NCONV_WARPS;
 constexpr int NTHREADS = (W_BPROD + 1) * 32;
-constexpr int NCONV = NCONV_WARPS * 32, NEPI = NEPI_WARPS * 32;
+constexpr int NEPI = NEPI_WARPS * 32;
 constexpr int STG_BYTES = TILE_M * KB * 4;   // one fp32 activation box: 16 KB
 constexpr int NEPIBUF = 2;
 // ring depths <activation staging, A operand, B operand>: Rings1 is the default, the others are kept for experiments

@@ -109,7 +109,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
   __shared__ uint64_t stg_full[cfg::NSLOTS], stg_empty[cfg::NSLOTS], op_full[cfg::NOPS], op_empty[cfg::NOPS], acc_full, acc_empty;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float sred[NCONV_WARPS][C];      // column-sum reduction; row 0 doubles as the pivot
-  __shared__ __align__(16) float spiv[cfg::RG][C];       // pivot partial sums
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const long long total_units = (long long)p.N * p.ups;

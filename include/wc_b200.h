@@ -14,9 +14,10 @@
  *     (G,g,g) array holds one row-major g x g matrix per group (g == C is the reference);
  *   - per-class arrays are indexed by the int32 label cls[n] in [0,K); K == 1 (cls == NULL)
  *     is the unconditional layer;
- *   - the caller owns every buffer including workspaces; the library keeps no mutable
+ *   - the caller owns every buffer including workspaces; the compute path keeps no mutable
  *     global state, never allocates, never synchronises; all work is enqueued on `stream`
- *     (a cudaStream_t passed as void*);
+ *     (a cudaStream_t passed as void*).  The only process-wide switches are diagnostics that
+ *     default to off/automatic: wc_set_tensor_core_gram below and include/wc_b200_debug.h;
  *   - return value: 0 ok; <0 invalid argument / unsupported shape (WC_E_*); >0 a
  *     cudaError_t from the launch.
  */
@@ -30,7 +31,7 @@
 extern "C" {
 #endif
 
-#define WC_B200_VERSION 100
+#define WC_B200_VERSION 101
 
 #define WC_E_ARG        (-1)  /* null pointer / non-positive size / C % g != 0 */
 #define WC_E_WORKSPACE  (-2)  /* workspace too small */
@@ -45,10 +46,15 @@ extern "C" {
 #define WC_INFO_NOT_PD     0  /* 1 + index of the first non-positive Cholesky pivot (TF raises InvalidArgumentError; gan/train.py:109-112 swallows it) */
 #define WC_INFO_BAD_CLASS  1  /* 1 + first sample index whose label is outside [0,K) (label is clamped, never read out of bounds) */
 #define WC_INFO_JACOBI     2  /* sweeps the ZCA eigensolver used */
+#define WC_INFO_XCHG_TIMEOUT 3 /* synchronised batch over peer memory: 1 + rank of a peer whose record never arrived within
+                                  WC_B200_XCHG_TIMEOUT_MS (default 10000); the step's results are then undefined */
 
 typedef void* wc_stream_t;
 
 int wc_version(void);
+/* sizeof(WcLayerCall) / sizeof(WcSavedLayout) as compiled: a binding checks its own struct mirror against these */
+size_t wc_sizeof_layer_call(void);
+size_t wc_sizeof_saved_layout(void);
 
 /* Statistics only: number of kernels this library has launched since it was loaded
  * (a relaxed atomic counter; bench.py reports the per-step delta as gpu_launches).        */

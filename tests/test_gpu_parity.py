@@ -183,6 +183,19 @@ def test_cfg3_zca_full_c():
     run_case('d', 'uconv', (16, 16, 16, 256), dec='zca', g=None)
 
 
+@pytest.mark.parametrize('dist', ['iid', 'correlated', 'relu'])
+def test_cfg3_full_size_vs_oracle(dist):
+    """BASELINE.json's headline shape at FULL size, 256x16x16x256 (M = 65536 rows), Cholesky g = C + unconditional
+    coloring, against the fp64 oracle: y, dx, d u_kernel, d u_bias and both moving statistics.  This is where the
+    bf16x3 accumulation of K1 / K4 over 65536 rows has to hold the north_star tolerances."""
+    run_case('d', 'uconv', (256, 16, 16, 256), dist=dist)
+
+
+def test_cfg2_full_size_conditional_vs_oracle():
+    """cfg4's largest generator layer shape (256 x 32 x 32 x 128, K = 10, E = 4, ufconv) against the fp64 oracle."""
+    run_case('d', 'ufconv', (256, 32, 32, 128), K=10, E=4)
+
+
 def test_cfg3_full_size_properties():
     """Full 256x16x16x256: size-independent properties instead of an fp64 oracle run:
     whitened output has identity covariance / zero mean (gan/unit_tests.py:602-628 criterion), and the

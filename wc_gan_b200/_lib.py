@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 WC_DECOMP = {'cholesky': 0, 'zca': 1}
 INFO_SLOTS = 4
-INFO_NOT_PD, INFO_BAD_CLASS, INFO_JACOBI = 0, 1, 2
+INFO_NOT_PD, INFO_BAD_CLASS, INFO_JACOBI, INFO_XCHG_TIMEOUT = 0, 1, 2, 3
 
 
 class WcError(RuntimeError):
@@ -22,9 +22,9 @@ class WcError(RuntimeError):
 
 
 def _load() -> ctypes.CDLL:
-    path = _build.LIB
-    if not os.path.exists(path) or os.environ.get('WC_B200_REBUILD'):
-        path = _build.build()
+    # build() is a no-op when the source digest matches the stamp next to the .so, so a library left behind by an
+    # older csrc/ or header is never loaded silently; it serialises concurrent ranks with a file lock.
+    path = _build.build(force=bool(os.environ.get('WC_B200_REBUILD')))
     try:
         return ctypes.CDLL(path)
     except OSError as e:  # fail loudly: the product has no other implementation
@@ -54,6 +54,8 @@ class WcSavedLayout(ctypes.Structure):
 _P = c_void_p
 _SIGS = {
     'wc_version': (c_int, []),
+    'wc_sizeof_layer_call': (c_size_t, []),
+    'wc_sizeof_saved_layout': (c_size_t, []),
     'wc_launch_count': (ctypes.c_longlong, []),
     'wc_path_for': (c_int, [c_int64, c_int, c_int, c_int]),
     'wc_set_tensor_core_gram': (None, [c_int]),
@@ -91,6 +93,13 @@ for _name, (_res, _args) in _SIGS.items():
     _fn.argtypes = _args
 
 EXPORTS = tuple(_SIGS.keys())
+
+# the ctypes mirrors above must describe the structs the library was compiled with
+if lib.wc_version() != 101:
+    raise WcError(f'libwc_b200.so reports version {lib.wc_version()}, this package expects 101 (stale build?)')
+if (lib.wc_sizeof_layer_call() != ctypes.sizeof(WcLayerCall) or
+        lib.wc_sizeof_saved_layout() != ctypes.sizeof(WcSavedLayout)):
+    raise WcError('WcLayerCall / WcSavedLayout layout mismatch between include/wc_b200.h and wc_gan_b200/_lib.py')
 
 _ERRS = {-1: 'invalid argument', -2: 'workspace too small', -3: 'unsupported shape', -4: 'misaligned pointer'}
 

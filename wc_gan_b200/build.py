@@ -38,13 +38,29 @@ def nvcc_path() -> str:
     raise RuntimeError('nvcc not found: libwc_b200.so cannot be built')
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ into one shared library.  Returns its path."""
-    dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+def _fresh(dig: str) -> bool:
+    if os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:
-            if fh.read().strip() == dig:
-                return LIB
+            return fh.read().strip() == dig
+    return False
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu under csrc/ into one shared library.  Returns its path.  A no-op when the digest of the
+    sources matches the stamp; concurrent callers (the ranks of one torchrun launch) are serialised with a file lock
+    and the library is moved into place atomically."""
+    import fcntl
+    dig = _digest()
+    if not force and _fresh(dig):
+        return LIB
+    with open(os.path.join(HERE, '.build.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and _fresh(dig):       # another rank built it while we waited
+            return LIB
+        return _build_locked(dig, verbose)
+
+
+def _build_locked(dig: str, verbose: bool) -> str:
     objdir = os.path.join(os.path.dirname(HERE), 'build')
     os.makedirs(objdir, exist_ok=True)
     nvcc = nvcc_path()
@@ -61,8 +77,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
-    cmd = [nvcc, '-shared', '-cudart', 'shared', '-o', LIB] + objs
+    tmp = LIB + f'.tmp{os.getpid()}'
+    cmd = [nvcc, '-shared', '-cudart', 'shared', '-o', tmp] + objs
     subprocess.run(cmd, check=True)
+    os.replace(tmp, LIB)
     with open(STAMP, 'w') as fh:
         fh.write(dig)
     return LIB

@@ -115,8 +115,9 @@ int wc_factor_bwd_impl(const float* dWeff, const float* gbar, const float* Weff,
 
 // peer-memory exchanges (wc_exchange.cu)
 int wc_stats_exchange(float* rec, float count_local, int C, int g, void* const* peers, void* state, int rank, int world, float eps,
-                      float extra_eps, float momentum, float* moving_mean, float* moving_cov, float* Ashr, cudaStream_t st);
-int wc_adjoint_exchange(float* red, int C, int g, void* const* peers, void* state, int rank, int world, cudaStream_t st);
+                      float extra_eps, float momentum, float* moving_mean, float* moving_cov, float* Ashr, int32_t* info, cudaStream_t st);
+int wc_adjoint_exchange(float* red, int C, int g, void* const* peers, void* state, int rank, int world, int32_t* info,
+                        cudaStream_t st);
 
 // tensor-map encoder for the TMA kernels (wc_tc_apply.cu)
 int wc_make_f32_map3(void* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,

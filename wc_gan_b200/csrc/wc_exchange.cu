@@ -16,6 +16,7 @@
 // reaching its target also means every local CTA has finished READING the local record, so the merged statistics may
 // overwrite it in place.  All CTAs of the grid must be co-resident (they spin): the grid is far below the SM count.
 #include "wc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -51,7 +52,15 @@ struct XchParams {
   size_t data_off, slot_floats;   // byte offset of this direction's slots, floats per (slot, rank) record
   int n;                     // floats actually exchanged
   int has_tail; float tail;  // forward: the record's last element (this shard's row count) is supplied by value
+  int32_t* info;             // nullable: info[WC_INFO_XCHG_TIMEOUT] is set when a peer never arrived
+  unsigned long long timeout_ns;   // bound of the spin (0 = wait forever)
 };
+
+__device__ __forceinline__ unsigned long long xch_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // push `src[0..n)` into slot [e & 1][rank] of every peer, signal, wait for all peers.  Returns the epoch.
 __device__ __forceinline__ uint32_t xch_push_wait(const XchParams& p, const float* __restrict__ src) {
@@ -68,7 +77,8 @@ __device__ __forceinline__ uint32_t xch_push_wait(const XchParams& p, const floa
   for (int q = 0; q < p.R; ++q) {
     const int r = (p.rank + 1 + q) % p.R;               // start with the neighbour: spreads the NVLink traffic
     float4* dst = reinterpret_cast<float4*>(p.peers[r] + rec_off);
-    for (int i = b4 + t; i < e4; i += blockDim.x) dst[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    // plain (coherent) loads: the same kernel later overwrites `src` in place with the merged result
+    for (int i = b4 + t; i < e4; i += blockDim.x) dst[i] = reinterpret_cast<const float4*>(src)[i];
     if (blockIdx.x == gridDim.x - 1) {
       float* dsts = reinterpret_cast<float*>(p.peers[r] + rec_off);
       for (int i = (n4 << 2) + t; i < p.n; i += blockDim.x) dsts[i] = src[i];
@@ -86,7 +96,16 @@ __device__ __forceinline__ uint32_t xch_push_wait(const XchParams& p, const floa
   const uint32_t target = gridDim.x * (e / 2u + 1u);
   if (t < p.R) {
     const uint32_t* f = reinterpret_cast<const uint32_t*>(p.peers[p.rank] + flag_off) + t;
-    while ((int32_t)(ld_acquire_sys(f) - target) < 0) { }
+    // bounded spin: a peer that died (or whose exchange is queued behind a kernel that waits for us) must not hang
+    // the GPU.  The deadline is only consulted every 1024 polls.
+    const unsigned long long t0 = p.timeout_ns ? xch_now() : 0ull;
+    uint32_t polls = 0;
+    while ((int32_t)(ld_acquire_sys(f) - target) < 0) {
+      if (p.timeout_ns && ((++polls & 1023u) == 0) && xch_now() - t0 > p.timeout_ns) {
+        if (p.info) atomicMax(&p.info[WC_INFO_XCHG_TIMEOUT], 1 + t);     // 1 + rank of the peer that is missing
+        break;
+      }
+    }
   }
   __syncthreads();
   return e;
@@ -176,27 +195,40 @@ extern "C" size_t wc_exchange_bytes(int C, int g, int world) {
 
 // rec: mean | S | count of this shard (the count is passed by value); on return the merged record.  state: 4 zero-initialised
 // uint32 owned by the layer ({epoch, ticket} for forward, then backward).
+static unsigned long long xch_timeout_ns() {
+  static const unsigned long long v = [] {
+    const char* e = getenv("WC_B200_XCHG_TIMEOUT_MS");
+    const long long ms = e ? atoll(e) : 10000;
+    return ms > 0 ? (unsigned long long)ms * 1000000ull : 0ull;
+  }();
+  return v;
+}
+
 int wc_stats_exchange(float* rec, float count_local, int C, int g, void* const* peers, void* state, int rank, int world, float eps,
-                      float extra_eps, float momentum, float* moving_mean, float* moving_cov, float* Ashr, cudaStream_t st) {
+                      float extra_eps, float momentum, float* moving_mean, float* moving_cov, float* Ashr, int32_t* info,
+                      cudaStream_t st) {
   if (!rec || !peers || !state || !moving_mean || !moving_cov || !Ashr || rank < 0 || rank >= world || world > XCH_MAXR) return WC_E_ARG;
   const XchLayout L = xch_layout(C, g, world);
   XchParams p{};
   p.peers = reinterpret_cast<char* const*>(peers); p.state = reinterpret_cast<uint32_t*>(state);
   p.rank = rank; p.R = world; p.dir = 0; p.data_off = L.fwd_off; p.slot_floats = L.fwd_floats;
   p.n = C + C * g + 1; p.has_tail = 1; p.tail = count_local;
+  p.info = info; p.timeout_ns = xch_timeout_ns();
   FwdMerge m{C, g, eps, extra_eps, momentum, moving_mean, moving_cov, rec, Ashr};
   WC_CUDA(wc_launch(stats_exchange_kernel, XCH_CTAS, XCH_THREADS, 0, st, p, m));
   WC_CHECK_LAUNCH();
   return 0;
 }
 
-int wc_adjoint_exchange(float* red, int C, int g, void* const* peers, void* state, int rank, int world, cudaStream_t st) {
+int wc_adjoint_exchange(float* red, int C, int g, void* const* peers, void* state, int rank, int world, int32_t* info,
+                        cudaStream_t st) {
   if (!red || !peers || !state || rank < 0 || rank >= world || world > XCH_MAXR) return WC_E_ARG;
   const XchLayout L = xch_layout(C, g, world);
   XchParams p{};
   p.peers = reinterpret_cast<char* const*>(peers); p.state = reinterpret_cast<uint32_t*>(state) + 2;
   p.rank = rank; p.R = world; p.dir = 1; p.data_off = L.bwd_off; p.slot_floats = L.bwd_floats;
   p.n = C * g + C;
+  p.info = info; p.timeout_ns = xch_timeout_ns();
   WC_CUDA(wc_launch(adjoint_exchange_kernel, XCH_CTAS, XCH_THREADS, 0, st, p, red));
   WC_CHECK_LAUNCH();
   return 0;

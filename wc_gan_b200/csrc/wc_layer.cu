@@ -94,6 +94,9 @@ template <typename T> inline T* at(void* base, size_t off) { return off == NONE 
 
 }  // namespace
 
+extern "C" size_t wc_sizeof_layer_call(void) { return sizeof(WcLayerCall); }
+extern "C" size_t wc_sizeof_saved_layout(void) { return sizeof(WcSavedLayout); }
+
 extern "C" int wc_layer_saved_layout(const WcLayerCall* c, WcSavedLayout* out) {
   int rc = check(c);
   if (rc || !out) return rc ? rc : WC_E_ARG;
@@ -142,7 +145,7 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
     // shard record -> every rank; Chan merge + prep from the complete set; saved mean | S | count become global
     rc = wc_stats_exchange(at<float>(c.saved, L.rec), (float)c.count, c.Cin, c.g, c.xchg_peers, c.xchg_state, c.xchg_rank,
                            c.xchg_world, c.eps, c.decomposition == WC_DECOMP_ZCA ? c.eps : 0.f, c.momentum, c.moving_mean,
-                           c.moving_cov, at<float>(c.workspace, W.factor), (cudaStream_t)stream);
+                           c.moving_cov, at<float>(c.workspace, W.factor), c.info, (cudaStream_t)stream);
     if (rc) return rc;
     prep_done = 1;
     count_dev = at<float>(c.saved, L.rec_count);
@@ -212,7 +215,7 @@ extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
   float *A = nullptr, *cvec = nullptr;
   const float* count_dev = c.count_dev;
   if (stats_grad && xchg_bwd(c)) {
-    rc = wc_adjoint_exchange(c.red, c.Cin, g, c.xchg_peers, c.xchg_state, c.xchg_rank, c.xchg_world, (cudaStream_t)stream);
+    rc = wc_adjoint_exchange(c.red, c.Cin, g, c.xchg_peers, c.xchg_state, c.xchg_rank, c.xchg_world, c.info, (cudaStream_t)stream);
     if (rc) return rc;
     count_dev = at<float>(c.saved, L.rec_count);       // global row count, left there by the forward exchange
   }

@@ -73,6 +73,30 @@ def _need_cuda(t: torch.Tensor, name: str) -> None:
         raise TypeError(f'{name} must be float32 (got {t.dtype})')
 
 
+# largest whitening group the factorisation kernels take (wc_factor_fwd: one group matrix per CTA / 8-CTA cluster)
+MAX_GROUP = 256
+
+
+def _operand(t, name, dev, shape, *, numel=None, inplace=False):
+    """Validate one weight / buffer before its data_ptr() goes to the C ABI.  Returns a contiguous tensor (in-place
+    buffers must already be contiguous: the kernels update them)."""
+    if t is None:
+        return None
+    if not t.is_cuda or t.device != dev:
+        raise ValueError(f'{name} is on {t.device}, x on {dev}: every operand must live on the same CUDA device')
+    if t.dtype != torch.float32:
+        raise TypeError(f'{name} must be float32 (got {t.dtype})')
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f'{name} has shape {tuple(t.shape)}, expected {tuple(shape)}')
+    if numel is not None and t.numel() != numel:
+        raise ValueError(f'{name} has {t.numel()} elements, expected {numel}')
+    if not t.is_contiguous():
+        if inplace:
+            raise ValueError(f'{name} is updated in place and must be contiguous')
+        t = t.contiguous()
+    return t
+
+
 def _f32(*shape, device):
     return torch.empty(shape, dtype=torch.float32, device=device)
 
@@ -136,15 +160,33 @@ class WhiteningColoringFn(torch.autograd.Function):
             cls = cls.contiguous()
         else:
             cls = None
-        for name, w in (('Wu', Wu), ('Wc', Wc), ('D', D)):
-            if w is not None and w.shape[-2] != Cin:
-                raise ValueError(f'{name} has {w.shape[-2]} input channels, x has {Cin}')
         Cout = next((w.shape[-1] for w in (Wu, Wc, D) if w is not None), Cin)
         E = class_matrix.shape[1] if class_matrix is not None else 0
         g = spec.group_size or Cin
         if spec.whiten and Cin % g:
             raise ValueError(f'channels {Cin} not divisible by group_size {g}')
+        if spec.whiten and g > MAX_GROUP:
+            raise ValueError(f'whitening group of {g} channels: the factorisation kernels hold one group matrix per '
+                             f'CTA / cluster and support at most {MAX_GROUP}; pass group_size<={MAX_GROUP} '
+                             f'(block-diagonal whitening) for C={Cin}')
         G = Cin // g
+        # The kernels take raw device pointers: every operand is checked here (device, dtype, layout, shape), so a
+        # mismatch raises instead of reading out of bounds.
+        Wu, bu, Wc, bc = (_operand(t, n, dev, s) for t, n, s in (
+            (Wu, 'Wu', (Cin, Cout)), (bu, 'bu', (Cout,)), (Wc, 'Wc', (K, Cin, Cout)), (bc, 'bc', (K, Cout))))
+        class_matrix, D, bf = (_operand(t, n, dev, s) for t, n, s in (
+            (class_matrix, 'class_matrix', (K, E)), (D, 'D', (E, Cin, Cout)), (bf, 'bf', (K, Cout))))
+        if (class_matrix is None) != (D is None):
+            raise ValueError('class_matrix and D (the FactorizedConv11 dictionary) go together')
+        if spec.whiten:
+            if moving_mean is None or moving_cov is None:
+                raise ValueError('whitening needs moving_mean and moving_cov buffers')
+            moving_mean = _operand(moving_mean, 'moving_mean', dev, None, numel=Cin, inplace=True)
+            moving_cov = _operand(moving_cov, 'moving_cov', dev, None, numel=Cin * g, inplace=True)
+        if cls is not None and cls.device != dev:
+            raise ValueError(f'cls is on {cls.device}, x on {dev}: labels must live on the same CUDA device')
+        if info is not None and (info.device != dev or info.dtype != torch.int32 or info.numel() < _lib.INFO_SLOTS):
+            raise ValueError(f'info must be an int32 tensor of {_lib.INFO_SLOTS} slots on {dev}')
         dec = _lib.WC_DECOMP[spec.decomposition]
         world = sync.world_size(group)
         do_sync = spec.whiten and training and world > 1

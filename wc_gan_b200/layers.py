@@ -91,6 +91,9 @@ class _LazyBuild(nn.Module):
             raise ArithmeticError(f'{self.layer_name}: covariance not positive definite at pivot {v[_lib.INFO_NOT_PD] - 1}')
         if v[_lib.INFO_BAD_CLASS]:
             raise IndexError(f'{self.layer_name}: class label out of range for sample {v[_lib.INFO_BAD_CLASS] - 1}')
+        if v[_lib.INFO_XCHG_TIMEOUT]:
+            raise TimeoutError(f'{self.layer_name}: synchronised-batch exchange timed out waiting for rank '
+                               f'{v[_lib.INFO_XCHG_TIMEOUT] - 1}')
 
 
 def _split_inputs(inputs):

@@ -76,23 +76,42 @@ class PeerExchange:
         self.peers_dev = int(handle.buffer_ptrs_dev)      # device array of `world` buffer pointers, rank order
 
 
-_EXCHANGES = {}
+_EXCHANGES = {}      # (process group object, C, g, device index) -> PeerExchange | None
 _WARNED = False
+
+
+def _all_agree(ok: bool, pg, device) -> bool:
+    """True iff `ok` on every rank (one small all-reduce: every rank calls it at the same point, whatever happened
+    to it locally, so nobody is left waiting in a collective the others skipped)."""
+    flag = torch.tensor([1 if ok else 0], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=pg)
+    return int(flag.item()) == 1
 
 
 def peer_exchange(group, C: int, g: int, device):
     """The peer-memory transport for layers of shape (C, g) on `group`, or None (then the host runs NCCL collectives).
-    Collective on first use per (group, C, g): every rank reaches it at the same layer.  Layers of the same shape share
-    one buffer: exchanges are stream-ordered and happen in the same order on every rank.
-    WC_B200_SYNC=nccl forces the host-collective path."""
+    Collective on first use per (group, C, g): every rank reaches it at the same layer.
+
+    Requirements of this transport (the NCCL path has none of them; WC_B200_SYNC=nccl forces it):
+      * layers of the same (C, g) share one buffer and one epoch counter, so their exchanges must be enqueued on ONE
+        stream, in the same order on every rank (true for a model stepped the same way on every rank);
+      * the exchange kernels spin until every peer has pushed: a kernel that a peer enqueues before ITS exchange must
+        not wait on this rank (e.g. an NCCL collective issued from an autograd hook between the layer's kernels on one
+        rank only).  With DDP keep the default CUDA_DEVICE_MAX_CONNECTIONS so NCCL's kernels and these run concurrently;
+      * a peer that never arrives (crashed rank) is detected after WC_B200_XCHG_TIMEOUT_MS (default 10000): the kernel
+        gives up, sets info[WC_INFO_XCHG_TIMEOUT] and the layer's check_info() raises; results of that step are garbage.
+    """
     global _WARNED
     if os.environ.get('WC_B200_SYNC', '').lower() == 'nccl' or device.type != 'cuda':
         return None
     pg = group if group is not None else dist.group.WORLD
-    key = (id(pg), C, g, device.index)
+    key = (pg, C, g, device.index)          # the group object itself: id() can be reused after garbage collection
     if key in _EXCHANGES:
         return _EXCHANGES[key]
-    xch = None
+    # Every fallible step is followed by an agreement round, so a rank that failed locally never skips a collective
+    # the others are already blocked in (symm.rendezvous and dist.barrier are collectives).
+    xch, err = None, None
+    buf = handle = None
     try:
         import torch.distributed._symmetric_memory as symm
         from ._lib import lib
@@ -102,20 +121,21 @@ def peer_exchange(group, C: int, g: int, device):
             raise RuntimeError(f'no peer exchange for C={C}, g={g}, world={world}')
         buf = symm.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
         buf.zero_()
-        handle = symm.rendezvous(buf, pg)
-        state = torch.zeros(4, dtype=torch.int32, device=device)
-        torch.cuda.synchronize(device)
-        dist.barrier(group=pg)              # every buffer is zeroed before anyone's first push can land in it
-        xch = PeerExchange(buf, handle, state, rank, world)
-    except Exception as e:                  # no P2P / symmetric memory here: the NCCL path is always available
-        if not _WARNED:
-            warnings.warn(f'wc_gan_b200: peer-memory exchange unavailable ({e!r}); using NCCL collectives')
-            _WARNED = True
-        xch = None
-    # all ranks must agree, or one would wait in a kernel for pushes that never come
-    ok = torch.tensor([1 if xch is not None else 0], device=device)
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=pg)
-    if int(ok.item()) == 0:
-        xch = None
+    except Exception as e:                  # no symmetric memory here
+        err = e
+    if _all_agree(err is None, pg, device):
+        try:
+            handle = symm.rendezvous(buf, pg)
+            state = torch.zeros(4, dtype=torch.int32, device=device)
+            torch.cuda.synchronize(device)
+        except Exception as e:              # no P2P mapping between these devices
+            err = e
+        if _all_agree(err is None, pg, device):
+            dist.barrier(group=pg)          # every buffer is zeroed before anyone's first push can land in it
+            xch = PeerExchange(buf, handle, state, rank, world)
+    if xch is None and not _WARNED:
+        warnings.warn(f'wc_gan_b200: peer-memory exchange unavailable ({err!r} on this or another rank); '
+                      f'using NCCL collectives')
+        _WARNED = True
     _EXCHANGES[key] = xch
     return xch

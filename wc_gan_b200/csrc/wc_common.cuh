@@ -57,6 +57,12 @@ __device__ __forceinline__ void wc_mark(unsigned long long* buf, int slot) {
   }
 }
 
+// L2 residency policy of the four streaming kernels (bit set = hint used): 1 K1 loads evict_last, 2 K3 loads evict_first,
+// 4 K3 stores evict_first, 8 K4 loads evict_last, 16 K6 loads evict_first, 32 K6 stores evict_first.
+// Default WC_L2_DEFAULT; the environment variable WC_B200_L2 (read once) overrides it for A/B measurements.
+constexpr int WC_L2_DEFAULT = 0;
+int wc_l2_mode();
+
 static inline bool wc_aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 static inline size_t wc_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int wc_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

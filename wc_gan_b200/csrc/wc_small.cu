@@ -1112,6 +1112,10 @@ extern "C" long long wc_launch_count(void) { return g_launches.load(std::memory_
 static int g_dbg_flags = 0;
 static unsigned long long* g_dbg_buf = nullptr;
 int wc_debug_flags() { return g_dbg_flags; }
+int wc_l2_mode() {
+  static const int mode = [] { const char* e = getenv("WC_B200_L2"); return e ? atoi(e) : WC_L2_DEFAULT; }();
+  return mode;
+}
 bool wc_pdl_enabled() {
   static const bool env_off = getenv("WC_B200_NO_PDL") != nullptr;    // A/B measurements
   return !env_off && !(g_dbg_flags & 8192);

@@ -50,6 +50,7 @@ struct TcApplyParams {
   int N, HW, tiles_per_sample;
   long long total_tiles;
   const int32_t* cls; int K; int32_t* info;
+  int l2_load[2], l2_store;                 // L2 eviction priority of the activation loads per segment / of the output stores (wctc::l2_policy)
   unsigned long long* dbg; int dbg_flags;   // debug marks / experiment switches (0 in normal use)
 };
 
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
     // (its own thread: the staging ring runs NSTG boxes ahead of the converters, independent of the B ring)
     if (lane == 0) {
       uint32_t ia = 0;
+      const uint64_t pol[2] = {l2_policy(p.l2_load[0]), l2_policy(p.l2_load[1])};
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileInfo ti = tile_info(p, tile);
         for (int it = 0; it < total_kb; ++it, ++ia) {
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
           if (p.dbg_flags & 1024) mbar_arrive(&stg_full[s]);
           else {
             mbar_arrive_expect_tx(&stg_full[s], STG_BYTES);
-            tma_load_3d(smem + s * STG_BYTES, sg == 0 ? &tm_a0 : &tm_a1, kb * KB, ti.r0, ti.sample, &stg_full[s]);
+            tma_load_3d_hint(smem + s * STG_BYTES, sg == 0 ? &tm_a0 : &tm_a1, kb * KB, ti.r0, ti.sample, &stg_full[s], pol[sg]);
           }
         }
       }
@@ -204,6 +206,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
     const int q = warp & 3;                // TMEM lanes 32q .. 32q+31 are the ones this warp may read
     const int row = q * 32 + lane;         // row of the tile held by this thread
     uint32_t lt = 0, ec = 0;
+    const uint64_t pol_st = l2_policy(p.l2_store);
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const TileInfo ti = tile_info(p, tile);
       const uint32_t ab = lt & 1;
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
         fence_proxy_async();
         asm volatile("bar.sync 2, %0;" ::"n"(NEPI));
         if (te == 0 && !(p.dbg_flags & 512)) {
-          tma_store_3d(&tm_out, c0, ti.r0, ti.sample, smem + cfg::OFF_EPI + eb * STG_BYTES);
+          tma_store_3d_hint(&tm_out, c0, ti.r0, ti.sample, smem + cfg::OFF_EPI + eb * STG_BYTES, pol_st);
           bulk_commit_group();
         }
       }
@@ -455,6 +458,9 @@ int wc_tc_apply_fwd(const float* x, int N, int HW, int C, const float* mean, con
   p.nseg = 1;
   p.bias = b; p.bias_slot_stride = C; p.bias_sign = 1.f;
   p.cls = cls; p.K = K; p.info = info;
+  const int l2 = wc_l2_mode();
+  p.l2_load[0] = (l2 & 2) ? 2 : 0;    // x: last use of the forward pass
+  p.l2_store = (l2 & 4) ? 2 : 0;      // y: written once, read by another layer much later
   return C == 256 ? launch_tc_apply<256>(p, x, nullptr, y, N, HW, st) : launch_tc_apply<128>(p, x, nullptr, y, N, HW, st);
 }
 
@@ -469,6 +475,9 @@ int wc_tc_apply_bwd(const float* x, const float* dy, int N, int HW, int C, const
   }
   p.bias = has_A ? cvec : nullptr; p.bias_slot_stride = 0; p.bias_sign = -1.f;
   p.cls = cls; p.K = K; p.info = nullptr;
+  const int l2 = wc_l2_mode();
+  p.l2_load[0] = p.l2_load[1] = (l2 & 16) ? 2 : 0;
+  p.l2_store = (l2 & 32) ? 2 : 0;
   return C == 256 ? launch_tc_apply<256>(p, dy, has_A ? x : nullptr, dx, N, HW, st)
                   : launch_tc_apply<128>(p, dy, has_A ? x : nullptr, dx, N, HW, st);
 }

@@ -44,6 +44,7 @@ struct TcGramParams {
   float* asum; float* bsum; long long sum_slot_stride;
   float* pivot_out;                     // self mode: the pivot every CTA used (written by CTA 0)
   int nslots;                           // number of [C][C] accumulators behind `out`
+  int l2_load;                          // L2 eviction priority of the activation loads (wctc::l2_policy)
   unsigned long long* dbg; int dbg_flags;   // debug marks (nullptr in normal use)
 };
 
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
     if (lane == 0) {
       StepIter iter(p, ub, ue);
       uint32_t pi = 0;
+      const uint64_t pol = l2_policy(p.l2_load);
       for (Step st = iter.next(); st.valid; st = iter.next()) {
         const long long off = ((long long)st.sample * p.HW + st.row0) * C;
         const uint32_t bytes = (uint32_t)st.nrows * C * 4;
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
           const int sl = pi % cfg::NSLOTS;
           mbar_wait(&stg_empty[sl], ((pi / cfg::NSLOTS) & 1) ^ 1);
           mbar_arrive_expect_tx(&stg_full[sl], bytes);
-          bulk_g2s(stg + sl * cfg::SLOT, (op == 0 ? p.A : p.B) + off, bytes, &stg_full[sl]);
+          bulk_g2s_hint(stg + sl * cfg::SLOT, (op == 0 ? p.A : p.B) + off, bytes, &stg_full[sl], pol);
         }
       }
     }
@@ -429,6 +431,7 @@ int wc_tc_gram_self(const float* x, long long M, int C, int g, float* pivot_out,
   p.out = Sp; p.out_slot_stride = 0;
   p.asum = sums; p.bsum = nullptr; p.sum_slot_stride = 0;
   p.pivot_out = pivot_out; p.nslots = 1;
+  p.l2_load = (wc_l2_mode() & 1) ? 1 : 0;      // x is read again by K3 right after the factorisation: keep it in L2
   return C == 256 ? launch_tc_gram<256>(p, st) : launch_tc_gram<128>(p, st);
 }
 
@@ -442,5 +445,6 @@ int wc_tc_gram_cross(const float* x, const float* dy, int N, int HW, int C, cons
   p.out = P; p.out_slot_stride = (long long)C * C;
   p.asum = nullptr; p.bsum = s; p.sum_slot_stride = C;
   p.pivot_out = nullptr; p.nslots = K;
+  p.l2_load = (wc_l2_mode() & 8) ? 1 : 0;      // x and dy are read again by K6
   return C == 256 ? launch_tc_gram<256>(p, st) : launch_tc_gram<128>(p, st);
 }

@@ -21,9 +21,9 @@ info = torch.zeros(4, dtype=torch.int32, device=dev)
 k3 = lambda i: lib.wc_apply_fwd(ptr(xs[i % NB]), N, HW, C, C, ptr(mean), ptr(T), ptr(pf), ptr(b), None, 1, 0, ptr(outs[i % 2]), ptr(info), st)
 k6 = lambda i: lib.wc_apply_bwd(ptr(xs[i % NB]), ptr(dys[i % NB]), N, HW, C, C, ptr(mean), ptr(T), ptr(A), ptr(pb), ptr(b), C, None, 1, ptr(outs[i % 2]), st)
 def marks(tag):
-    buf = (ctypes.c_ulonglong * (160 * 8))()
+    buf = (ctypes.c_ulonglong * (160 * 32))()
     lib.wc_debug_marks(buf)
-    rows = [[buf[bb * 8 + k] for k in range(2)] for bb in range(148) if buf[bb * 8]]
+    rows = [[buf[bb * 32 + k] for k in range(2)] for bb in range(148) if buf[bb * 32]]
     t0 = min(r[0] for r in rows)
     ends = [(r[1] - t0) / 1e3 for r in rows]
     starts = [(r[0] - t0) / 1e3 for r in rows]

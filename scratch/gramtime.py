@@ -14,9 +14,9 @@ P = torch.zeros(C * C + C, device=dev); s = P[C * C:]
 st = torch.cuda.current_stream().cuda_stream
 lib.wc_debug_set.argtypes = [ctypes.c_int]; lib.wc_debug_marks.argtypes = [ctypes.c_void_p]
 def marks(tag):
-    buf = (ctypes.c_ulonglong * (160 * 8))()
+    buf = (ctypes.c_ulonglong * (160 * 32))()
     lib.wc_debug_marks(buf)
-    rows = [[buf[b * 8 + k] for k in range(3)] for b in range(148) if buf[b * 8]]
+    rows = [[buf[b * 32 + k] for k in range(3)] for b in range(148) if buf[b * 32]]
     t0 = min(r[0] for r in rows)
     main = [r[1] - r[0] for r in rows]; fl = [r[2] - r[1] for r in rows]; end = [r[2] - t0 for r in rows]
     print(f'{tag}: ctas {len(rows)} main avg {sum(main)/len(main)/1e3:.1f} max {max(main)/1e3:.1f} us | flush avg {sum(fl)/len(fl)/1e3:.1f} max {max(fl)/1e3:.1f} us | end max {max(end)/1e3:.1f} us, start spread {max(r[0] for r in rows)-t0} ns')

@@ -9,10 +9,10 @@ import sys
 lib.wc_debug_set(int(sys.argv[1]))
 for _ in range(3): layer(x)
 torch.cuda.synchronize()
-buf = (ctypes.c_ulonglong * (160 * 8))()
+buf = (ctypes.c_ulonglong * (160 * 32))()
 lib.wc_debug_marks(buf)
 for b in (0, 8):
-    r = [buf[b * 8 + k] for k in range(8)]
+    r = [buf[b * 32 + k] for k in range(8)]
     print('block', b, [r[k] - r[0] if r[k] else None for k in range(8)])
-t0 = min(buf[b * 8] for b in range(32) if buf[b * 8])
-print('start spread', [buf[b * 8] - t0 for b in range(0, 32, 4)])
+t0 = min(buf[b * 32] for b in range(32) if buf[b * 32])
+print('start spread', [buf[b * 32] - t0 for b in range(0, 32, 4)])

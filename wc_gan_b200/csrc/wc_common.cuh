@@ -46,7 +46,7 @@ inline cudaError_t wc_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size
 // ---- debug-only instrumentation (not part of include/wc_b200.h) ---------------------------------------
 // wc_debug_set(flags): bit0 = kernels record globaltimer marks into a device buffer [block][slot] (allocated by
 // wc_debug_set, the only place this library allocates); other bits are kernel-specific experiment switches.
-constexpr int WC_DBG_BLOCKS = 160, WC_DBG_SLOTS = 8;
+constexpr int WC_DBG_BLOCKS = 160, WC_DBG_SLOTS = 32;   // slots 0-7: streaming kernels, 8-15: chain kernel stages, 16-31: inside its last tile
 int wc_debug_flags();
 unsigned long long* wc_debug_buf();     // nullptr unless bit0 is set
 __device__ __forceinline__ void wc_mark(unsigned long long* buf, int slot) {
@@ -62,6 +62,11 @@ __device__ __forceinline__ void wc_mark(unsigned long long* buf, int slot) {
 // Default WC_L2_DEFAULT; the environment variable WC_B200_L2 (read once) overrides it for A/B measurements.
 constexpr int WC_L2_DEFAULT = 0;
 int wc_l2_mode();
+
+// cheap SM-local cycle stamp (globaltimer reads cost hundreds of ns each and perturb what they measure)
+__device__ __forceinline__ void wc_mark_clk(unsigned long long* buf, int slot) {
+  if (buf && blockIdx.x < WC_DBG_BLOCKS) buf[blockIdx.x * WC_DBG_SLOTS + slot] = (unsigned long long)clock64();
+}
 
 static inline bool wc_aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 static inline size_t wc_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -118,6 +123,17 @@ int wc_factor_bwd_impl(const float* dWeff, const float* gbar, const float* Weff,
                        const float* U, const float* lam, const float* count_dev, double count_host, int C, int g,
                        float eps, int decomposition, int renorm, float* A, float* cvec, float* workspace,
                        size_t workspace_bytes, void* Tp_bwd, int pack_K, cudaStream_t st);
+
+int wc_reduce_bwd_impl(const float* x, const float* dy, int N, int HW, int Cin, int Cout, const float* mean, const int32_t* cls,
+                       int K, float* P, float* s, float* workspace, size_t workspace_bytes, int zero_tail_floats,
+                       cudaStream_t stream);
+
+// K5a + K5b as one persistent multi-stage launch (wc_small.cu); WC_E_UNSUPPORTED: use the per-product launches
+int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float* Wk, int Cin, int Cout, int g, int K,
+                 float* dWu, float* dbu, float* dWc, float* dbc, int triangular, const float* class_matrix, const float* ehat,
+                 const float* D, int E, float* dD, float* dclass_matrix, float* dbf, float* red, float* A, float* cvec,
+                 const float* count_dev, double count_host, float eps, void* Tp_bwd, int pack_K, float* ws_color,
+                 float* ws_factor, unsigned* barrier, int stage_lo, int stage_hi, cudaStream_t st);
 
 // peer-memory exchanges (wc_exchange.cu)
 int wc_stats_exchange(float* rec, float count_local, int C, int g, void* const* peers, void* state, int rank, int world, float eps,

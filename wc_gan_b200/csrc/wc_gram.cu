@@ -446,6 +446,14 @@ extern "C" size_t wc_reduce_workspace_bytes(int N, int HW, int Cin, int Cout, in
 extern "C" int wc_reduce_bwd(const float* x, const float* dy, int N, int HW, int Cin, int Cout,
                              const float* mean, const int32_t* cls, int K,
                              float* P, float* s, float* workspace, size_t workspace_bytes, wc_stream_t stream) {
+  return wc_reduce_bwd_impl(x, dy, N, HW, Cin, Cout, mean, cls, K, P, s, workspace, workspace_bytes, 0, (cudaStream_t)stream);
+}
+
+// zero_tail_floats: floats after s (P | s | tail contiguous) that the accumulator memset also clears (the grid-barrier
+// counter of the chain launch that consumes P and s)
+int wc_reduce_bwd_impl(const float* x, const float* dy, int N, int HW, int Cin, int Cout, const float* mean, const int32_t* cls,
+                       int K, float* P, float* s, float* workspace, size_t workspace_bytes, int zero_tail_floats,
+                       cudaStream_t stream) {
   if (!x || !dy || !P || !s || N <= 0 || HW <= 0 || Cin <= 0 || Cout <= 0 || K <= 0) return WC_E_ARG;
   if ((int64_t)N * HW > (int64_t)INT32_MAX) return WC_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
@@ -461,8 +469,9 @@ extern "C" int wc_reduce_bwd(const float* x, const float* dy, int N, int HW, int
     WC_CHECK_LAUNCH();
   }
   if (s == P + (size_t)K * Cin * Cout) {   // P | s contiguous (wc_layer_bwd's workspace): one memset
-    WC_CUDA(cudaMemsetAsync(P, 0, ((size_t)K * Cin * Cout + (size_t)K * Cout) * 4, st));
+    WC_CUDA(cudaMemsetAsync(P, 0, ((size_t)K * Cin * Cout + (size_t)K * Cout + (size_t)zero_tail_floats) * 4, st));
   } else {
+    if (zero_tail_floats) return WC_E_ARG;
     WC_CUDA(cudaMemsetAsync(P, 0, (size_t)K * Cin * Cout * 4, st));
     WC_CUDA(cudaMemsetAsync(s, 0, (size_t)K * Cout * 4, st));
   }

@@ -8,6 +8,7 @@
 namespace {
 
 constexpr size_t NONE = (size_t)-1;
+constexpr int CHAIN_TAIL = 4;      // floats after P | s zeroed together with them (u32 grid-barrier counter of the chain)
 
 struct Carver {
   size_t off = 0;
@@ -82,7 +83,8 @@ FwdWs fwd_ws(const WcLayerCall& c) {
 struct BwdWs { size_t Ps, reduce, reduce_bytes, color, color_bytes, factor, factor_bytes, total; };
 BwdWs bwd_ws(const WcLayerCall& c) {
   Carver cv; BwdWs w{};
-  w.Ps = cv.take(((size_t)c.K * c.Cin * c.Cout + (size_t)c.K * c.Cout) * sizeof(float));   // P | s contiguous: one memset
+  // P | s | grid-barrier counter of the chain launch, contiguous: one memset
+  w.Ps = cv.take(((size_t)c.K * c.Cin * c.Cout + (size_t)c.K * c.Cout + CHAIN_TAIL) * sizeof(float));
   w.reduce_bytes = wc_reduce_workspace_bytes(c.N, c.HW, c.Cin, c.Cout, c.K); w.reduce = cv.take(w.reduce_bytes);
   w.color_bytes = wc_color_bwd_workspace_bytes(c.Cin, c.Cout, c.g > 0 ? c.g : c.Cin, c.K, c.E); w.color = cv.take(w.color_bytes);
   if (c.whiten && c.training) { w.factor_bytes = wc_factor_bwd_workspace_bytes(c.Cin, c.g, c.decomposition, c.renorm); w.factor = cv.take(w.factor_bytes); }
@@ -201,30 +203,56 @@ extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
   float* P = at<float>(c.workspace, W.Ps);
   float* s = P + (size_t)c.K * c.Cin * c.Cout;
 
+  // Cholesky whitening without renorm on tile-aligned shapes: K5a + K5b run as ONE persistent launch (wc_bwd_chain);
+  // with the adjoint exchanged between ranks, as two (stage 0 | exchange | stages 1-3)
+  unsigned* barrier = reinterpret_cast<unsigned*>(s + (size_t)c.K * c.Cout);
+  const bool chain_ok = stats_grad && c.decomposition == WC_DECOMP_CHOLESKY && !c.renorm && c.Cin == c.Cout &&
+                        (g % 32) == 0 && !(c.triangular && c.dWc) && !(wc_debug_flags() & 262144);
+  const float* Wk = plain_u(c) ? c.Wu : at<float>(c.saved, L.Wk);
+  float *A = stats_grad ? at<float>(c.saved, L.A) : nullptr, *cvec = stats_grad ? at<float>(c.saved, L.cvec) : nullptr;
+  const float* count_dev = c.count_dev;
+  const bool xb = stats_grad && xchg_bwd(c);
+  if (xb) count_dev = at<float>(c.saved, L.rec_count);       // global row count, left there by the forward exchange
+  auto chain = [&](int lo, int hi) {
+    return wc_bwd_chain(P, s, at<float>(c.saved, L.Weff), Wk, c.Cin, c.Cout, g, c.K, c.dWu, c.dbu, c.dWc, c.dbc, c.triangular,
+                        c.class_matrix, at<float>(c.saved, L.ehat), c.D, c.E, c.dD, c.dclass_matrix, c.dbf, c.red, A, cvec,
+                        count_dev, c.count, c.eps, at<void>(c.saved, L.Tp_bwd), c.K, at<float>(c.workspace, W.color),
+                        at<float>(c.workspace, W.factor), barrier, lo, hi, (cudaStream_t)stream);
+  };
+  bool chained = false, all_done = false;
   if (c.phases & WC_PHASE_REDUCE) {
-    rc = wc_reduce_bwd(c.x, c.dy, c.N, c.HW, c.Cin, c.Cout, mean, cls, c.K, P, s, at<float>(c.workspace, W.reduce),
-                       W.reduce_bytes, stream);
+    rc = wc_reduce_bwd_impl(c.x, c.dy, c.N, c.HW, c.Cin, c.Cout, mean, cls, c.K, P, s, at<float>(c.workspace, W.reduce),
+                            W.reduce_bytes, CHAIN_TAIL, (cudaStream_t)stream);
     if (rc) return rc;
-    rc = wc_color_bwd(P, s, at<float>(c.saved, L.Weff), plain_u(c) ? c.Wu : at<float>(c.saved, L.Wk), c.Cin, c.Cout, g, c.K, c.dWu, c.dbu, c.dWc,
-                      c.dbc, c.triangular, c.class_matrix, at<float>(c.saved, L.ehat), c.D, c.E, c.dD, c.dclass_matrix, c.dbf,
-                      stats_grad ? c.red : nullptr, stats_grad ? c.red + gg : nullptr, at<float>(c.workspace, W.color),
-                      W.color_bytes, stream);
-    if (rc) return rc;
+    if (chain_ok) {
+      const bool whole = (c.phases & WC_PHASE_DX) && c.dx && !xb;
+      rc = chain(0, whole ? 4 : 1);
+      if (rc == 0) chained = true;
+      else if (rc != WC_E_UNSUPPORTED) return rc;
+      all_done = chained && whole;
+    }
+    if (!chained) {
+      rc = wc_color_bwd(P, s, at<float>(c.saved, L.Weff), Wk, c.Cin, c.Cout, g, c.K, c.dWu, c.dbu, c.dWc,
+                        c.dbc, c.triangular, c.class_matrix, at<float>(c.saved, L.ehat), c.D, c.E, c.dD, c.dclass_matrix, c.dbf,
+                        stats_grad ? c.red : nullptr, stats_grad ? c.red + gg : nullptr, at<float>(c.workspace, W.color),
+                        W.color_bytes, stream);
+      if (rc) return rc;
+    }
   }
   if (!(c.phases & WC_PHASE_DX) || !c.dx) return 0;
-  float *A = nullptr, *cvec = nullptr;
-  const float* count_dev = c.count_dev;
-  if (stats_grad && xchg_bwd(c)) {
+  if (xb && !all_done) {
     rc = wc_adjoint_exchange(c.red, c.Cin, g, c.xchg_peers, c.xchg_state, c.xchg_rank, c.xchg_world, c.info, (cudaStream_t)stream);
     if (rc) return rc;
-    count_dev = at<float>(c.saved, L.rec_count);       // global row count, left there by the forward exchange
   }
-  if (stats_grad) {
-    A = at<float>(c.saved, L.A); cvec = at<float>(c.saved, L.cvec);
-    rc = wc_factor_bwd_impl(c.red, c.red + gg, at<float>(c.saved, L.Weff), at<float>(c.saved, L.Wm), at<float>(c.saved, L.R),
-                            at<float>(c.saved, L.U), at<float>(c.saved, L.lam), count_dev, c.count, c.Cin, g, c.eps,
-                            c.decomposition, c.renorm, A, cvec, at<float>(c.workspace, W.factor), W.factor_bytes,
-                            at<void>(c.saved, L.Tp_bwd), c.K, (cudaStream_t)stream);
+  if (stats_grad && !all_done) {
+    rc = WC_E_UNSUPPORTED;
+    // (the barrier counter is still zero here: a one-stage launch never touches it)
+    if (chain_ok && (chained || !(c.phases & WC_PHASE_REDUCE))) rc = chain(1, 4);
+    if (rc == WC_E_UNSUPPORTED)
+      rc = wc_factor_bwd_impl(c.red, c.red + gg, at<float>(c.saved, L.Weff), at<float>(c.saved, L.Wm), at<float>(c.saved, L.R),
+                              at<float>(c.saved, L.U), at<float>(c.saved, L.lam), count_dev, c.count, c.Cin, g, c.eps,
+                              c.decomposition, c.renorm, A, cvec, at<float>(c.workspace, W.factor), W.factor_bytes,
+                              at<void>(c.saved, L.Tp_bwd), c.K, (cudaStream_t)stream);
     if (rc) return rc;
   }
   void* Tp = at<void>(c.saved, L.Tp_bwd);

@@ -7,6 +7,8 @@
 #include "wc_common.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <stddef.h>
+#include <algorithm>
 
 // =============================================================================================
 // generic batched small matmul
@@ -291,6 +293,372 @@ __global__ void __launch_bounds__(SMM_THREADS) smm_multi_kernel(const __grid_con
   } else {
     if (jb.bk) smm_tile<false, true>(jb.p, jb.ex, jb.ep, bx, by, z, smm_sm); else smm_tile<false, false>(jb.p, jb.ex, jb.ep, bx, by, z, smm_sm);
   }
+}
+
+// =============================================================================================
+// "chain": the serial small-matrix stages of one direction as ONE persistent launch
+// =============================================================================================
+// The backward pass between K4 and K6 is a chain of four dependent C x C products (dWm -> Psi -> Y -> A) plus the
+// parameter gradients that hang off its first link.  As separate launches each link costs a kernel boundary (drain,
+// launch, cold instruction cache, first touch of the operands) of 6-10 us for ~1 us of arithmetic.  Here the whole chain
+// is one grid of <= 148 co-resident CTAs that walks a small "program": stage by stage, every CTA takes the tile / vector /
+// elementwise jobs of the stage round-robin, and the stages are separated by a grid-wide barrier (one release-add and an
+// acquire-spin on a counter in L2, ~1 us) instead of a kernel boundary.  The tile code is ONE runtime-layout routine, so
+// it is fetched once and stays in the instruction cache for all stages.  Jobs that are off the critical path (Q_k and
+// everything derived from it) ride in the CTAs the critical products leave idle.
+//
+// Co-residency: grid <= number of SMs, one CTA fits on every SM, and nothing a chain CTA waits for depends on a kernel
+// launched after it (the dependent launch is triggered only once every CTA of this grid is running).
+enum { CJ_SMM = 0, CJ_VEC = 1, CJ_SUMK = 2, CJ_COPY = 3, CJ_WSUMK = 4, CJ_DOT = 5, CJ_L2N = 6 };
+constexpr int CH_MAXSMM = 5, CH_MAXVEC = 3, CH_MAXELT = 7, CH_MAXSTAGE = 6, CH_ELT_CHUNK = 2048;
+struct EltJob {
+  const float* a; const float* b; float* out;
+  long long n;                 // elements per slice
+  int K, E;
+  const float* cm; const float* ehat;
+};
+struct ChainEnt { short type, idx, stage, pad; int v0, n; };
+// one tiled product of the chain, everything the tile routine needs in 32-bit form (all strides in elements)
+struct TJob {
+  const float* A; const float* B; float* C;
+  uint8_t* pk0; uint8_t* pk1;      // EPI_PACK images (see SmmEpi)
+  int lda, ldb;                    // leading dimension along the non-contiguous index of the operand
+  int rsC, csC;
+  int bA1, bA2, bB1, bB2, bC1, bC2;
+  int sA, sB;                      // stride of the extra summed dimension
+  int K, nsum, nb2, gx, gy;
+  int pk_slot_stride, pkC, row_per_b2;
+  short ak, bk, epi, count_mode, tri, pad;
+  float alpha;
+};
+struct ChainProgram {
+  TJob smm[CH_MAXSMM]; VecJob vec[CH_MAXVEC]; EltJob elt[CH_MAXELT];
+  ChainEnt ent[CH_MAXSMM + CH_MAXVEC + CH_MAXELT];
+  int nent, nstages;
+  const float* count_dev; float count_host;       // rows of the global batch (count_dev[0] when non-NULL)
+  int stage_total[CH_MAXSTAGE];      // virtual CTAs of each stage
+  unsigned* barrier;                 // one counter, zero on entry (the caller's memset of the accumulators covers it)
+  unsigned long long* dbg;           // debug marks (nullptr in normal use)
+  int dbg_flags;                     // experiment switches (0 in normal use)
+};
+static_assert(sizeof(ChainProgram) <= 4000, "kernel parameter space");
+static_assert(sizeof(TJob) % 4 == 0 && offsetof(ChainProgram, smm) % 4 == 0, "word copy of a job");
+// the same bytes as plain words, so that a thread can touch an arbitrary line of the parameter block
+union ChainParams { ChainProgram pr; int words[(sizeof(ChainProgram) + 3) / 4]; };
+
+// ---- tensor-core tile: C(32 x 32) = alpha * sum_q A_q(32 x K) B_q(K x 32) on mma.sync, "3xTF32" ----------------------------
+// Each operand chunk (32 x 64) is copied in its NATIVE layout with fully coalesced 16-byte cp.async.cg (L2 only: operands
+// may have been written by another SM earlier in the same launch) into a 4-stage ring: for K <= 256 the whole panel is in
+// flight at once (one L2 round trip, ~1 us measured, instead of one per chunk), and the extra summed dimension of
+// dWeff = sum_k W_k P_k^T streams through the ring.  Either operand orientation is then just a pair of shared-memory
+// strides for the m16n8k8 fragment loads (pitch 68 when k is the contiguous index, 40 when it is not: both
+// conflict-free).  fp32 accuracy: x = hi + lo with hi, lo TF32 (21+ mantissa bits); lo.hi, hi.lo and hi.hi are
+// accumulated in separate fp32 accumulators (short dependency chains) and summed at the end; the dropped lo.lo term is
+// 2^-22 relative.  16 warps: 4 warp tiles of m16 x n16, times four quarters of every k chunk, summed through shared memory.
+constexpr int MT_NS = 4, MT_KC = 64, MT_OPF = 64 * 40, MT_STAGEF = 2 * MT_OPF;     // floats per operand / stage buffer
+constexpr int MT_PK = MT_KC + 4, MT_PM = 40;                                       // pitches: k contiguous / mn contiguous
+constexpr int MT_REDF = 3 * 4 * 32 * 8;
+constexpr int CHAIN_SMEM = (MT_NS * MT_STAGEF + MT_REDF + 32 * 33) * 4;
+static_assert(32 * MT_PK <= MT_OPF && MT_KC * MT_PM <= MT_OPF, "operand buffer");
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// x = hi + lo (+ at most 2^-21 |x|): hi keeps the top 11 significand bits (truncation: one mask), the remainder
+// x - hi is exact in fp32 and is truncated to TF32 the same way.  3 instructions per element instead of the ~9 of two
+// round-to-nearest cvt.rna.tf32 (the splits, not the MMAs, were what bound the tile).
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __noinline__ void smm_tile_rt(const TJob& jb, int bx, int by, int z, float* smm_sm, int dflags, unsigned long long* dbg, float cnt) {
+  if (threadIdx.x == 0) wc_mark_clk(dbg, 16);
+  if (jb.epi == EPI_PSI && by < bx) return;                // block-uniform
+  const bool ak = jb.ak != 0, bk = jb.bk != 0;             // k is the contiguous index of the operand in memory
+  const int b1 = z / jb.nb2, b2 = z - b1 * jb.nb2;
+  const int i0 = by * SMM_T, j0 = bx * SMM_T;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int kq = warp >> 2, wt = warp & 3;                  // quarter of the k chunk, warp tile
+  const int m0 = (wt & 1) * 16, n0 = (wt >> 1) * 16;
+  const int gq = lane >> 2, tq = lane & 3;
+  // loader: every thread copies one 16-byte piece of the A chunk and one of the B chunk
+  const int r16 = t >> 4, c16 = 4 * (t & 15), r8 = t >> 3, c8 = 4 * (t & 7);
+  const float* ga = jb.A + (b1 * jb.bA1 + b2 * jb.bA2 + (ak ? (i0 + r16) * jb.lda + c16 : r8 * jb.lda + i0 + c8));
+  const float* gb = jb.B + (b1 * jb.bB1 + b2 * jb.bB2 + (bk ? (j0 + r16) * jb.ldb + c16 : r8 * jb.ldb + j0 + c8));
+  const int ka = ak ? MT_KC : MT_KC * jb.lda, kb = bk ? MT_KC : MT_KC * jb.ldb;     // global stride of one k chunk
+  const int sa = ak ? r16 * MT_PK + c16 : r8 * MT_PM + c8;
+  const int sb = MT_OPF + (bk ? r16 * MT_PK + c16 : r8 * MT_PM + c8);
+  const int kta = ak ? c16 : r8, ktb = bk ? c16 : r8;      // k index (in the chunk) of this thread's pieces
+  const int K = jb.K, nkc = (K + MT_KC - 1) / MT_KC, nchunks = jb.nsum * nkc;
+  int iq = 0, ic = 0;                                       // (summed index, k chunk) of the next chunk to issue
+  auto issue = [&](int c) {
+    const int kval = K - ic * MT_KC;      // K is a multiple of 32: the last chunk may be half empty (zero-filled)
+    float* st = smm_sm + (c % MT_NS) * MT_STAGEF;
+    if (kta < kval) cp_async16(st + sa, ga + (iq * jb.sA + ic * ka));
+    else *reinterpret_cast<float4*>(st + sa) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ktb < kval) cp_async16(st + sb, gb + (iq * jb.sB + ic * kb));
+    else *reinterpret_cast<float4*>(st + sb) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (++ic == nkc) { ic = 0; ++iq; }
+  };
+  // fragment addressing: element (mn, k) of an operand chunk at mn * s_mn + k * s_k
+  const int a_smn = ak ? MT_PK : 1, a_sk = ak ? 1 : MT_PM, b_smn = bk ? MT_PK : 1, b_sk = bk ? 1 : MT_PM;
+  const int a_off = (m0 + gq) * a_smn + tq * a_sk, b_off = MT_OPF + (n0 + gq) * b_smn + tq * b_sk;
+  float acc[2][3][4];
+#pragma unroll
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[n][q][e] = 0.f;
+#pragma unroll
+  for (int c = 0; c < MT_NS - 1; ++c) { if (c < nchunks) issue(c); cp_async_commit(); }
+  if (threadIdx.x == 0) wc_mark_clk(dbg, 17);
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<MT_NS - 2>();
+    __syncthreads();                      // chunk c has landed for every thread; everyone is done with chunk c-1
+    if (threadIdx.x == 0 && c < 8) wc_mark_clk(dbg, 18 + c);
+    if (c + MT_NS - 1 < nchunks) issue(c + MT_NS - 1);
+    cp_async_commit();
+    if (dflags & 1048576) continue;
+    const float* st = smm_sm + (c % MT_NS) * MT_STAGEF;
+#pragma unroll
+    for (int ks = 0; ks < MT_KC / 32; ++ks) {
+      const int kk = (kq * (MT_KC / 32) + ks) * 8;
+      const float* ap = st + a_off + kk * a_sk;
+      const float* bp = st + b_off + kk * b_sk;
+      uint32_t ah[4], al[4], bh[2][2], bl[2][2];
+      tf32_split(ap[0], ah[0], al[0]);
+      tf32_split(ap[8 * a_smn], ah[1], al[1]);
+      tf32_split(ap[4 * a_sk], ah[2], al[2]);
+      tf32_split(ap[8 * a_smn + 4 * a_sk], ah[3], al[3]);
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        tf32_split(bp[8 * n * b_smn], bh[n][0], bl[n][0]);
+        tf32_split(bp[8 * n * b_smn + 4 * b_sk], bh[n][1], bl[n][1]);
+      }
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        mma_tf32(acc[n][0], al, bh[n]);
+        mma_tf32(acc[n][1], ah, bl[n]);
+        mma_tf32(acc[n][2], ah, bh[n]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();                        // the ring is free: reduction scratch and the output tile live behind it
+  if (threadIdx.x == 0) wc_mark_clk(dbg, 26);
+  float* red = smm_sm + MT_NS * MT_STAGEF;          // [3 k quarters][4 warp tiles][32 lanes][8]
+  float* tile = red + MT_REDF;                      // [32][33]
+  float v8[8];
+#pragma unroll
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v8[n * 4 + e] = (acc[n][0][e] + acc[n][1][e]) + acc[n][2][e];
+  if (kq > 0) {
+    float* r = red + (((kq - 1) * 4 + wt) * 32 + lane) * 8;
+    *reinterpret_cast<float4*>(r) = make_float4(v8[0], v8[1], v8[2], v8[3]);
+    *reinterpret_cast<float4*>(r + 4) = make_float4(v8[4], v8[5], v8[6], v8[7]);
+  }
+  __syncthreads();
+  if (kq == 0) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const float* r = red + ((q * 4 + wt) * 32 + lane) * 8;
+      const float4 o0 = *reinterpret_cast<const float4*>(r), o1 = *reinterpret_cast<const float4*>(r + 4);
+      v8[0] += o0.x; v8[1] += o0.y; v8[2] += o0.z; v8[3] += o0.w; v8[4] += o1.x; v8[5] += o1.y; v8[6] += o1.z; v8[7] += o1.w;
+    }
+    float alpha = jb.alpha;
+    if (jb.count_mode) alpha = __fdividef(alpha, jb.count_mode == 1 ? cnt : (cnt - 1.f));
+    float* C = jb.C + (b1 * jb.bC1 + b2 * jb.bC2);
+    const int rsC = jb.rsC, csC = jb.csC, tri = jb.tri;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int li = m0 + gq + ((e >> 1) & 1) * 8, lj = n0 + (e >> 2) * 8 + 2 * tq + (e & 1);
+      const int i = i0 + li, j = j0 + lj;
+      if (jb.epi == EPI_PSI) {
+        if (j > i) continue;
+        const float v = -alpha * v8[e];
+        C[i * rsC + j * csC] = v;
+        if (j < i) C[j * rsC + i * csC] = v;
+      } else {
+        float v = alpha * v8[e];
+        if ((tri == 1 && j > i) || (tri == 2 && j < i)) v = 0.f;
+        C[i * rsC + j * csC] = v;
+        if (jb.epi == EPI_PACK) tile[li * 33 + lj] = v;
+      }
+    }
+  }
+  if (threadIdx.x == 0) wc_mark_clk(dbg, 27);
+  if (jb.epi != EPI_PACK) return;
+  __syncthreads();
+  if (t >= 128) return;
+  // the tile also leaves as bf16 hi/lo operand images of the tcgen05 apply kernels (see SmmEpi)
+  const int lane32 = t & 31, ch = t >> 5;
+  const int gi0 = b2 * jb.row_per_b2 + i0;
+  const long long b_img = (long long)jb.pkC * 64;
+  uint32_t hi[4], lo[4];
+  if (jb.pk0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) smm_split2(tile[(8 * ch + 2 * q) * 33 + lane32], tile[(8 * ch + 2 * q + 1) * 33 + lane32], hi[q], lo[q]);
+    uint8_t* dst = jb.pk0 + (long long)b1 * jb.pk_slot_stride + (long long)(gi0 >> 5) * (2 * b_img) + smm_kmajor32_off(j0 + lane32, ch);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst + b_img) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  if (jb.pk1) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) smm_split2(tile[lane32 * 33 + 8 * ch + 2 * q], tile[lane32 * 33 + 8 * ch + 2 * q + 1], hi[q], lo[q]);
+    uint8_t* dst = jb.pk1 + (long long)b1 * jb.pk_slot_stride + (long long)(j0 >> 5) * (2 * b_img) + smm_kmajor32_off(gi0 + lane32, ch);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst + b_img) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// elementwise / reduction jobs of the parameter gradients (one virtual CTA each)
+__device__ __forceinline__ void elt_job_run(int type, const EltJob& j, int cta, float* sm) {
+  const int t = threadIdx.x;
+  if (type == CJ_SUMK || type == CJ_COPY) {
+    // out[i] = sum_k a[k n + i]   (COPY: K == 1)
+    const long long i = (long long)cta * CH_ELT_CHUNK + 4 * t;
+    if (i + 3 < j.n) {
+      float4 acc = __ldcg(reinterpret_cast<const float4*>(j.a + i));
+      for (int k = 1; k < j.K; ++k) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(j.a + (long long)k * j.n + i));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(j.out + i) = acc;
+    } else {
+      for (long long q = i; q < j.n; ++q) {
+        float acc = 0.f;
+        for (int k = 0; k < j.K; ++k) acc += __ldcg(j.a + (long long)k * j.n + q);
+        j.out[q] = acc;
+      }
+    }
+  } else if (type == CJ_WSUMK) {
+    // out[e n + i] = sum_k ehat[k E + e] a[k n + i]          (dD, conditional_layers.py:996-1001 transposed)
+    const int nchunk = (int)((j.n + CH_ELT_CHUNK - 1) / CH_ELT_CHUNK);
+    const int e = cta / nchunk;
+    const long long i = (long long)(cta % nchunk) * CH_ELT_CHUNK + 4 * t;
+    if (i + 3 < j.n) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < j.K; ++k) {
+        const float w = j.ehat[k * j.E + e];
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(j.a + (long long)k * j.n + i));
+        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+      }
+      *reinterpret_cast<float4*>(j.out + (long long)e * j.n + i) = acc;
+    } else {
+      for (long long q = i; q < j.n; ++q) {
+        float acc = 0.f;
+        for (int k = 0; k < j.K; ++k) acc = fmaf(j.ehat[k * j.E + e], __ldcg(j.a + (long long)k * j.n + q), acc);
+        j.out[(long long)e * j.n + q] = acc;
+      }
+    }
+  } else if (type == CJ_DOT) {
+    // out[k E + e] = <a_k, b_e>
+    const int k = cta / j.E, e = cta % j.E;
+    const float* q = j.a + (long long)k * j.n;
+    const float* d = j.b + (long long)e * j.n;
+    float s = 0.f;
+    if ((j.n & 3) == 0) {
+      for (long long i = 4 * t; i < j.n; i += 4 * SMM_THREADS) {
+        const float4 x = __ldcg(reinterpret_cast<const float4*>(q + i)), y = __ldg(reinterpret_cast<const float4*>(d + i));
+        s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+      }
+    } else {
+      for (long long i = t; i < j.n; i += SMM_THREADS) s = fmaf(__ldcg(q + i), d[i], s);
+    }
+    s = wc_warp_sum(s);
+    if ((t & 31) == 0) sm[t >> 5] = s;
+    __syncthreads();
+    if (t == 0) {
+      float a = 0.f;
+      for (int w = 0; w < SMM_THREADS / 32; ++w) a += sm[w];
+      j.out[cta] = a;
+    }
+  } else if (type == CJ_L2N) {
+    // backward of tf.nn.l2_normalize (conditional_layers.py:994); a = de (K,E)
+    for (int k = t; k < j.K; k += SMM_THREADS) {
+      float sq = 0.f, dot = 0.f;
+      for (int e = 0; e < j.E; ++e) { const float v = j.cm[k * j.E + e]; sq = fmaf(v, v, sq); dot = fmaf(__ldcg(j.a + k * j.E + e), j.ehat[k * j.E + e], dot); }
+      const float rho = rsqrtf(fmaxf(sq, 1e-12f));
+      const bool clamped = !(sq > 1e-12f);
+      for (int e = 0; e < j.E; ++e) {
+        const float de = __ldcg(j.a + k * j.E + e);
+        j.out[k * j.E + e] = clamped ? rho * de : rho * (de - j.ehat[k * j.E + e] * dot);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void chain_grid_barrier(unsigned* ctr, unsigned target) {
+  __syncthreads();     // orders every thread's stores of this stage before thread 0's release
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    unsigned v;
+    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (v < target);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(SMM_THREADS, 1) chain_kernel(const __grid_constant__ ChainParams kp) {
+  const ChainProgram& pr = kp.pr;
+  extern __shared__ __align__(16) float smm_sm[];
+  __shared__ float s_cnt[1];
+  __shared__ int s_sink;
+  // the tile routine takes its job descriptor from SHARED memory: reading it through a reference into the parameter
+  // block (generic loads from the parameter window, ~700 cycles each, in dependent chains) cost 2800 cycles of set-up and
+  // 2400 of epilogue per tile
+  __shared__ __align__(16) int s_job[(sizeof(TJob) + 3) / 4];
+  // The program (3.3 KB of kernel parameters) is read through the constant cache; cold, every job descriptor costs a
+  // chain of ~300-cycle misses at the start of every stage (measured: 1.5 us per tile).  Touch every line of it once
+  // here, BEFORE the dependency wait, where it overlaps the predecessor's tail.
+  if (threadIdx.x < (int)(sizeof(ChainProgram) / 64)) {
+    const int v = kp.words[threadIdx.x * 16];
+    if (v == 0x7fffffff) s_sink = v;       // never true for a pointer / count word in practice; keeps the load alive
+  }
+  wc_pdl_wait();
+  if (threadIdx.x == 0) s_cnt[0] = pr.count_dev ? __ldcg(pr.count_dev) : pr.count_host;
+  __syncthreads();
+  if (threadIdx.x == 0) wc_mark(pr.dbg, 8);
+  for (int s = 0; s < pr.nstages; ++s) {
+    if (s > 0) {
+      if (threadIdx.x == 0 && s < 4) wc_mark(pr.dbg, 7 + 2 * s);      // own jobs of stage s-1 done
+      chain_grid_barrier(pr.barrier, (unsigned)s * gridDim.x);
+      if (threadIdx.x == 0 && s < 4) wc_mark(pr.dbg, 8 + 2 * s);      // barrier passed
+    }
+    for (int v = blockIdx.x; v < pr.stage_total[s]; v += gridDim.x) {
+      int e = 0;
+      for (; e < pr.nent; ++e)
+        if (pr.ent[e].stage == s && v >= pr.ent[e].v0 && v < pr.ent[e].v0 + pr.ent[e].n) break;
+      if (e < pr.nent) {
+        const ChainEnt en = pr.ent[e];
+        const int l = v - en.v0;
+        if (en.type == CJ_SMM) {
+          constexpr int JW = (int)(sizeof(TJob) / 4);
+          const int w0 = (int)(offsetof(ChainProgram, smm) / 4) + en.idx * JW;
+          if (threadIdx.x < JW) s_job[threadIdx.x] = kp.words[w0 + threadIdx.x];
+          __syncthreads();
+          const TJob& jb = *reinterpret_cast<const TJob*>(s_job);
+          const int gxy = jb.gx * jb.gy, zz = l / gxy, rem = l - zz * gxy, yy = rem / jb.gx;
+          smm_tile_rt(jb, rem - yy * jb.gx, yy, zz, smm_sm, pr.dbg_flags, pr.dbg, s_cnt[0]);
+        } else if (en.type == CJ_VEC) {
+          vec_job_run(pr.vec[en.idx], l, smm_sm);
+        } else {
+          elt_job_run(en.type, pr.elt[en.idx], l, smm_sm);
+        }
+      }
+      __syncthreads();   // shared memory is reused by the next job of this CTA
+    }
+  }
+  if (threadIdx.x == 0) wc_mark(pr.dbg, 15);
 }
 
 // ---- generic path: any shape, any strides ------------------------------------------------------------------------
@@ -1090,6 +1458,155 @@ int wc_factor_bwd_impl(const float* dWeff, const float* gbar, const float* Weff,
     rc = wc_pack_bwd(nullptr, A, C, g, pack_K, Tp_bwd, (wc_stream_t)st);
     if (rc) return rc;
   }
+  return 0;
+}
+
+// =============================================================================================
+// K5a + K5b as one persistent launch (the "chain"; Cholesky whitening, no renorm, tile-aligned shapes)
+// =============================================================================================
+namespace {
+struct ChainBuilder {
+  ChainProgram pr{};
+  int nsmm = 0, nvec = 0, nelt = 0;
+  bool ok = true;
+  void ent(int type, int idx, int stage, int n) {
+    ChainEnt& e = pr.ent[pr.nent++];
+    e.type = (short)type; e.idx = (short)idx; e.stage = (short)stage; e.pad = 0;
+    e.v0 = pr.stage_total[stage]; e.n = n;
+    pr.stage_total[stage] += n;
+    if (stage + 1 > pr.nstages) pr.nstages = stage + 1;
+  }
+  void smm(int stage, const WcSmm& p, const SmmEpi& ep = SmmEpi{}, int count_mode = 0) {
+    if (nsmm >= CH_MAXSMM || !smm_is_fast(p) || p.beta != 0.f || (p.K % 32)) { ok = false; return; }
+    if (ep.kind == EPI_PACK && (ep.pkC % 32 || (ep.pk0 && !wc_aligned16(ep.pk0)) || (ep.pk1 && !wc_aligned16(ep.pk1)))) { ok = false; return; }
+    const long long lim = 1ll << 30;
+    for (long long v : {p.rsA, p.csA, p.rsB, p.csB, p.rsC, p.csC, p.bA1, p.bA2, p.bB1, p.bB2, p.bC1, p.bC2, p.sA, p.sB, ep.pk_slot_stride})
+      if (v < 0 || v >= lim) { ok = false; return; }
+    if ((long long)p.nb1 * std::max({p.bA1, p.bB1, p.bC1}) >= lim || (long long)p.nsum * std::max(p.sA, p.sB) >= lim) { ok = false; return; }
+    TJob& j = pr.smm[nsmm];
+    j.A = p.A; j.B = p.B; j.C = p.C; j.pk0 = ep.pk0; j.pk1 = ep.pk1;
+    j.ak = p.csA == 1; j.bk = p.rsB == 1;
+    j.lda = (int)(j.ak ? p.rsA : p.csA); j.ldb = (int)(j.bk ? p.csB : p.rsB);
+    j.rsC = (int)p.rsC; j.csC = (int)p.csC;
+    j.bA1 = (int)p.bA1; j.bA2 = (int)p.bA2; j.bB1 = (int)p.bB1; j.bB2 = (int)p.bB2; j.bC1 = (int)p.bC1; j.bC2 = (int)p.bC2;
+    j.sA = (int)p.sA; j.sB = (int)p.sB;
+    j.K = p.K; j.nsum = p.nsum; j.nb2 = p.nb2; j.gx = p.N / SMM_T; j.gy = p.M / SMM_T;
+    j.pk_slot_stride = (int)ep.pk_slot_stride; j.pkC = ep.pkC; j.row_per_b2 = ep.row_per_b2;
+    j.epi = (short)ep.kind; j.count_mode = (short)count_mode; j.tri = (short)p.tri; j.pad = 0;
+    j.alpha = p.alpha;
+    ent(CJ_SMM, nsmm++, stage, j.gx * j.gy * p.nb1 * p.nb2);
+  }
+  void vec(int stage, const VecJob& v0) {
+    if (nvec >= CH_MAXVEC || v0.M <= 0 || v0.nb <= 0) { ok = false; return; }
+    VecJob& v = pr.vec[nvec];
+    v = v0; v.cta0 = 0; v.nctas = ((v.M + 31) / 32) * v.nb;
+    ent(CJ_VEC, nvec++, stage, v.nctas);
+  }
+  void elt(int stage, int type, const EltJob& j, int nctas) {
+    if (nelt >= CH_MAXELT) { ok = false; return; }
+    pr.elt[nelt] = j;
+    ent(type, nelt++, stage, nctas);
+  }
+  int launch(unsigned* barrier, cudaStream_t st) {
+    if (!ok) return WC_E_UNSUPPORTED;
+    int mx = 1;
+    for (int s2 = 0; s2 < pr.nstages; ++s2) mx = std::max(mx, pr.stage_total[s2]);
+    pr.barrier = barrier; pr.dbg = wc_debug_buf(); pr.dbg_flags = wc_debug_flags();
+    static bool attr_set = false;
+    if (!attr_set) {
+      WC_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
+      attr_set = true;
+    }
+    ChainParams kp; kp.pr = pr;
+    WC_CUDA(wc_launch(chain_kernel, std::min(mx, WC_NUM_SMS), SMM_THREADS, CHAIN_SMEM, st, kp));
+    WC_CHECK_LAUNCH();
+    return 0;
+  }
+};
+inline int elt_chunks(long long n) { return (int)((n + CH_ELT_CHUNK - 1) / CH_ELT_CHUNK); }
+}  // namespace
+
+// Stages [stage_lo, stage_hi) of the backward chain:
+//   0: Q_k = Weff P_k, dWeff = sum_k W_k P_k^T, gbar = sum_k W_k s_k, dbu = sum_k s_k, dbc = dbf = s
+//   1: Psi from Z = dWeff Wm^T, cvec = Weff^T gbar / count, dWu = sum_k Q_k, dD = ehat^T Q, de = <Q_k, D_e>
+//   2: Y^T = (Psi Wm)^T, dclass_matrix = l2_normalize'(de)
+//   3: A = (1-eps)/(count-1) Wm^T Y  (+ its bf16 operand image for K6)
+// A synchronised-batch layer runs [0,1), all-reduces red = {dWeff, gbar}, then [1,4).  Returns WC_E_UNSUPPORTED when a
+// shape does not fit the tile routine (the caller then takes the launch-per-product path).  `barrier`: one zeroed u32.
+int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float* Wk, int Cin, int Cout, int g, int K,
+                 float* dWu, float* dbu, float* dWc, float* dbc, int triangular, const float* class_matrix, const float* ehat,
+                 const float* D, int E, float* dD, float* dclass_matrix, float* dbf, float* red, float* A, float* cvec,
+                 const float* count_dev, double count_host, float eps, void* Tp_bwd, int pack_K, float* ws_color,
+                 float* ws_factor, unsigned* barrier, int stage_lo, int stage_hi, cudaStream_t st) {
+  if (!P || !s || !Weff || !Wk || !red || !barrier || Cin != Cout || g <= 0 || Cin % g) return WC_E_UNSUPPORTED;
+  if (triangular && dWc) return WC_E_UNSUPPORTED;
+  if ((dD || dclass_matrix) && (!class_matrix || !ehat || !D || E <= 0)) return WC_E_ARG;
+  const int C = Cin, G = C / g;
+  const long long per = (long long)C * C;
+  const size_t gb = gg_bytes(C, g);
+  float* Qws = ws_color;
+  float* de = reinterpret_cast<float*>(reinterpret_cast<char*>(ws_color) + wc_align_up((size_t)K * per * 4, 256));
+  float* W0 = ws_factor;
+  float* W1 = reinterpret_cast<float*>(reinterpret_cast<char*>(ws_factor) + gb);
+  float* dWeff = red; float* gbar = red + (size_t)C * g;
+  const float ch = (float)count_host;
+  const bool need_q = dWu || dWc || dD || dclass_matrix;
+  float* Qdst = Qws;
+  if (dWc) Qdst = dWc; else if (K == 1 && dWu) Qdst = dWu;
+  ChainBuilder cb;
+  cb.pr.count_dev = count_dev; cb.pr.count_host = ch;
+  auto in = [&](int stage) { return stage >= stage_lo && stage < stage_hi; };
+  const int base = stage_lo;     // stages are renumbered from 0 inside the launch
+  if (in(0)) {
+    if (need_q) cb.smm(0 - base, smm_blockdiag_left(Weff, false, P, Qdst, g, G, C, C, K, per));
+    WcSmm pw = smm_init();
+    pw.A = Wk; pw.B = P; pw.C = dWeff; pw.M = g; pw.N = g; pw.K = C;
+    pw.rsA = C; pw.csA = 1; pw.rsB = 1; pw.csB = C; pw.rsC = g; pw.csC = 1;
+    pw.nb1 = 1; pw.nb2 = G; pw.bA2 = (long long)g * C; pw.bB2 = (long long)g * C; pw.bC2 = (long long)g * g;
+    pw.nsum = K; pw.sA = per; pw.sB = per;
+    cb.smm(0 - base, pw);
+    VecJob v{};
+    v.A = Wk; v.x = s; v.out = gbar; v.M = C; v.K = C; v.rsA = C; v.csA = 1;
+    v.nsum = K; v.sA = per; v.sx = C; v.nb = 1; v.alpha = 1.f;
+    cb.vec(0 - base, v);
+    if (dbu) {
+      VecJob u{};
+      u.A = s; u.x = nullptr; u.out = dbu; u.M = C; u.K = K; u.rsA = 1; u.csA = C;
+      u.nsum = 1; u.nb = 1; u.alpha = 1.f;
+      cb.vec(0 - base, u);
+    }
+    if (dbc) { EltJob j{}; j.a = s; j.out = dbc; j.n = (long long)K * C; j.K = 1; cb.elt(0 - base, CJ_COPY, j, elt_chunks(j.n)); }
+    if (dbf) { EltJob j{}; j.a = s; j.out = dbf; j.n = (long long)K * C; j.K = 1; cb.elt(0 - base, CJ_COPY, j, elt_chunks(j.n)); }
+  }
+  if (in(1)) {
+    SmmEpi e1{}; e1.kind = EPI_PSI;
+    cb.smm(1 - base, smm_gg(dWeff, false, Weff, true, W0, g, G), e1);
+    VecJob vc{};
+    vc.A = Weff; vc.x = gbar; vc.out = cvec; vc.M = g; vc.K = g; vc.rsA = 1; vc.csA = g;
+    vc.nsum = 1; vc.nb = G; vc.bA = (long long)g * g; vc.bx = g; vc.bo = g;
+    vc.count_dev = count_dev; vc.count_host = ch; vc.count_mode = 1; vc.alpha = 1.f;
+    cb.vec(1 - base, vc);
+    if (dWu && Qdst != dWu) { EltJob j{}; j.a = Qdst; j.out = dWu; j.n = per; j.K = K; cb.elt(1 - base, CJ_SUMK, j, elt_chunks(per)); }
+    if (dD) { EltJob j{}; j.a = Qdst; j.out = dD; j.n = per; j.K = K; j.E = E; j.ehat = ehat; cb.elt(1 - base, CJ_WSUMK, j, E * elt_chunks(per)); }
+    if (dclass_matrix) { EltJob j{}; j.a = Qdst; j.b = D; j.out = de; j.n = per; j.K = K; j.E = E; cb.elt(1 - base, CJ_DOT, j, K * E); }
+  }
+  if (in(2)) {
+    WcSmm py = smm_gg(W0, false, Weff, false, W1, g, G);
+    py.rsC = 1; py.csC = g;                                   // stored transposed: the next product reads row panels
+    cb.smm(2 - base, py);
+    if (dclass_matrix) { EltJob j{}; j.a = de; j.out = dclass_matrix; j.K = K; j.E = E; j.cm = class_matrix; j.ehat = ehat; cb.elt(2 - base, CJ_L2N, j, 1); }
+  }
+  if (in(3)) {
+    WcSmm pa = smm_gg(W1, false, Weff, false, A, g, G);
+    pa.rsC = 1; pa.csC = g;
+    pa.alpha = 1.f - eps;
+    SmmEpi e3{};
+    if (Tp_bwd && g == C) { e3.kind = EPI_PACK; e3.pk1 = (uint8_t*)Tp_bwd + (size_t)pack_K * C * C * 4; e3.pkC = C; }
+    cb.smm(3 - base, pa, e3, 2);
+  }
+  int rc = cb.launch(barrier, st);
+  if (rc) return rc;
+  if (in(3) && Tp_bwd && g != C) return wc_pack_bwd(nullptr, A, C, g, pack_K, Tp_bwd, (wc_stream_t)st);
   return 0;
 }
 

@@ -62,6 +62,39 @@ def test_label_validation(stubbed):
         W.DecorelationNormalization(group_size=3)(x)         # channels not divisible by the group size
 
 
+def test_operand_validation(stubbed):
+    """whitening_coloring() hands raw pointers to the C ABI: every operand's dtype, layout and shape is checked first
+    (a mismatch used to read out of bounds silently)."""
+    from wc_gan_b200.functional import WCSpec, whitening_coloring, MAX_GROUP
+    x = torch.zeros(4, 2, 2, 8)
+    mm, mc = torch.zeros(8, 1), torch.eye(8)
+    spec = WCSpec(number_of_classes=3)
+    ok = dict(spec=spec, training=True, moving_mean=mm, moving_cov=mc, cls=torch.zeros(4, 1, dtype=torch.int32))
+    whitening_coloring(x, Wu=torch.zeros(8, 8), Wc=torch.zeros(3, 8, 8), bc=torch.zeros(3, 8), **ok)
+    with pytest.raises(ValueError):
+        whitening_coloring(x, Wu=torch.zeros(8, 8), Wc=torch.zeros(2, 8, 8), **ok)          # K mismatch
+    with pytest.raises(ValueError):
+        whitening_coloring(x, Wu=torch.zeros(8, 6), Wc=torch.zeros(3, 8, 8), **ok)          # Cout disagrees
+    with pytest.raises(ValueError):
+        whitening_coloring(x, Wc=torch.zeros(3, 8, 8), bc=torch.zeros(3, 4), **ok)          # bias shape
+    with pytest.raises(ValueError):
+        whitening_coloring(x, class_matrix=torch.zeros(3, 2), **ok)                          # dictionary missing
+    with pytest.raises(ValueError):
+        whitening_coloring(x, class_matrix=torch.zeros(2, 2), D=torch.zeros(2, 8, 8), **ok)  # class_matrix rows != K
+    with pytest.raises(TypeError):
+        whitening_coloring(x, Wu=torch.zeros(8, 8, dtype=torch.float64), **ok)
+    with pytest.raises(ValueError):
+        whitening_coloring(x, Wu=torch.zeros(8, 8), spec=spec, training=True, moving_mean=mm, moving_cov=torch.eye(4),
+                           cls=ok['cls'])                                                    # moving_cov size
+    with pytest.raises(ValueError):
+        whitening_coloring(x, Wu=torch.zeros(8, 8), spec=spec, training=True, moving_mean=mm,
+                           moving_cov=torch.eye(16)[::2, ::2], cls=ok['cls'])                # in-place buffer not contiguous
+    big = torch.zeros(1, 1, 2, 2 * MAX_GROUP)
+    with pytest.raises(ValueError, match='group_size'):
+        whitening_coloring(big, spec=WCSpec(), training=True, moving_mean=torch.zeros(2 * MAX_GROUP),
+                           moving_cov=torch.eye(2 * MAX_GROUP))                              # g = C > 256: named limit
+
+
 def test_peer_exchange_is_only_offered_on_cuda(monkeypatch):
     """The peer-memory transport is never chosen for CPU tensors or when WC_B200_SYNC=nccl asks for host collectives;
     neither case touches torch.distributed."""

@@ -107,8 +107,10 @@ int wc_smm_launch(const WcSmm& p, cudaStream_t st);
 
 // K1's finalize kernel can run K2's prep step in the same launch (single-process training, tensor-core path)
 struct WcPrepFuse { float eps, extra_eps, momentum; float* moving_mean; float* moving_cov; float* Ashr; };
+// zeroed_out (nullable): receives the address of 64 zeroed bytes inside the workspace (cleared by the accumulator memset of
+// the tensor-core path; NULL when that path is not taken) -- the grid-barrier counter of the forward chain launch
 int wc_stats_fwd_impl(const float* x, int64_t M, int C, int g, float* workspace, size_t workspace_bytes,
-                      float* mean, float* S, const WcPrepFuse* fuse, int* fused, cudaStream_t stream);
+                      float* mean, float* S, const WcPrepFuse* fuse, int* fused, unsigned** zeroed_out, cudaStream_t stream);
 int wc_factor_fwd_impl(const float* mean, const float* S, const float* count_dev, double count_host, int C, int g,
                        float eps, float momentum, int decomposition, int renorm, int training,
                        float* moving_mean, float* moving_cov, float* Weff, float* Wm, float* R, float* U,
@@ -118,7 +120,7 @@ int wc_factor_fwd_impl(const float* mean, const float* S, const float* count_dev
 int wc_compose_fwd_impl(const float* Weff, int Cin, int Cout, int g, int K, const float* Wu, const float* bu,
                         const float* Wc, const float* bc, int triangular, const float* class_matrix,
                         const float* D, int E, const float* bf, float* ehat, float* Wk, float* T, float* b,
-                        void* Tp_fwd, void* Tp_bwd, const float* Wk_ready, cudaStream_t st);
+                        void* Tp_fwd, void* Tp_bwd, const float* Wk_ready, unsigned* barrier, cudaStream_t st);
 int wc_factor_bwd_impl(const float* dWeff, const float* gbar, const float* Weff, const float* Wm, const float* R,
                        const float* U, const float* lam, const float* count_dev, double count_host, int C, int g,
                        float eps, int decomposition, int renorm, float* A, float* cvec, float* workspace,

@@ -337,7 +337,7 @@ __global__ void class_order_kernel(const int32_t* __restrict__ cls, int N, int K
   }
 }
 
-struct StatsPlan { int ntiles, nchunks, units_per_chunk, ups, tw, tpg; size_t off_pivot, off_sum, off_S, bytes; };
+struct StatsPlan { int ntiles, nchunks, units_per_chunk, ups, tw, tpg; size_t off_pivot, off_zero, off_sum, off_S, bytes; };
 
 StatsPlan plan_stats(int64_t M, int C, int g) {
   StatsPlan pl{};
@@ -350,7 +350,8 @@ StatsPlan plan_stats(int64_t M, int C, int g) {
   pl.units_per_chunk = wc_cdiv(pl.ups, pl.nchunks);
   pl.nchunks = wc_cdiv(pl.ups, pl.units_per_chunk);
   pl.off_pivot = 0;
-  pl.off_sum = wc_align_up((size_t)C * 4, 256);
+  pl.off_zero = wc_align_up((size_t)C * 4, 256);      // 256 bytes cleared together with the accumulators (tensor-core path)
+  pl.off_sum = pl.off_zero + 256;
   pl.off_S = pl.off_sum + wc_align_up((size_t)pl.nchunks * C * 4, 256);
   pl.bytes = pl.off_S + (size_t)pl.nchunks * C * C * 4;
   return pl;
@@ -373,14 +374,15 @@ extern "C" size_t wc_stats_workspace_bytes(int64_t M, int C, int g) {
 
 extern "C" int wc_stats_fwd(const float* x, int64_t M, int C, int g, float* workspace, size_t workspace_bytes,
                             float* mean, float* S, wc_stream_t stream) {
-  return wc_stats_fwd_impl(x, M, C, g, workspace, workspace_bytes, mean, S, nullptr, nullptr, (cudaStream_t)stream);
+  return wc_stats_fwd_impl(x, M, C, g, workspace, workspace_bytes, mean, S, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 // fuse (nullable): also run the prep step of wc_factor_fwd when the tensor-core path is taken; *fused reports whether
 // that happened (the caller then tells wc_factor_fwd_impl to skip its own prep launch)
 int wc_stats_fwd_impl(const float* x, int64_t M, int C, int g, float* workspace, size_t workspace_bytes,
-                      float* mean, float* S, const WcPrepFuse* fuse, int* fused, cudaStream_t stream) {
+                      float* mean, float* S, const WcPrepFuse* fuse, int* fused, unsigned** zeroed_out, cudaStream_t stream) {
   if (fused) *fused = 0;
+  if (zeroed_out) *zeroed_out = nullptr;
   if (!x || !workspace || !mean || !S || M <= 0 || C <= 0 || g <= 0 || C % g) return WC_E_ARG;
   if (M > (int64_t)INT32_MAX) return WC_E_UNSUPPORTED;
   StatsPlan pl = plan_stats(M, C, g);
@@ -395,7 +397,8 @@ int wc_stats_fwd_impl(const float* x, int64_t M, int C, int g, float* workspace,
     // tensor-core path: the full C x C scatter is accumulated with vector reductions into one zeroed buffer
     // (partial slot 0; column sums and scatter are adjacent: one memset); the kernel computes its own pivot and
     // the finalize kernel keeps the diagonal blocks when g < C.
-    WC_CUDA(cudaMemsetAsync(psum, 0, (pl.off_S - pl.off_sum) + (size_t)C * C * 4, st));
+    WC_CUDA(cudaMemsetAsync(ws + pl.off_zero, 0, (pl.off_S - pl.off_zero) + (size_t)C * C * 4, st));
+    if (zeroed_out) *zeroed_out = reinterpret_cast<unsigned*>(ws + pl.off_zero);
     int rc = wc_tc_gram_self(x, M, C, g, pivot, pS, psum, st);
     if (rc) return rc;
     long long tot = (long long)C * g;

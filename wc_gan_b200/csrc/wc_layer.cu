@@ -130,6 +130,7 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
   if (c.whiten && (!c.moving_mean || !c.moving_cov)) return WC_E_ARG;
 
   int prep_done = 0;
+  unsigned* fwd_barrier = nullptr;       // zeroed by K1's accumulator memset: grid-barrier counter of the K2b chain launch
   if ((c.phases & WC_PHASE_STATS) && train_w) {
     // single process, no renorm: the finalize kernel of the statistics also scales / shrinks the covariance and
     // updates the moving averages (K2's prep step), one launch less on the serial path
@@ -137,7 +138,7 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
     WcPrepFuse f{c.eps, c.decomposition == WC_DECOMP_ZCA ? c.eps : 0.f, c.momentum, c.moving_mean, c.moving_cov,
                  at<float>(c.workspace, W.factor)};
     rc = wc_stats_fwd_impl(c.x, M, c.Cin, c.g, at<float>(c.workspace, W.stats), W.stats_bytes, at<float>(c.saved, L.mean),
-                           at<float>(c.saved, L.S), can_fuse ? &f : nullptr, &prep_done, (cudaStream_t)stream);
+                           at<float>(c.saved, L.S), can_fuse ? &f : nullptr, &prep_done, &fwd_barrier, (cudaStream_t)stream);
     if (rc) return rc;
   }
   if (!(c.phases & WC_PHASE_APPLY)) return 0;
@@ -176,7 +177,7 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
   rc = wc_compose_fwd_impl(at<float>(c.saved, L.Weff), c.Cin, c.Cout, c.whiten ? c.g : c.Cin, c.K, c.Wu, c.bu, c.Wc, c.bc,
                            c.triangular, c.class_matrix, c.D, c.E, c.bf, at<float>(c.saved, L.ehat), at<float>(c.saved, L.Wk),
                            at<float>(c.saved, L.T), at<float>(c.saved, L.b), Tp, Tp ? at<void>(c.saved, L.Tp_bwd) : nullptr,
-                           plain_u(c) ? c.Wu : nullptr, (cudaStream_t)stream);
+                           plain_u(c) ? c.Wu : nullptr, fwd_barrier, (cudaStream_t)stream);
   if (rc) return rc;
   const int band = (c.whiten && !has_coloring(c) && c.g < c.Cin) ? c.g : 0;
   return wc_apply_fwd(c.x, c.N, c.HW, c.Cin, c.Cout, mean, at<float>(c.saved, L.T), Tp, plain_u(c) ? c.bu : at<float>(c.saved, L.b),

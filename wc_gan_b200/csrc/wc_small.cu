@@ -309,13 +309,20 @@ __global__ void __launch_bounds__(SMM_THREADS) smm_multi_kernel(const __grid_con
 //
 // Co-residency: grid <= number of SMs, one CTA fits on every SM, and nothing a chain CTA waits for depends on a kernel
 // launched after it (the dependent launch is triggered only once every CTA of this grid is running).
-enum { CJ_SMM = 0, CJ_VEC = 1, CJ_SUMK = 2, CJ_COPY = 3, CJ_WSUMK = 4, CJ_DOT = 5, CJ_L2N = 6 };
+enum { CJ_SMM = 0, CJ_VEC = 1, CJ_SUMK = 2, CJ_COPY = 3, CJ_WSUMK = 4, CJ_DOT = 5, CJ_L2N = 6, CJ_BUILDWK = 7 };
 constexpr int CH_MAXSMM = 5, CH_MAXVEC = 3, CH_MAXELT = 7, CH_MAXSTAGE = 6, CH_ELT_CHUNK = 2048;
 struct EltJob {
   const float* a; const float* b; float* out;
   long long n;                 // elements per slice
   int K, E;
   const float* cm; const float* ehat;
+};
+// K2b's first half (generator.py:41-78, conditional_layers.py:811-819, :993-1005): W_k = Wu + triu?(Wc_k) + sum_e ehat[k,e] D_e,
+// b_k = bu + bc_k + bf_k, ehat = l2_normalize(class_matrix)
+struct BuildJob {
+  const float *Wu, *bu, *Wc, *bc, *cm, *D, *bf;
+  float *ehat, *Wk, *b;
+  int Cin, Cout, K, E, triangular, identity;
 };
 struct ChainEnt { short type, idx, stage, pad; int v0, n; };
 // one tiled product of the chain, everything the tile routine needs in 32-bit form (all strides in elements)
@@ -332,9 +339,10 @@ struct TJob {
   float alpha;
 };
 struct ChainProgram {
-  TJob smm[CH_MAXSMM]; VecJob vec[CH_MAXVEC]; EltJob elt[CH_MAXELT];
+  TJob smm[CH_MAXSMM]; VecJob vec[CH_MAXVEC]; EltJob elt[CH_MAXELT]; BuildJob build;
   ChainEnt ent[CH_MAXSMM + CH_MAXVEC + CH_MAXELT];
   int nent, nstages;
+  int prewait;                       // stages [0, prewait) read nothing the preceding kernel writes: they run before the dependency wait
   const float* count_dev; float count_host;       // rows of the global batch (count_dev[0] when non-NULL)
   int stage_total[CH_MAXSTAGE];      // virtual CTAs of each stage
   unsigned* barrier;                 // one counter, zero on entry (the caller's memset of the accumulators covers it)
@@ -598,6 +606,48 @@ __device__ __forceinline__ void elt_job_run(int type, const EltJob& j, int cta, 
   }
 }
 
+__device__ __forceinline__ void build_job_run(const BuildJob& j, int cta) {
+  const long long per = (long long)j.Cin * j.Cout, total = per * j.K;
+  const long long idx0 = (long long)cta * CH_ELT_CHUNK + 4 * threadIdx.x;
+  if (idx0 >= total) return;
+  // Cout % 4 == 0 (checked by the host): the four elements share (k, i)
+  const int k = (int)(idx0 / per);
+  const long long ij0 = idx0 - (long long)k * per;
+  const int i = (int)(ij0 / j.Cout), j0 = (int)(ij0 - (long long)i * j.Cout);
+  float w[4];
+  if (j.Wu) { const float4 v = __ldg(reinterpret_cast<const float4*>(j.Wu + ij0)); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+  else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = (j.identity && i == j0 + q) ? 1.f : 0.f;      // no coloring at all: W = I (generator.py:79-80)
+  }
+  if (j.Wc) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(j.Wc + idx0));
+    const float c[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (!(j.triangular && j0 + q < i)) w[q] += c[q];     // matrix_band_part(kernel, 0, -1): upper triangle
+  }
+  if (j.cm) {
+    float sq = 0.f;
+    for (int e = 0; e < j.E; ++e) { const float v = j.cm[k * j.E + e]; sq = fmaf(v, v, sq); }
+    const float rho = rsqrtf(fmaxf(sq, 1e-12f));                                     // tf.nn.l2_normalize
+    for (int e = 0; e < j.E; ++e) {
+      const float eh = j.cm[k * j.E + e] * rho;
+      const float4 d = __ldg(reinterpret_cast<const float4*>(j.D + (long long)e * per + ij0));
+      w[0] = fmaf(eh, d.x, w[0]); w[1] = fmaf(eh, d.y, w[1]); w[2] = fmaf(eh, d.z, w[2]); w[3] = fmaf(eh, d.w, w[3]);
+      if (ij0 == 0) j.ehat[k * j.E + e] = eh;
+    }
+  }
+  *reinterpret_cast<float4*>(j.Wk + idx0) = make_float4(w[0], w[1], w[2], w[3]);
+  if (i == 0 && j.b) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int jj = j0 + q;
+      j.b[(long long)k * j.Cout + jj] = (j.bu ? j.bu[jj] : 0.f) + (j.bc ? j.bc[(long long)k * j.Cout + jj] : 0.f) +
+                                        (j.bf ? j.bf[(long long)k * j.Cout + jj] : 0.f);
+    }
+  }
+}
+
 __device__ __forceinline__ void chain_grid_barrier(unsigned* ctr, unsigned target) {
   __syncthreads();     // orders every thread's stores of this stage before thread 0's release
   if (threadIdx.x == 0) {
@@ -624,15 +674,19 @@ __global__ void __launch_bounds__(SMM_THREADS, 1) chain_kernel(const __grid_cons
     const int v = kp.words[threadIdx.x * 16];
     if (v == 0x7fffffff) s_sink = v;       // never true for a pointer / count word in practice; keeps the load alive
   }
-  wc_pdl_wait();
-  if (threadIdx.x == 0) s_cnt[0] = pr.count_dev ? __ldcg(pr.count_dev) : pr.count_host;
-  __syncthreads();
-  if (threadIdx.x == 0) wc_mark(pr.dbg, 8);
+  bool waited = false;
   for (int s = 0; s < pr.nstages; ++s) {
     if (s > 0) {
       if (threadIdx.x == 0 && s < 4) wc_mark(pr.dbg, 7 + 2 * s);      // own jobs of stage s-1 done
       chain_grid_barrier(pr.barrier, (unsigned)s * gridDim.x);
       if (threadIdx.x == 0 && s < 4) wc_mark(pr.dbg, 8 + 2 * s);      // barrier passed
+    }
+    if (!waited && s >= pr.prewait) {
+      wc_pdl_wait();
+      waited = true;
+      if (threadIdx.x == 0) s_cnt[0] = pr.count_dev ? __ldcg(pr.count_dev) : pr.count_host;
+      __syncthreads();
+      if (threadIdx.x == 0) wc_mark(pr.dbg, 8);
     }
     for (int v = blockIdx.x; v < pr.stage_total[s]; v += gridDim.x) {
       int e = 0;
@@ -651,6 +705,8 @@ __global__ void __launch_bounds__(SMM_THREADS, 1) chain_kernel(const __grid_cons
           smm_tile_rt(jb, rem - yy * jb.gx, yy, zz, smm_sm, pr.dbg_flags, pr.dbg, s_cnt[0]);
         } else if (en.type == CJ_VEC) {
           vec_job_run(pr.vec[en.idx], l, smm_sm);
+        } else if (en.type == CJ_BUILDWK) {
+          build_job_run(pr.build, l);
         } else {
           elt_job_run(en.type, pr.elt[en.idx], l, smm_sm);
         }
@@ -658,6 +714,7 @@ __global__ void __launch_bounds__(SMM_THREADS, 1) chain_kernel(const __grid_cons
       __syncthreads();   // shared memory is reused by the next job of this CTA
     }
   }
+  if (!waited) wc_pdl_wait();     // every kernel of the library executes the dependency wait exactly once
   if (threadIdx.x == 0) wc_mark(pr.dbg, 15);
 }
 
@@ -1196,24 +1253,116 @@ int wc_factor_fwd_impl(const float* mean, const float* S, const float* count_dev
 }
 
 // =============================================================================================
+// host side of the chain launches (forward: K2b; backward: K5a + K5b)
+// =============================================================================================
+namespace {
+struct ChainBuilder {
+  ChainProgram pr{};
+  int nsmm = 0, nvec = 0, nelt = 0;
+  bool ok = true;
+  void ent(int type, int idx, int stage, int n) {
+    ChainEnt& e = pr.ent[pr.nent++];
+    e.type = (short)type; e.idx = (short)idx; e.stage = (short)stage; e.pad = 0;
+    e.v0 = pr.stage_total[stage]; e.n = n;
+    pr.stage_total[stage] += n;
+    if (stage + 1 > pr.nstages) pr.nstages = stage + 1;
+  }
+  void smm(int stage, const WcSmm& p, const SmmEpi& ep = SmmEpi{}, int count_mode = 0) {
+    if (nsmm >= CH_MAXSMM || !smm_is_fast(p) || p.beta != 0.f || (p.K % 32)) { ok = false; return; }
+    if (ep.kind == EPI_PACK && (ep.pkC % 32 || (ep.pk0 && !wc_aligned16(ep.pk0)) || (ep.pk1 && !wc_aligned16(ep.pk1)))) { ok = false; return; }
+    const long long lim = 1ll << 30;
+    for (long long v : {p.rsA, p.csA, p.rsB, p.csB, p.rsC, p.csC, p.bA1, p.bA2, p.bB1, p.bB2, p.bC1, p.bC2, p.sA, p.sB, ep.pk_slot_stride})
+      if (v < 0 || v >= lim) { ok = false; return; }
+    if ((long long)p.nb1 * std::max({p.bA1, p.bB1, p.bC1}) >= lim || (long long)p.nsum * std::max(p.sA, p.sB) >= lim) { ok = false; return; }
+    TJob& j = pr.smm[nsmm];
+    j.A = p.A; j.B = p.B; j.C = p.C; j.pk0 = ep.pk0; j.pk1 = ep.pk1;
+    j.ak = p.csA == 1; j.bk = p.rsB == 1;
+    j.lda = (int)(j.ak ? p.rsA : p.csA); j.ldb = (int)(j.bk ? p.csB : p.rsB);
+    j.rsC = (int)p.rsC; j.csC = (int)p.csC;
+    j.bA1 = (int)p.bA1; j.bA2 = (int)p.bA2; j.bB1 = (int)p.bB1; j.bB2 = (int)p.bB2; j.bC1 = (int)p.bC1; j.bC2 = (int)p.bC2;
+    j.sA = (int)p.sA; j.sB = (int)p.sB;
+    j.K = p.K; j.nsum = p.nsum; j.nb2 = p.nb2; j.gx = p.N / SMM_T; j.gy = p.M / SMM_T;
+    j.pk_slot_stride = (int)ep.pk_slot_stride; j.pkC = ep.pkC; j.row_per_b2 = ep.row_per_b2;
+    j.epi = (short)ep.kind; j.count_mode = (short)count_mode; j.tri = (short)p.tri; j.pad = 0;
+    j.alpha = p.alpha;
+    ent(CJ_SMM, nsmm++, stage, j.gx * j.gy * p.nb1 * p.nb2);
+  }
+  void vec(int stage, const VecJob& v0) {
+    if (nvec >= CH_MAXVEC || v0.M <= 0 || v0.nb <= 0) { ok = false; return; }
+    VecJob& v = pr.vec[nvec];
+    v = v0; v.cta0 = 0; v.nctas = ((v.M + 31) / 32) * v.nb;
+    ent(CJ_VEC, nvec++, stage, v.nctas);
+  }
+  void build(int stage, const BuildJob& j) {
+    pr.build = j;
+    ent(CJ_BUILDWK, 0, stage, elt_chunks_((long long)j.Cin * j.Cout * j.K));
+  }
+  static int elt_chunks_(long long n) { return (int)((n + CH_ELT_CHUNK - 1) / CH_ELT_CHUNK); }
+  void elt(int stage, int type, const EltJob& j, int nctas) {
+    if (nelt >= CH_MAXELT) { ok = false; return; }
+    pr.elt[nelt] = j;
+    ent(type, nelt++, stage, nctas);
+  }
+  int launch(unsigned* barrier, cudaStream_t st) {
+    if (!ok || (pr.nstages > 1 && !barrier)) return WC_E_UNSUPPORTED;
+    int mx = 1;
+    for (int s2 = 0; s2 < pr.nstages; ++s2) mx = std::max(mx, pr.stage_total[s2]);
+    pr.barrier = barrier; pr.dbg = wc_debug_buf(); pr.dbg_flags = wc_debug_flags();
+    static bool attr_set = false;
+    if (!attr_set) {
+      WC_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
+      attr_set = true;
+    }
+    ChainParams kp; kp.pr = pr;
+    WC_CUDA(wc_launch(chain_kernel, std::min(mx, WC_NUM_SMS), SMM_THREADS, CHAIN_SMEM, st, kp));
+    WC_CHECK_LAUNCH();
+    return 0;
+  }
+};
+inline int elt_chunks(long long n) { return (int)((n + CH_ELT_CHUNK - 1) / CH_ELT_CHUNK); }
+}  // namespace
+
+// =============================================================================================
 // K2b entry point
 // =============================================================================================
 int wc_compose_fwd_impl(const float* Weff, int Cin, int Cout, int g, int K, const float* Wu, const float* bu,
                         const float* Wc, const float* bc, int triangular, const float* class_matrix,
                         const float* D, int E, const float* bf, float* ehat, float* Wk, float* T, float* b,
-                        void* Tp_fwd, void* Tp_bwd, const float* Wk_ready, cudaStream_t st) {
+                        void* Tp_fwd, void* Tp_bwd, const float* Wk_ready, unsigned* barrier, cudaStream_t st) {
+  // barrier (nullable): one zeroed u32 for the chain launch (without it only single-stage programs take that path)
   // Wk_ready (nullable): the per-class matrix already exists (K == 1 with only the unconditional kernel: it IS Wu, and the
   // bias is bu); nothing is built and `Wk` / `b` are not written
   if (Cin <= 0 || Cout <= 0 || K <= 0 || (!Wk && !Wk_ready) || !T) return WC_E_ARG;
   if (Weff && (g <= 0 || Cin % g)) return WC_E_ARG;
   if (class_matrix && (!D || E <= 0 || !ehat)) return WC_E_ARG;
   long long per = (long long)Cin * Cout;
+  const float* Wsrc = Wk_ready ? Wk_ready : Wk;
+  // One persistent launch (chain kernel): stage 0 builds W_k, b_k, ehat -- it reads only parameters, so it runs BEFORE the
+  // dependency wait, under the factorisation -- and stage 1 forms T_k = Weff^T W_k on the tensor-core tile, leaving it as
+  // fp32 and as the bf16 operand images of K3 / K6.
+  if (Weff && Cin == Cout && (Cin % 32) == 0 && (g % 32) == 0 && !(wc_debug_flags() & 262144)) {
+    ChainBuilder cb;
+    int st_t = 0;
+    if (!Wk_ready) {
+      BuildJob bj{Wu, bu, Wc, bc, class_matrix, D, bf, ehat, Wk, b, Cin, Cout, K, E, triangular, (!Wu && !Wc && !D) ? 1 : 0};
+      cb.build(0, bj);
+      cb.pr.prewait = 1;
+      st_t = 1;
+    }
+    SmmEpi ep{};
+    if (Tp_fwd || Tp_bwd) {
+      ep.kind = EPI_PACK; ep.pk0 = (uint8_t*)Tp_fwd; ep.pk1 = (uint8_t*)Tp_bwd;
+      ep.pk_slot_stride = (long long)Cin * Cout * 4; ep.pkC = Cin; ep.row_per_b2 = g;
+    }
+    cb.smm(st_t, smm_blockdiag_left(Weff, true, Wsrc, T, g, Cin / g, Cout, Cout, K, per), ep);
+    const int rcc = cb.launch(barrier, st);
+    if (rcc != WC_E_UNSUPPORTED) return rcc;
+  }
   if (!Wk_ready) {
     WC_CUDA(wc_launch(build_wk_kernel, wc_cdiv(per * K, 256), 256, 0, st, Cin, Cout, K, Wu, bu, Wc, bc, triangular, class_matrix, D, E, bf,
                                                            ehat, Wk, b, (!Wu && !Wc && !D) ? 1 : 0));
     WC_CHECK_LAUNCH();
   }
-  const float* Wsrc = Wk_ready ? Wk_ready : Wk;
   int rc = 0;
   bool packed = false;
   if (!Weff) {
@@ -1246,7 +1395,7 @@ extern "C" int wc_compose_fwd(const float* Weff, int Cin, int Cout, int g, int K
                               const float* D, int E, const float* bf, float* ehat, float* Wk, float* T, float* b,
                               wc_stream_t stream) {
   return wc_compose_fwd_impl(Weff, Cin, Cout, g, K, Wu, bu, Wc, bc, triangular, class_matrix, D, E, bf, ehat, Wk, T, b,
-                             nullptr, nullptr, nullptr, (cudaStream_t)stream);
+                             nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 // =============================================================================================
@@ -1462,70 +1611,8 @@ int wc_factor_bwd_impl(const float* dWeff, const float* gbar, const float* Weff,
 }
 
 // =============================================================================================
-// K5a + K5b as one persistent launch (the "chain"; Cholesky whitening, no renorm, tile-aligned shapes)
+// K5a + K5b as one persistent launch (Cholesky whitening, no renorm, tile-aligned shapes)
 // =============================================================================================
-namespace {
-struct ChainBuilder {
-  ChainProgram pr{};
-  int nsmm = 0, nvec = 0, nelt = 0;
-  bool ok = true;
-  void ent(int type, int idx, int stage, int n) {
-    ChainEnt& e = pr.ent[pr.nent++];
-    e.type = (short)type; e.idx = (short)idx; e.stage = (short)stage; e.pad = 0;
-    e.v0 = pr.stage_total[stage]; e.n = n;
-    pr.stage_total[stage] += n;
-    if (stage + 1 > pr.nstages) pr.nstages = stage + 1;
-  }
-  void smm(int stage, const WcSmm& p, const SmmEpi& ep = SmmEpi{}, int count_mode = 0) {
-    if (nsmm >= CH_MAXSMM || !smm_is_fast(p) || p.beta != 0.f || (p.K % 32)) { ok = false; return; }
-    if (ep.kind == EPI_PACK && (ep.pkC % 32 || (ep.pk0 && !wc_aligned16(ep.pk0)) || (ep.pk1 && !wc_aligned16(ep.pk1)))) { ok = false; return; }
-    const long long lim = 1ll << 30;
-    for (long long v : {p.rsA, p.csA, p.rsB, p.csB, p.rsC, p.csC, p.bA1, p.bA2, p.bB1, p.bB2, p.bC1, p.bC2, p.sA, p.sB, ep.pk_slot_stride})
-      if (v < 0 || v >= lim) { ok = false; return; }
-    if ((long long)p.nb1 * std::max({p.bA1, p.bB1, p.bC1}) >= lim || (long long)p.nsum * std::max(p.sA, p.sB) >= lim) { ok = false; return; }
-    TJob& j = pr.smm[nsmm];
-    j.A = p.A; j.B = p.B; j.C = p.C; j.pk0 = ep.pk0; j.pk1 = ep.pk1;
-    j.ak = p.csA == 1; j.bk = p.rsB == 1;
-    j.lda = (int)(j.ak ? p.rsA : p.csA); j.ldb = (int)(j.bk ? p.csB : p.rsB);
-    j.rsC = (int)p.rsC; j.csC = (int)p.csC;
-    j.bA1 = (int)p.bA1; j.bA2 = (int)p.bA2; j.bB1 = (int)p.bB1; j.bB2 = (int)p.bB2; j.bC1 = (int)p.bC1; j.bC2 = (int)p.bC2;
-    j.sA = (int)p.sA; j.sB = (int)p.sB;
-    j.K = p.K; j.nsum = p.nsum; j.nb2 = p.nb2; j.gx = p.N / SMM_T; j.gy = p.M / SMM_T;
-    j.pk_slot_stride = (int)ep.pk_slot_stride; j.pkC = ep.pkC; j.row_per_b2 = ep.row_per_b2;
-    j.epi = (short)ep.kind; j.count_mode = (short)count_mode; j.tri = (short)p.tri; j.pad = 0;
-    j.alpha = p.alpha;
-    ent(CJ_SMM, nsmm++, stage, j.gx * j.gy * p.nb1 * p.nb2);
-  }
-  void vec(int stage, const VecJob& v0) {
-    if (nvec >= CH_MAXVEC || v0.M <= 0 || v0.nb <= 0) { ok = false; return; }
-    VecJob& v = pr.vec[nvec];
-    v = v0; v.cta0 = 0; v.nctas = ((v.M + 31) / 32) * v.nb;
-    ent(CJ_VEC, nvec++, stage, v.nctas);
-  }
-  void elt(int stage, int type, const EltJob& j, int nctas) {
-    if (nelt >= CH_MAXELT) { ok = false; return; }
-    pr.elt[nelt] = j;
-    ent(type, nelt++, stage, nctas);
-  }
-  int launch(unsigned* barrier, cudaStream_t st) {
-    if (!ok) return WC_E_UNSUPPORTED;
-    int mx = 1;
-    for (int s2 = 0; s2 < pr.nstages; ++s2) mx = std::max(mx, pr.stage_total[s2]);
-    pr.barrier = barrier; pr.dbg = wc_debug_buf(); pr.dbg_flags = wc_debug_flags();
-    static bool attr_set = false;
-    if (!attr_set) {
-      WC_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
-      attr_set = true;
-    }
-    ChainParams kp; kp.pr = pr;
-    WC_CUDA(wc_launch(chain_kernel, std::min(mx, WC_NUM_SMS), SMM_THREADS, CHAIN_SMEM, st, kp));
-    WC_CHECK_LAUNCH();
-    return 0;
-  }
-};
-inline int elt_chunks(long long n) { return (int)((n + CH_ELT_CHUNK - 1) / CH_ELT_CHUNK); }
-}  // namespace
-
 // Stages [stage_lo, stage_hi) of the backward chain:
 //   0: Q_k = Weff P_k, dWeff = sum_k W_k P_k^T, gbar = sum_k W_k s_k, dbu = sum_k s_k, dbc = dbf = s
 //   1: Psi from Z = dWeff Wm^T, cvec = Weff^T gbar / count, dWu = sum_k Q_k, dD = ehat^T Q, de = <Q_k, D_e>

@@ -82,10 +82,11 @@ def _operand(t, name, dev, shape, *, numel=None, inplace=False):
     buffers must already be contiguous: the kernels update them)."""
     if t is None:
         return None
-    if not t.is_cuda or t.device != dev:
-        raise ValueError(f'{name} is on {t.device}, x on {dev}: every operand must live on the same CUDA device')
+    _need_cuda(t, name)
     if t.dtype != torch.float32:
         raise TypeError(f'{name} must be float32 (got {t.dtype})')
+    if t.device != dev:
+        raise ValueError(f'{name} is on {t.device}, x on {dev}: every operand must live on the same CUDA device')
     if shape is not None and tuple(t.shape) != tuple(shape):
         raise ValueError(f'{name} has shape {tuple(t.shape)}, expected {tuple(shape)}')
     if numel is not None and t.numel() != numel:

@@ -27,9 +27,15 @@ def marks(tag):
     t0 = min(r[0] for r in rows)
     ends = [(r[1] - t0) / 1e3 for r in rows]
     starts = [(r[0] - t0) / 1e3 for r in rows]
-    e4 = ends[:68]; e3 = ends[68:]
-    print(f'{tag}: start spread {max(starts):.2f} us | CTAs 0-67 (4 tiles) end avg {sum(e4)/len(e4):.1f} max {max(e4):.1f} | CTAs 68-147 (3 tiles) end avg {sum(e3)/max(1,len(e3)):.1f} max {max(e3) if e3 else 0:.1f}')
-for flags in (1, 1 | 256, 1 | 128 | 256, 1 | 64 | 128 | 256):
+    prof = [[buf[bb * 32 + k] for k in range(2, 8)] for bb in range(0, 148, 2) if buf[bb * 32]]
+    if prof and prof[0][4]:
+        n = len(prof)
+        avg = [sum(r[k] for r in prof) / n for k in range(6)]
+        print(f'   issuer cycles (avg over {n} leaders): wait local {avg[0]:.0f} | peer A {avg[1]:.0f} | peer B {avg[2]:.0f} | accum {avg[3]:.0f} | total {avg[4]:.0f} | k-blocks {avg[5]:.0f}')
+    print(f'{tag}: start spread {max(starts):.2f} us | end min {min(ends):.1f} avg {sum(ends)/len(ends):.1f} max {max(ends):.1f}')
+import os
+BASE = int(os.environ.get('WC_DBG', '0'))
+for flags in (1 | BASE,):
     lib.wc_debug_set(flags)
     for nm, fn in (('K3', k3), ('K6', k6)):
         for i in range(3): fn(i)

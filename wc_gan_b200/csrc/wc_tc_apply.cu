@@ -304,6 +304,294 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
   if (warp == W_MMA) tmem_dealloc(td, cfg::TMEM_COLS);
 }
 
+// =====================================================================================================================
+// CTA-pair version (cta_group::2).  NOT the default: measured (profiles/r02_pair_apply.txt) it is 3 us faster than the
+// single-CTA kernel on warm inputs (K3 24.4 vs 27.4 us, issuer 810 of 1190 cycles per k-block busy issuing MMAs) but no
+// faster inside the cold-cache step (K3 33.0 vs 32.3, K6 52.7 vs 50.3 us per graph timeline), where both wait for HBM and
+// for the 256-row wave quantisation (256 pair tiles on 74 pairs = 3.46 rounds).  Selected with wc_debug_set bit 2097152.
+// =====================================================================================================================
+// The single-CTA kernel above re-streams the packed C x C matrices from L2 for every 128-row tile: at C = 256 that is
+// 256 KB (K3) / 512 KB (K6) of L2 reads per 128 KB of activations, ~70 % of the kernel's L2 -> SM traffic, and with it the
+// kernel sits at the L2 output limit with the tensor pipe 44 / 58 % busy (profiles/r01e_ncu_full_summary.txt).  Here two
+// CTAs of a cluster (one TPC) share each MMA: a pair works on 256 rows, every CTA converts its own 128 rows (A operand)
+// and loads only HALF of the N rows of each matrix image (B operand); tcgen05.mma.cta_group::2 with M = 256 reads both
+// halves from the same shared-memory offsets of the two CTAs.  Matrix traffic from L2 and the MMA's shared-memory reads
+// of B are halved; everything on the activation side (TMA boxes, converters, epilogue, TMA stores) stays CTA-local.
+//
+// Hand-overs across the pair (rank 0 = leader, issues every MMA):
+//   peer A / B stage ready  -> a relay thread in the peer (its otherwise idle MMA warp) waits on the peer's LOCAL full barrier
+//                              and arrives remotely on the leader's aop_pfull / bop_pfull
+//   stage consumed, accumulator complete -> tcgen05.commit multicast: arrives on the same barrier offset in both CTAs
+//   peer accumulator drained -> the peer's epilogue warps arrive remotely on the leader's acc_pempty
+template <int C>
+struct Cfg2 {
+  static constexpr int NSTG = 4, NAOP = 3, NBOP = 4;
+  static constexpr int N = C;
+  static constexpr int NKB = C / KB;
+  static constexpr int A_IMG = TILE_M * KB * 2;            // 8 KB: one bf16 split of this CTA's A tile
+  static constexpr int B_HALF = (N / 2) * KB * 2;          // 8 KB (C=256) / 4 KB (C=128): this CTA's half of one bf16 split of B
+  static constexpr int B_IMG = N * KB * 2;                 // the whole split in the packed buffer
+  static constexpr int OFF_AOP = NSTG * STG_BYTES;
+  static constexpr int OFF_BOP = OFF_AOP + NAOP * 2 * A_IMG;
+  static constexpr int OFF_EPI = OFF_BOP + NBOP * 2 * B_HALF;
+  static constexpr int SMEM = OFF_EPI + NEPIBUF * STG_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * N;
+};
+
+__device__ __forceinline__ TileInfo tile_info2(const TcApplyParams& p, long long ptile, int rank) {
+  TileInfo ti;
+  const long long tr = p.total_tiles - 1 - ptile;          // pair tiles, visited from the end of the tensor
+  ti.sample = (int)(tr / p.tiles_per_sample);
+  ti.r0 = (int)(tr % p.tiles_per_sample) * (2 * TILE_M) + rank * TILE_M;    // rows past the sample end: zero-filled / clipped by TMA
+  ti.slot = 0;
+  if (p.cls) {
+    int c = p.cls[ti.sample];
+    if (c < 0 || c >= p.K) {
+      if (p.info && threadIdx.x == 0 && ti.r0 == 0) atomicMax(&p.info[WC_INFO_BAD_CLASS], ti.sample + 1);
+      c = c < 0 ? 0 : p.K - 1;
+    }
+    ti.slot = c;
+  }
+  return ti;
+}
+
+template <int C>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_apply2_kernel(TcApplyParams p, const __grid_constant__ CUtensorMap tm_a0,
+                                                                const __grid_constant__ CUtensorMap tm_a1,
+                                                                const __grid_constant__ CUtensorMap tm_out) {
+  using cfg = Cfg2<C>;
+  constexpr int NSTG = cfg::NSTG, NAOP = cfg::NAOP, NBOP = cfg::NBOP;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t stg_full[NSTG], stg_empty[NSTG], aop_full[NAOP], aop_pfull[NAOP], aop_empty[NAOP], bop_full[NBOP],
+      bop_pfull[NBOP], bop_empty[NBOP], acc_full[2], acc_empty[2], acc_pempty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int rank = (int)cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int total_kb = p.nseg * cfg::NKB;
+
+  if (t == 0) {
+    for (int s = 0; s < NSTG; ++s) { mbar_init(&stg_full[s], 1); mbar_init(&stg_empty[s], NCONV_WARPS); }
+    for (int s = 0; s < NAOP; ++s) { mbar_init(&aop_full[s], NCONV_WARPS); mbar_init(&aop_pfull[s], 1); mbar_init(&aop_empty[s], 1); }
+    for (int s = 0; s < NBOP; ++s) { mbar_init(&bop_full[s], 1); mbar_init(&bop_pfull[s], 1); mbar_init(&bop_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NEPI_WARPS); mbar_init(&acc_pempty[s], NEPI_WARPS); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tm_a0); tma_prefetch_desc(&tm_a1); tma_prefetch_desc(&tm_out);
+  }
+  __syncthreads();
+  cluster_sync_all();                  // both CTAs' barriers exist before anything can arrive on them
+  if (warp == W_MMA) { tmem_alloc2(&tmem_slot, cfg::TMEM_COLS); tmem_relinquish2(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t td = tmem_slot;
+  wc_pdl_wait();
+  if (t == 0) wc_mark(p.dbg, 0);
+
+  if (warp == W_PROD) {
+    // ------------------------------------------------------------------ activation producer (CTA-local)
+    if (lane == 0) {
+      uint32_t ia = 0;
+      const uint64_t pol[2] = {l2_policy(p.l2_load[0]), l2_policy(p.l2_load[1])};
+      for (long long pt = pair; pt < p.total_tiles; pt += npairs) {
+        const TileInfo ti = tile_info2(p, pt, rank);
+        for (int it = 0; it < total_kb; ++it, ++ia) {
+          const int sg = it / cfg::NKB, kb = it % cfg::NKB;
+          const int s = ia % NSTG;
+          mbar_wait(&stg_empty[s], ((ia / NSTG) & 1) ^ 1);
+          mbar_arrive_expect_tx(&stg_full[s], STG_BYTES);
+          tma_load_3d_hint(smem + s * STG_BYTES, sg == 0 ? &tm_a0 : &tm_a1, kb * KB, ti.r0, ti.sample, &stg_full[s], pol[sg]);
+        }
+      }
+    }
+  } else if (warp == W_BPROD) {
+    // ------------------------------------------------------------------ matrix-image producer: this CTA's half of N
+    if (lane == 0) {
+      uint32_t ib = 0;
+      for (long long pt = pair; pt < p.total_tiles; pt += npairs) {
+        const TileInfo ti = tile_info2(p, pt, rank);
+        for (int it = 0; it < total_kb; ++it, ++ib) {
+          const int sg = it / cfg::NKB, kb = it % cfg::NKB;
+          const int s = ib % NBOP;
+          const uint8_t* src = p.seg[sg].Bp + (long long)ti.slot * p.seg[sg].slot_stride + (long long)kb * (2 * cfg::B_IMG) +
+                               (long long)rank * cfg::B_HALF;
+          mbar_wait(&bop_empty[s], ((ib / NBOP) & 1) ^ 1);
+          uint8_t* dst = smem + cfg::OFF_BOP + s * 2 * cfg::B_HALF;
+          mbar_arrive_expect_tx(&bop_full[s], 2 * cfg::B_HALF);
+          bulk_g2s(dst, src, cfg::B_HALF, &bop_full[s]);                                   // hi
+          bulk_g2s(dst + cfg::B_HALF, src + cfg::B_IMG, cfg::B_HALF, &bop_full[s]);        // lo
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    if (lane == 0 && rank == 0) {
+      // ---------------------------------------------------------------- MMA issuer (leader CTA)
+      const uint32_t idesc = make_idesc_bf16(2 * TILE_M, cfg::N, 0, 0);
+      uint32_t ia = 0, ib = 0, lt = 0;
+      const bool prof = p.dbg != nullptr;
+      long long w_loc = 0, w_pa = 0, w_pb = 0, w_acc = 0;
+      const long long cstart = prof ? clock64() : 0;
+      for (long long pt = pair; pt < p.total_tiles; pt += npairs, ++lt) {
+        const uint32_t ab = lt & 1;
+        const long long ca = prof ? clock64() : 0;
+        mbar_wait(&acc_empty[ab], ((lt >> 1) & 1) ^ 1);               // both epilogues have drained this accumulator
+        mbar_wait_cluster(&acc_pempty[ab], ((lt >> 1) & 1) ^ 1);
+        w_acc += (prof ? clock64() : 0) - ca;
+        tc_fence_after();
+        const uint32_t tacc = td + ab * cfg::N;
+        uint32_t acc = 0;
+        for (int it = 0; it < total_kb; ++it, ++ia, ++ib) {
+          const int sa = ia % NAOP, sb = ib % NBOP;
+          const long long c0 = prof ? clock64() : 0;
+          mbar_wait(&aop_full[sa], (ia / NAOP) & 1);
+          mbar_wait(&bop_full[sb], (ib / NBOP) & 1);
+          const long long c1 = prof ? clock64() : 0;
+          mbar_wait_cluster(&aop_pfull[sa], (ia / NAOP) & 1);
+          const long long c2 = prof ? clock64() : 0;
+          mbar_wait_cluster(&bop_pfull[sb], (ib / NBOP) & 1);
+          const long long c3 = prof ? clock64() : 0;
+          w_loc += c1 - c0; w_pa += c2 - c1; w_pb += c3 - c2;
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + cfg::OFF_AOP + sa * 2 * cfg::A_IMG);
+          const uint32_t a_lo = a_hi + cfg::A_IMG;
+          const uint32_t b_hi = smem_u32(smem + cfg::OFF_BOP + sb * 2 * cfg::B_HALF);
+          const uint32_t b_lo = b_hi + cfg::B_HALF;
+#pragma unroll
+          for (int kk = 0; kk < KB / 16; ++kk) {
+            const uint64_t dah = make_desc(a_hi + kk * 32, 16, 8 * KB * 2, LAYOUT_SW64);
+            const uint64_t dal = make_desc(a_lo + kk * 32, 16, 8 * KB * 2, LAYOUT_SW64);
+            const uint64_t dbh = make_desc(b_hi + kk * 32, 16, 8 * KB * 2, LAYOUT_SW64);
+            const uint64_t dbl = make_desc(b_lo + kk * 32, 16, 8 * KB * 2, LAYOUT_SW64);
+            if (!(p.dbg_flags & 256)) umma_bf16_2cta(tacc, dah, dbh, idesc, acc);
+            if (!(p.dbg_flags & (256 | 512))) {
+              umma_bf16_2cta(tacc, dah, dbl, idesc, 1);
+              umma_bf16_2cta(tacc, dal, dbh, idesc, 1);
+            }
+            acc = 1;
+          }
+          umma_commit_pair(&aop_empty[sa]);      // frees the stage in BOTH CTAs
+          umma_commit_pair(&bop_empty[sb]);
+        }
+        umma_commit_pair(&acc_full[ab]);
+      }
+      if (prof && blockIdx.x < WC_DBG_BLOCKS) {     // cycles the issuer spent waiting: local stages | peer A | peer B | accumulators | total
+        unsigned long long* d = p.dbg + blockIdx.x * WC_DBG_SLOTS;
+        d[2] = w_loc; d[3] = w_pa; d[4] = w_pb; d[5] = w_acc; d[6] = clock64() - cstart; d[7] = ia;
+      }
+    } else if (lane == 0) {
+      // ---------------------------------------------------------------- relay (peer CTA): local "stage full" -> leader
+      uint32_t ia = 0, ib = 0;
+      for (long long pt = pair; pt < p.total_tiles; pt += npairs) {
+        for (int it = 0; it < total_kb; ++it, ++ia, ++ib) {
+          const int sa = ia % NAOP, sb = ib % NBOP;
+          mbar_wait(&aop_full[sa], (ia / NAOP) & 1);
+          mbar_arrive_remote_relaxed(&aop_pfull[sa], 0);
+          mbar_wait(&bop_full[sb], (ib / NBOP) & 1);
+          mbar_arrive_remote_relaxed(&bop_pfull[sb], 0);
+        }
+      }
+    }
+  } else if (warp >= W_EPI0 && warp < W_CONV0) {
+    // ------------------------------------------------------------------ epilogue (4 warps = this CTA's 128 TMEM lanes)
+    const int te = t - W_EPI0 * 32;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t lt = 0, ec = 0;
+    const uint64_t pol_st = l2_policy(p.l2_store);
+    for (long long pt = pair; pt < p.total_tiles; pt += npairs, ++lt) {
+      const TileInfo ti = tile_info2(p, pt, rank);
+      const uint32_t ab = lt & 1;
+      const float* bias = p.bias ? p.bias + (long long)ti.slot * p.bias_slot_stride : nullptr;
+      mbar_wait(&acc_full[ab], (lt >> 1) & 1);
+      tc_fence_after();
+      for (int c0 = 0; c0 < cfg::N; c0 += 32, ++ec) {
+        const uint32_t eb = ec & 1;
+        if (te == 0) bulk_wait_group_read<1>();
+        asm volatile("bar.sync 2, %0;" ::"n"(NEPI));
+        float acc[32];
+        tmem_ld32(td + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * cfg::N + c0), acc);
+        if (c0 + 32 == cfg::N) {           // last read of this accumulator: hand it back to the leader's MMA thread
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (rank == 0) mbar_arrive(&acc_empty[ab]); else mbar_arrive_remote(&acc_pempty[ab], 0); }
+        }
+        const uint32_t ebase = smem_u32(smem + cfg::OFF_EPI + eb * STG_BYTES) + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+          const float s = p.bias_sign;
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ebase + ((j ^ (row & 7)) << 4)), "f"(fmaf(s, bv.x, acc[4 * j])),
+                       "f"(fmaf(s, bv.y, acc[4 * j + 1])), "f"(fmaf(s, bv.z, acc[4 * j + 2])), "f"(fmaf(s, bv.w, acc[4 * j + 3])) : "memory");
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 2, %0;" ::"n"(NEPI));
+        if (te == 0) {
+          tma_store_3d_hint(&tm_out, c0, ti.r0, ti.sample, smem + cfg::OFF_EPI + eb * STG_BYTES, pol_st);
+          bulk_commit_group();
+        }
+      }
+    }
+    if (te == 0) bulk_wait_group<0>();
+  } else {
+    // ------------------------------------------------------------------ A converters (256 threads, CTA-local)
+    const int tcv = t - W_CONV0 * 32;
+    const int crow0 = tcv >> 2, cch = tcv & 3;
+    const uint32_t stg_u32 = smem_u32(smem), aop_u32 = smem_u32(smem + cfg::OFF_AOP);
+    uint32_t ld_off[2][2], st_off[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = crow0 + h * 64;
+      ld_off[h][0] = r * 128 + (((2 * cch) ^ (r & 7)) << 4);
+      ld_off[h][1] = r * 128 + (((2 * cch + 1) ^ (r & 7)) << 4);
+      st_off[h] = kmajor_chunk_off<KB>(r, cch);
+    }
+    uint32_t ia = 0;
+    for (long long pt = pair; pt < p.total_tiles; pt += npairs) {
+      for (int it = 0; it < total_kb; ++it, ++ia) {
+        const int sg = it / cfg::NKB, kb = it % cfg::NKB;
+        const int s = ia % NSTG, sa = ia % NAOP;
+        float4 m0 = make_float4(0.f, 0.f, 0.f, 0.f), m1 = m0;
+        if (const float* mp = p.seg[sg].mean) {
+          m0 = __ldg(reinterpret_cast<const float4*>(mp + kb * KB + cch * 8));
+          m1 = __ldg(reinterpret_cast<const float4*>(mp + kb * KB + cch * 8 + 4));
+        }
+        mbar_wait(&stg_full[s], (ia / NSTG) & 1);
+        uint32_t hi[2][4], lo[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4 a = lds128(stg_u32 + s * STG_BYTES + ld_off[h][0]);
+          float4 b = lds128(stg_u32 + s * STG_BYTES + ld_off[h][1]);
+          a.x -= m0.x; a.y -= m0.y; a.z -= m0.z; a.w -= m0.w; b.x -= m1.x; b.y -= m1.y; b.z -= m1.z; b.w -= m1.w;
+          split2(a.x, a.y, hi[h][0], lo[h][0]);
+          split2(a.z, a.w, hi[h][1], lo[h][1]);
+          split2(b.x, b.y, hi[h][2], lo[h][2]);
+          split2(b.z, b.w, hi[h][3], lo[h][3]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stg_empty[s]);
+        mbar_wait(&aop_empty[sa], ((ia / NAOP) & 1) ^ 1);
+        const uint32_t dst = aop_u32 + sa * 2 * cfg::A_IMG;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          sts128(dst + st_off[h], hi[h][0], hi[h][1], hi[h][2], hi[h][3]);
+          sts128(dst + cfg::A_IMG + st_off[h], lo[h][0], lo[h][1], lo[h][2], lo[h][3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&aop_full[sa]);
+      }
+    }
+  }
+  if (t == 0) wc_mark(p.dbg, 1);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // the leader's last MMAs have read the peer's shared memory; both epilogues are done
+  if (warp == W_MMA) tmem_dealloc2(td, cfg::TMEM_COLS);
+}
+
 // ---- operand packing: fp32 matrix -> bf16 hi/lo K-major SWIZZLE_64B images -------------------------------
 // image(kb)[n][k in 32] = src(n, kb*32 + k);  one thread per 16-byte chunk (8 k's of one n).
 // mode 0: src(n,k) = M[k*ld + n] (K3: T^T);  mode 1: src(n,k) = M[n*ld + k] (K6 term 1: T);
@@ -379,10 +667,36 @@ int launch_tc_apply_r(const TcApplyParams& p, const CUtensorMap& tm_a0, const CU
 }
 
 template <int C>
+int launch_tc_apply2(const TcApplyParams& p, const CUtensorMap& tm_a0, const CUtensorMap& tm_a1, const CUtensorMap& tm_out,
+                     cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    WC_CUDA(cudaFuncSetAttribute(tc_apply2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<C>::SMEM));
+    attr_set = true;
+  }
+  const long long pairs = p.total_tiles < WC_NUM_SMS / 2 ? p.total_tiles : WC_NUM_SMS / 2;
+  WC_CUDA(wc_launch_cluster(tc_apply2_kernel<C>, (unsigned)(2 * pairs), NTHREADS, Cfg2<C>::SMEM, st, 2, p, tm_a0, tm_a1, tm_out));
+  WC_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int C>
 int launch_tc_apply(TcApplyParams& p, const float* a0, const float* a1, float* out, int N, int HW, cudaStream_t st) {
   const bool cond = p.cls != nullptr && p.K > 1;
   if (!cond) { HW = N * HW; N = 1; p.cls = nullptr; }
   p.N = N; p.HW = HW;
+  if (wc_debug_flags() & 2097152) {
+    // CTA pairs: a pair tile is 256 rows of one sample
+    p.tiles_per_sample = wc_cdiv(HW, 2 * TILE_M);
+    p.total_tiles = (long long)N * p.tiles_per_sample;
+    p.dbg = wc_debug_buf(); p.dbg_flags = wc_debug_flags();
+    alignas(64) CUtensorMap tm_a0, tm_a1, tm_out;
+    int rc = make_act_map(&tm_a0, a0, N, HW, C);
+    if (!rc) rc = make_act_map(&tm_a1, a1 ? a1 : a0, N, HW, C);
+    if (!rc) rc = make_act_map(&tm_out, out, N, HW, C);
+    if (rc) return rc;
+    return launch_tc_apply2<C>(p, tm_a0, tm_a1, tm_out, st);
+  }
   p.tiles_per_sample = wc_cdiv(HW, TILE_M);
   p.total_tiles = (long long)N * p.tiles_per_sample;
   p.dbg = wc_debug_buf(); p.dbg_flags = wc_debug_flags();

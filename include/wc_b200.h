@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define WC_B200_VERSION 101
+#define WC_B200_VERSION 102
 
 #define WC_E_ARG        (-1)  /* null pointer / non-positive size / C % g != 0 */
 #define WC_E_WORKSPACE  (-2)  /* workspace too small */
@@ -201,6 +201,10 @@ typedef struct WcLayerCall {
   int32_t N, HW, Cin, Cout, g, K, E;
   int32_t whiten, decomposition, renorm, training, triangular;
   int32_t phases, use_tensor_cores;
+  int32_t relu;                 /* 1: y = max(0, .) -- the Activation('relu') that follows every WC layer in the reference's
+                                   blocks (gan/layer_utils.py:170,178; generator.py:155) applied in K3's epilogue.  Backward then
+                                   expects dy already multiplied by the mask (y > 0).                                          */
+  int32_t reserved0;
   float eps, momentum;
   double count;                 /* rows of the global batch; count_dev[0] overrides it when non-NULL */
   const float* count_dev;

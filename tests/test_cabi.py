@@ -22,7 +22,7 @@ def test_header_symbols_exported():
     for n in names:
         assert hasattr(_lib.lib, n), f'{n} declared in include/wc_b200.h but not exported'
     assert set(names) == set(_lib.EXPORTS), 'ctypes signatures and header disagree'
-    assert _lib.lib.wc_version() == 101
+    assert _lib.lib.wc_version() == 102
     # the diagnostic entry points are declared too (include/wc_b200_debug.h), and nothing else is exported
     dbg = re.sub(r'/\*.*?\*/', '', open(os.path.join(ROOT, 'include', 'wc_b200_debug.h')).read(), flags=re.S)
     dbg_names = sorted(set(re.findall(r'\b(wc_[a-z0-9_]+)\s*\(', dbg)))

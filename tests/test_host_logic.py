@@ -26,6 +26,9 @@ def test_stage_sequence(stubbed, norm, after_norm, c):
     stack.train()
     y = stack(x, cls)
     assert y.shape == x.shape
+    if norm == 'n' and after_norm == 'n':                         # generator.py:19-20,79-80: the identity, no pass at all
+        assert stubbed == [] and y is x
+        return
     assert [n for n, _ in stubbed] == ['wc_layer_fwd']            # one foreign call per direction
     call = stubbed[0][1][0]._obj
     assert call.phases == 3 and call.training == 1

@@ -9,6 +9,13 @@ from .functional import WCSpec, whitening_coloring, new_info
 from .layers import (ConditionalConv11, Conv11, DecorelationNormalization, FactorizedConv11,
                      WhiteningColoring, create_norm)
 
-__all__ = ['WCSpec', 'whitening_coloring', 'new_info', 'ConditionalConv11', 'Conv11',
+from .blocks import DCBlock, Discriminator, Generator, ResBlock, make_discriminator, make_generator
+from .spectral import SNConditionalConv11, SNConv11, SNFactorizedConv11, max_singular_val
+from .train import GanTrainer, discriminator_loss, generator_loss
+from . import checkpoint
+
+__all__ = ['ResBlock', 'DCBlock', 'Generator', 'Discriminator', 'make_generator', 'make_discriminator', 'SNConv11',
+           'SNConditionalConv11', 'SNFactorizedConv11', 'max_singular_val', 'GanTrainer', 'generator_loss',
+           'discriminator_loss', 'checkpoint', 'WCSpec', 'whitening_coloring', 'new_info', 'ConditionalConv11', 'Conv11',
            'DecorelationNormalization', 'FactorizedConv11', 'WhiteningColoring', 'create_norm']
 __version__ = '0.1.0'

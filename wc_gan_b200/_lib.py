@@ -37,7 +37,7 @@ lib = _load()
 class WcLayerCall(ctypes.Structure):
     """include/wc_b200.h: struct WcLayerCall (field order and types must match)."""
     _fields_ = ([(n, c_int32) for n in ('N', 'HW', 'Cin', 'Cout', 'g', 'K', 'E', 'whiten', 'decomposition', 'renorm',
-                                        'training', 'triangular', 'phases', 'use_tensor_cores')] +
+                                        'training', 'triangular', 'phases', 'use_tensor_cores', 'relu', 'reserved0')] +
                 [('eps', c_float), ('momentum', c_float), ('count', c_double)] +
                 [(n, c_void_p) for n in ('count_dev', 'Wu', 'bu', 'Wc', 'bc', 'class_matrix', 'D', 'bf', 'moving_mean',
                                          'moving_cov', 'cls', 'info', 'x', 'y', 'mean_ext', 'S_ext', 'dy', 'dx', 'dWu',
@@ -95,8 +95,8 @@ for _name, (_res, _args) in _SIGS.items():
 EXPORTS = tuple(_SIGS.keys())
 
 # the ctypes mirrors above must describe the structs the library was compiled with
-if lib.wc_version() != 101:
-    raise WcError(f'libwc_b200.so reports version {lib.wc_version()}, this package expects 101 (stale build?)')
+if lib.wc_version() != 102:
+    raise WcError(f'libwc_b200.so reports version {lib.wc_version()}, this package expects 102 (stale build?)')
 if (lib.wc_sizeof_layer_call() != ctypes.sizeof(WcLayerCall) or
         lib.wc_sizeof_saved_layout() != ctypes.sizeof(WcSavedLayout)):
     raise WcError('WcLayerCall / WcSavedLayout layout mismatch between include/wc_b200.h and wc_gan_b200/_lib.py')

@@ -29,6 +29,7 @@ struct ApplyParams {
   const int32_t* cls; int K; int32_t* info;
   float* out; int ldo;
   int tiles_per_sample;
+  int relu;                                      // 1: out = max(0, .)  (the activation that follows the WC layer, fused)
 };
 
 template <bool kVec>
@@ -166,11 +167,14 @@ __global__ void __launch_bounds__(NT) apply_kernel(ApplyParams p) {
     int r = ty * 4 + a;
     if (r >= rows_valid) continue;
     float* op = p.out + (row_base + r) * p.ldo + j;
+    float o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { o[q] = acc[a][q] + bb[q]; if (p.relu) o[q] = fmaxf(o[q], 0.f); }
     if (kVec && j + 3 < jend) {
-      *reinterpret_cast<float4*>(op) = make_float4(acc[a][0] + bb[0], acc[a][1] + bb[1], acc[a][2] + bb[2], acc[a][3] + bb[3]);
+      *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
     } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) if (j + q < jend) op[q] = acc[a][q] + bb[q];
+      for (int q = 0; q < 4; ++q) if (j + q < jend) op[q] = o[q];
     }
   }
 }
@@ -190,7 +194,7 @@ int launch_apply(ApplyParams& p, bool vec, cudaStream_t st) {
 }  // namespace
 
 int wc_tc_apply_fwd(const float* x, int N, int HW, int C, const float* mean, const void* packed, const float* b,
-                    const int32_t* cls, int K, float* y, int32_t* info, cudaStream_t st);
+                    const int32_t* cls, int K, float* y, int32_t* info, int relu, cudaStream_t st);
 int wc_tc_apply_bwd(const float* x, const float* dy, int N, int HW, int C, const float* mean, const void* packed,
                     bool has_A, const float* cvec, const int32_t* cls, int K, float* dx, cudaStream_t st);
 bool wc_tc_apply_ok(int Cin, int Cout);
@@ -198,16 +202,22 @@ bool wc_tc_apply_ok(int Cin, int Cout);
 extern "C" int wc_apply_fwd(const float* x, int N, int HW, int Cin, int Cout, const float* mean, const float* T,
                             const void* T_packed, const float* b, const int32_t* cls, int K, int band, float* y,
                             int32_t* info, wc_stream_t stream) {
+  return wc_apply_fwd_impl(x, N, HW, Cin, Cout, mean, T, T_packed, b, cls, K, band, y, info, 0, (cudaStream_t)stream);
+}
+
+// relu != 0: y = max(0, .), the Activation('relu') that follows every WC layer (gan/layer_utils.py:170,178; generator.py:155)
+int wc_apply_fwd_impl(const float* x, int N, int HW, int Cin, int Cout, const float* mean, const float* T, const void* T_packed,
+                      const float* b, const int32_t* cls, int K, int band, float* y, int32_t* info, int relu, cudaStream_t stream) {
   if (!x || !T || !y || N <= 0 || HW <= 0 || Cin <= 0 || Cout <= 0 || K <= 0) return WC_E_ARG;
   if ((int64_t)N * HW > (int64_t)INT32_MAX) return WC_E_UNSUPPORTED;
   if (T_packed && wc_tc_apply_ok(Cin, Cout) && wc_aligned16(x) && wc_aligned16(y) && wc_aligned16(T_packed) &&
       (!mean || wc_aligned16(mean)))
-    return wc_tc_apply_fwd(x, N, HW, Cin, mean, T_packed, b, cls, K, y, info, (cudaStream_t)stream);
+    return wc_tc_apply_fwd(x, N, HW, Cin, mean, T_packed, b, cls, K, y, info, relu, (cudaStream_t)stream);
   ApplyParams p{};
   p.t1 = Term{x, Cin, mean, T, (long long)Cin * Cout, Cout, 1, Cin, band, 0};
   p.nterms = 1;
   p.bias = b; p.bias_slot_stride = Cout; p.bias_sign = 1.f;
-  p.N = N; p.HW = HW; p.Nout = Cout; p.cls = cls; p.K = K; p.info = info; p.out = y; p.ldo = Cout;
+  p.N = N; p.HW = HW; p.Nout = Cout; p.cls = cls; p.K = K; p.info = info; p.out = y; p.ldo = Cout; p.relu = relu;
   bool vec = (Cin % 4 == 0) && (Cout % 4 == 0) && (band <= 0 || band % 4 == 0) && wc_aligned16(x) && wc_aligned16(T) &&
              wc_aligned16(y) && (!mean || wc_aligned16(mean));
   return launch_apply(p, vec, (cudaStream_t)stream);

@@ -152,6 +152,9 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
                  const float* count_dev, double count_host, float eps, void* Tp_bwd, int pack_K, float* ws_color,
                  float* ws_factor, unsigned* barrier, int stage_lo, int stage_hi, cudaStream_t st);
 
+int wc_apply_fwd_impl(const float* x, int N, int HW, int Cin, int Cout, const float* mean, const float* T, const void* T_packed,
+                      const float* b, const int32_t* cls, int K, int band, float* y, int32_t* info, int relu, cudaStream_t stream);
+
 // peer-memory exchanges (wc_exchange.cu)
 int wc_stats_exchange(float* rec, float count_local, int C, int g, void* const* peers, void* state, int rank, int world, float eps,
                       float extra_eps, float momentum, float* moving_mean, float* moving_cov, float* Ashr, int32_t* info, cudaStream_t st);

@@ -180,8 +180,8 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
                            plain_u(c) ? c.Wu : nullptr, fwd_barrier, (cudaStream_t)stream);
   if (rc) return rc;
   const int band = (c.whiten && !has_coloring(c) && c.g < c.Cin) ? c.g : 0;
-  return wc_apply_fwd(c.x, c.N, c.HW, c.Cin, c.Cout, mean, at<float>(c.saved, L.T), Tp, plain_u(c) ? c.bu : at<float>(c.saved, L.b),
-                      conditional(c) ? c.cls : nullptr, c.K, band, c.y, c.info, stream);
+  return wc_apply_fwd_impl(c.x, c.N, c.HW, c.Cin, c.Cout, mean, at<float>(c.saved, L.T), Tp, plain_u(c) ? c.bu : at<float>(c.saved, L.b),
+                           conditional(c) ? c.cls : nullptr, c.K, band, c.y, c.info, c.relu, (cudaStream_t)stream);
 }
 
 extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {

@@ -50,6 +50,7 @@ struct TcApplyParams {
   int N, HW, tiles_per_sample;
   long long total_tiles;
   const int32_t* cls; int K; int32_t* info;
+  int relu;                                 // 1: out = max(0, .) in the epilogue
   int l2_load[2], l2_store;                 // L2 eviction priority of the activation loads per segment / of the output stores (wctc::l2_policy)
   unsigned long long* dbg; int dbg_flags;   // debug marks / experiment switches (0 in normal use)
 };
@@ -231,8 +232,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
           const float s = p.bias_sign;
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ebase + ((j ^ (row & 7)) << 4)), "f"(fmaf(s, bv.x, acc[4 * j])),
-                       "f"(fmaf(s, bv.y, acc[4 * j + 1])), "f"(fmaf(s, bv.z, acc[4 * j + 2])), "f"(fmaf(s, bv.w, acc[4 * j + 3])) : "memory");
+          float o0 = fmaf(s, bv.x, acc[4 * j]), o1 = fmaf(s, bv.y, acc[4 * j + 1]), o2 = fmaf(s, bv.z, acc[4 * j + 2]), o3 = fmaf(s, bv.w, acc[4 * j + 3]);
+          if (p.relu) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); o2 = fmaxf(o2, 0.f); o3 = fmaxf(o3, 0.f); }
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ebase + ((j ^ (row & 7)) << 4)), "f"(o0), "f"(o1), "f"(o2), "f"(o3) : "memory");
         }
         fence_proxy_async();
         asm volatile("bar.sync 2, %0;" ::"n"(NEPI));
@@ -523,8 +525,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply2_kernel(TcApplyParams p,
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
           const float s = p.bias_sign;
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ebase + ((j ^ (row & 7)) << 4)), "f"(fmaf(s, bv.x, acc[4 * j])),
-                       "f"(fmaf(s, bv.y, acc[4 * j + 1])), "f"(fmaf(s, bv.z, acc[4 * j + 2])), "f"(fmaf(s, bv.w, acc[4 * j + 3])) : "memory");
+          float o0 = fmaf(s, bv.x, acc[4 * j]), o1 = fmaf(s, bv.y, acc[4 * j + 1]), o2 = fmaf(s, bv.z, acc[4 * j + 2]), o3 = fmaf(s, bv.w, acc[4 * j + 3]);
+          if (p.relu) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); o2 = fmaxf(o2, 0.f); o3 = fmaxf(o3, 0.f); }
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ebase + ((j ^ (row & 7)) << 4)), "f"(o0), "f"(o1), "f"(o2), "f"(o3) : "memory");
         }
         fence_proxy_async();
         asm volatile("bar.sync 2, %0;" ::"n"(NEPI));
@@ -766,12 +769,12 @@ extern "C" int wc_pack_bwd(const float* T, const float* A, int C, int g, int K, 
 
 // called from wc_apply.cu
 int wc_tc_apply_fwd(const float* x, int N, int HW, int C, const float* mean, const void* packed, const float* b,
-                    const int32_t* cls, int K, float* y, int32_t* info, cudaStream_t st) {
+                    const int32_t* cls, int K, float* y, int32_t* info, int relu, cudaStream_t st) {
   TcApplyParams p{};
   p.seg[0] = TcSeg{mean, (const uint8_t*)packed, (long long)C * C * 4};
   p.nseg = 1;
   p.bias = b; p.bias_slot_stride = C; p.bias_sign = 1.f;
-  p.cls = cls; p.K = K; p.info = info;
+  p.cls = cls; p.K = K; p.info = info; p.relu = relu;
   const int l2 = wc_l2_mode();
   p.l2_load[0] = (l2 & 2) ? 2 : 0;    // x: last use of the forward pass
   p.l2_store = (l2 & 4) ? 2 : 0;      // y: written once, read by another layer much later

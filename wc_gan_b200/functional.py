@@ -36,6 +36,7 @@ class WCSpec:
     group_size: int = 0              # 0 = all channels (the reference); extension otherwise
     triangular: bool = False         # ConditionalConv11(triangular=True) :811-812
     number_of_classes: int = 1
+    relu: bool = False               # fuse the Activation('relu') that follows the layer (gan/layer_utils.py:170,178)
 
 
 # When set to a dict, every C-ABI call is bracketed by CUDA events on the launching stream:
@@ -196,6 +197,7 @@ class WhiteningColoringFn(torch.autograd.Function):
         c.N, c.HW, c.Cin, c.Cout, c.g, c.K, c.E = N, HW, Cin, Cout, g, K, E
         c.whiten, c.decomposition, c.renorm = int(spec.whiten), dec, int(spec.renorm)
         c.training, c.triangular = int(training), int(spec.triangular)
+        c.relu = int(spec.relu)
         c.use_tensor_cores = int(USE_TENSOR_CORES)
         c.eps, c.momentum = spec.epsilon, spec.momentum
         c.count = float(N * HW)
@@ -204,7 +206,7 @@ class WhiteningColoringFn(torch.autograd.Function):
         c.moving_mean, c.moving_cov = ptr(moving_mean), ptr(moving_cov)
         c.cls, c.info = ptr(cls), ptr(info)
         has = tuple(t is not None for t in (Wu, bu, Wc, bc, class_matrix, D, bf))
-        key = (N, HW, Cin, Cout, g, K, E, c.whiten, dec, c.renorm, c.training, c.triangular, c.use_tensor_cores, has)
+        key = (N, HW, Cin, Cout, g, K, E, c.whiten, dec, c.renorm, c.training, c.triangular, c.use_tensor_cores, has)   # relu changes no size
         saved_bytes, fws, bws, lay = _plan(c, key)
 
         saved = torch.empty(saved_bytes // 4, dtype=torch.float32, device=dev)
@@ -244,7 +246,8 @@ class WhiteningColoringFn(torch.autograd.Function):
         ctx.dims = (N, H, W_, Cin, Cout, g, K, E, bws)
         ctx.has = has
         ctx.stats_train = bool(spec.whiten and training)
-        ctx.save_for_backward(x, cls, Wu, bu, Wc, bc, class_matrix, D, bf, moving_mean)
+        ctx.relu = bool(spec.relu)
+        ctx.save_for_backward(x, cls, Wu, bu, Wc, bc, class_matrix, D, bf, moving_mean, y if spec.relu else None)
         return y
 
     @staticmethod
@@ -257,6 +260,10 @@ class WhiteningColoringFn(torch.autograd.Function):
         dev = x.device
         st = _stream()
         _need_cuda(dy, 'grad_output')
+        if ctx.relu:
+            # backward of the fused activation: one elementwise pass (dy, y -> dy); the kernels then see the gradient
+            # with respect to the pre-activation output
+            dy = dy * (ctx.saved_tensors[10] > 0)
         dy = dy.contiguous()
         G = Cin // g
 

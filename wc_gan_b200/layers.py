@@ -274,8 +274,11 @@ class WhiteningColoring(_LazyBuild):
     def __init__(self, norm, after_norm, number_of_classes=None, filters_emb=10, cls=None, name=None,
                  decomposition='cholesky', group_size=None, process_group=None, triangular=False,
                  uncoditional_conv_layer=None, conditional_conv_layer=None, factor_conv_layer=None,
-                 momentum=0.99, epsilon=1e-3):
+                 momentum=0.99, epsilon=1e-3, activation=None):
         super().__init__(name)
+        if activation not in (None, 'relu'):
+            raise ValueError("only activation='relu' can be fused into the WC layer")
+        self.activation = activation
         assert norm in ('n', 'd', 'dr')
         assert after_norm in ('uconv', 'cconv', 'ucconv', 'fconv', 'ufconv', 'n')
         self.norm, self.after_norm = norm, after_norm
@@ -332,12 +335,13 @@ class WhiteningColoring(_LazyBuild):
             if m is not self.npart:
                 w.update(m.weights())
         K = self.number_of_classes if self.after_norm in ('cconv', 'ucconv', 'fconv', 'ufconv') else 1
+        relu = self.activation == 'relu'
         if self.npart is not None:
-            spec = self.npart.spec(triangular=self.triangular, number_of_classes=K or 1)
+            spec = self.npart.spec(triangular=self.triangular, number_of_classes=K or 1, relu=relu)
             kw = dict(moving_mean=self.npart.moving_mean, moving_cov=self.npart.moving_variance,
                       group=self.npart.process_group)
         else:
-            spec = WCSpec(whiten=False, triangular=self.triangular, number_of_classes=K or 1)
+            spec = WCSpec(whiten=False, triangular=self.triangular, number_of_classes=K or 1, relu=relu)
             kw = {}
         conditional = self.after_norm in ('cconv', 'ucconv', 'fconv', 'ufconv')
         return whitening_coloring(x, spec=spec, training=self.training,
@@ -354,11 +358,14 @@ _OUT_OF_SCOPE = {
 def create_norm(norm, after_norm, cls=None, number_of_classes=None, filters_emb=10,
                 uncoditional_conv_layer=Conv11, conditional_conv_layer=ConditionalConv11,
                 factor_conv_layer=FactorizedConv11, decomposition='cholesky', group_size=None,
-                process_group=None):
+                process_group=None, activation=None):
     """generator.py:13-90.  Same flag vocabulary and call protocol:
 
         block_norm = create_norm('d', 'ufconv', cls=cls, number_of_classes=10, filters_emb=4)
         y = block_norm(axis=-1, name='Generator.0_bn1')(x)
+
+    ``activation='relu'`` (an addition) fuses the ReLU that every block applies right after the layer
+    (gan/layer_utils.py:170,178; generator.py:155) into the layer's output pass.
 
     ``cls`` may be a tensor, a zero-argument callable returning the current (N,1) int32 labels
     (the Keras Input tensor of generator.py:102 has no eager equivalent), or None when the
@@ -372,12 +379,39 @@ def create_norm(norm, after_norm, cls=None, number_of_classes=None, filters_emb=
         if flag in _OUT_OF_SCOPE and flag != 'n':
             raise NotImplementedError(_OUT_OF_SCOPE[flag] + ' is not part of the whitening-coloring hot path')
 
+    if norm == 'n' and after_norm == 'n':                                              # generator.py:19-20,79-80: identity
+        def identity_norm(axis, name):
+            return _Identity(activation)
+        return identity_norm
+
     def result_norm(axis, name):
         if axis not in (-1, 3):
             raise ValueError('the WC layer normalises the last (channel) axis of NHWC tensors')
         return WhiteningColoring(norm, after_norm, number_of_classes=number_of_classes, filters_emb=filters_emb,
                                  cls=cls, name=name, decomposition=decomposition, group_size=group_size,
                                  process_group=process_group, uncoditional_conv_layer=uncoditional_conv_layer,
-                                 conditional_conv_layer=conditional_conv_layer, factor_conv_layer=factor_conv_layer)
+                                 conditional_conv_layer=conditional_conv_layer, factor_conv_layer=factor_conv_layer,
+                                 activation=activation)
 
     return result_norm
+
+
+class _Identity(nn.Module):
+    """create_norm('n', 'n'): no normalisation, no coloring (the discriminator's default, discriminator.py:19)."""
+
+    def __init__(self, activation=None):
+        super().__init__()
+        self.activation = activation
+        self.built = True
+        self.npart = None
+
+    def build(self, dim, device):
+        pass
+
+    def check_info(self):
+        pass
+
+    def forward(self, x, cls=None):
+        if isinstance(x, (list, tuple)):
+            x = x[0]
+        return torch.relu(x) if self.activation == 'relu' else x

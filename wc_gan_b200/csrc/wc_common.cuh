@@ -122,10 +122,14 @@ int wc_smm_launch(const WcSmm& p, cudaStream_t st);
 
 // K1's finalize kernel can run K2's prep step in the same launch (single-process training, tensor-core path)
 struct WcPrepFuse { float eps, extra_eps, momentum; float* moving_mean; float* moving_cov; float* Ashr; };
+// raw accumulators of the tensor-core K1 (lower blocks of the pivot-shifted scatter, column sums, pivot): set by
+// wc_stats_fwd_impl when asked to leave the finalize step to the consumer (the peer-memory exchange kernel)
+struct WcRawStats { const float* partS; const float* psum; const float* pivot; };
 // zeroed_out (nullable): receives the address of 64 zeroed bytes inside the workspace (cleared by the accumulator memset of
 // the tensor-core path; NULL when that path is not taken) -- the grid-barrier counter of the forward chain launch
 int wc_stats_fwd_impl(const float* x, int64_t M, int C, int g, float* workspace, size_t workspace_bytes,
-                      float* mean, float* S, const WcPrepFuse* fuse, int* fused, unsigned** zeroed_out, cudaStream_t stream);
+                      float* mean, float* S, const WcPrepFuse* fuse, int* fused, unsigned** zeroed_out, WcRawStats* raw_out,
+                      cudaStream_t stream);
 int wc_factor_fwd_impl(const float* mean, const float* S, const float* count_dev, double count_host, int C, int g,
                        float eps, float momentum, int decomposition, int renorm, int training,
                        float* moving_mean, float* moving_cov, float* Weff, float* Wm, float* R, float* U,
@@ -150,14 +154,16 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
                  float* dWu, float* dbu, float* dWc, float* dbc, int triangular, const float* class_matrix, const float* ehat,
                  const float* D, int E, float* dD, float* dclass_matrix, float* dbf, float* red, float* A, float* cvec,
                  const float* count_dev, double count_host, float eps, void* Tp_bwd, int pack_K, float* ws_color,
-                 float* ws_factor, unsigned* barrier, int stage_lo, int stage_hi, cudaStream_t st);
+                 float* ws_factor, unsigned* barrier, int stage_lo, int stage_hi, void* const* xchg_peers, void* xchg_state,
+                 int xchg_rank, int xchg_world, int32_t* info, cudaStream_t st);
 
 int wc_apply_fwd_impl(const float* x, int N, int HW, int Cin, int Cout, const float* mean, const float* T, const void* T_packed,
                       const float* b, const int32_t* cls, int K, int band, float* y, int32_t* info, int relu, cudaStream_t stream);
 
 // peer-memory exchanges (wc_exchange.cu)
 int wc_stats_exchange(float* rec, float count_local, int C, int g, void* const* peers, void* state, int rank, int world, float eps,
-                      float extra_eps, float momentum, float* moving_mean, float* moving_cov, float* Ashr, int32_t* info, cudaStream_t st);
+                      float extra_eps, float momentum, float* moving_mean, float* moving_cov, float* Ashr, int32_t* info,
+                      const float* partS, const float* psum, const float* pivot, double M, cudaStream_t st);
 int wc_adjoint_exchange(float* red, int C, int g, void* const* peers, void* state, int rank, int world, int32_t* info,
                         cudaStream_t st);
 

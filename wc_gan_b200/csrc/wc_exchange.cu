@@ -16,34 +16,10 @@
 // reaching its target also means every local CTA has finished READING the local record, so the merged statistics may
 // overwrite it in place.  All CTAs of the grid must be co-resident (they spin): the grid is far below the SM count.
 #include "wc_common.cuh"
+#include "wc_xch.cuh"
 #include <stdlib.h>
 
 namespace {
-
-constexpr int XCH_CTAS = 32, XCH_THREADS = 512, XCH_MAXR = 16;
-constexpr size_t XCH_FLAG_BYTES = 1024;     // 2 directions x 2 slots x 16 ranks x u32 = 256 B, padded
-
-struct XchLayout { size_t fwd_floats, bwd_floats, fwd_off, bwd_off, total; };
-
-inline XchLayout xch_layout(int C, int g, int R) {
-  XchLayout L;
-  const size_t gg = (size_t)C * g;
-  L.fwd_floats = wc_align_up(C + gg + 1, 64);       // one padded shard record
-  L.bwd_floats = wc_align_up(gg + C, 64);
-  L.fwd_off = XCH_FLAG_BYTES;
-  L.bwd_off = L.fwd_off + 2 * (size_t)R * L.fwd_floats * 4;
-  L.total = L.bwd_off + 2 * (size_t)R * L.bwd_floats * 4;
-  return L;
-}
-
-__device__ __forceinline__ void red_release_sys_add(uint32_t* p, uint32_t v) {
-  asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
 struct XchParams {
   char* const* peers;        // device array of R pointers: every rank's exchange buffer (index = rank)
@@ -54,13 +30,9 @@ struct XchParams {
   int has_tail; float tail;  // forward: the record's last element (this shard's row count) is supplied by value
   int32_t* info;             // nullable: info[WC_INFO_XCHG_TIMEOUT] is set when a peer never arrived
   unsigned long long timeout_ns;   // bound of the spin (0 = wait forever)
+  unsigned long long* dbg;   // debug marks (nullptr in normal use): slots 28..31 of the mark buffer
+  int dbg_flags;
 };
-
-__device__ __forceinline__ unsigned long long xch_now() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 
 // push `src[0..n)` into slot [e & 1][rank] of every peer, signal, wait for all peers.  Returns the epoch.
 __device__ __forceinline__ uint32_t xch_push_wait(const XchParams& p, const float* __restrict__ src) {
@@ -77,6 +49,7 @@ __device__ __forceinline__ uint32_t xch_push_wait(const XchParams& p, const floa
   for (int q = 0; q < p.R; ++q) {
     const int r = (p.rank + 1 + q) % p.R;               // start with the neighbour: spreads the NVLink traffic
     float4* dst = reinterpret_cast<float4*>(p.peers[r] + rec_off);
+    if ((p.dbg_flags & 4194304) && r != p.rank) continue;     // experiment: no remote stores (the peers then time out / read stale data)
     // plain (coherent) loads: the same kernel later overwrites `src` in place with the merged result
     for (int i = b4 + t; i < e4; i += blockDim.x) dst[i] = reinterpret_cast<const float4*>(src)[i];
     if (blockIdx.x == gridDim.x - 1) {
@@ -88,6 +61,7 @@ __device__ __forceinline__ uint32_t xch_push_wait(const XchParams& p, const floa
       }
     }
   }
+  if (t == 0) wc_mark(p.dbg, 30);
   // release pattern: the CTA barrier orders every thread's stores before the signalling threads' release-RMW at
   // system scope (release is cumulative over what the barrier made visible); no per-thread system fence is needed
   __syncthreads();
@@ -108,6 +82,7 @@ __device__ __forceinline__ uint32_t xch_push_wait(const XchParams& p, const floa
     }
   }
   __syncthreads();
+  if (t == 0) wc_mark(p.dbg, 31);
   return e;
 }
 
@@ -125,6 +100,11 @@ __device__ __forceinline__ void xch_finish(const XchParams& p, uint32_t e) {
   }
 }
 
+// K1's raw accumulators (tensor-core path): when given, the exchange kernel computes the shard record itself -- the finalize
+// step of wc_stats_fwd, d = sum(x-p)/M, mean = p + d, S = S_p - M d d^T -- right before pushing it (one launch less on the
+// serial path of every synchronised layer)
+struct FinalizeSrc { const float* partS; const float* psum; const float* pivot; double M; };
+
 struct FwdMerge {
   int C, g;
   float eps, extra_eps, momentum;
@@ -133,8 +113,32 @@ struct FwdMerge {
   float* Ashr;       // out: shrunk covariance for the factorisation
 };
 
-__global__ void __launch_bounds__(XCH_THREADS) stats_exchange_kernel(XchParams p, FwdMerge m) {
+__global__ void __launch_bounds__(XCH_THREADS) stats_exchange_kernel(XchParams p, FwdMerge m, FinalizeSrc fin) {
   wc_pdl_wait();
+  if (threadIdx.x == 0) wc_mark(p.dbg, 28);
+  if (fin.partS) {
+    // every CTA finalizes exactly the slice of the record it is about to push (same float4 partition as xch_push_wait)
+    const int C = m.C, g = m.g;
+    const int n4 = p.n >> 2;
+    const int per = (n4 + gridDim.x - 1) / gridDim.x;
+    const int b = 4 * blockIdx.x * per, e2 = (blockIdx.x == gridDim.x - 1) ? p.n : min(p.n, b + 4 * per);
+    for (int i = b + threadIdx.x; i < e2; i += blockDim.x) {
+      float v;
+      if (i < C) {
+        v = (float)((double)fin.pivot[i] + (double)fin.psum[i] / fin.M);
+      } else if (i < C + C * g) {
+        const int idx = i - C, grp = idx / (g * g), rem = idx % (g * g);
+        const int ri = grp * g + rem / g, ci = grp * g + rem % g;
+        const double ddi = (double)fin.psum[ri] / fin.M, ddj = (double)fin.psum[ci] / fin.M;
+        v = (float)((double)fin.partS[(long long)max(ri, ci) * C + min(ri, ci)] - fin.M * ddi * ddj);
+      } else {
+        v = p.tail;
+      }
+      m.rec[i] = v;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) wc_mark(p.dbg, 29);
   const uint32_t e = xch_push_wait(p, m.rec);
   const int C = m.C, g = m.g;
   const long long total = (long long)C * g;
@@ -195,7 +199,7 @@ extern "C" size_t wc_exchange_bytes(int C, int g, int world) {
 
 // rec: mean | S | count of this shard (the count is passed by value); on return the merged record.  state: 4 zero-initialised
 // uint32 owned by the layer ({epoch, ticket} for forward, then backward).
-static unsigned long long xch_timeout_ns() {
+unsigned long long wc_xch_timeout_ns() {
   static const unsigned long long v = [] {
     const char* e = getenv("WC_B200_XCHG_TIMEOUT_MS");
     const long long ms = e ? atoll(e) : 10000;
@@ -206,16 +210,17 @@ static unsigned long long xch_timeout_ns() {
 
 int wc_stats_exchange(float* rec, float count_local, int C, int g, void* const* peers, void* state, int rank, int world, float eps,
                       float extra_eps, float momentum, float* moving_mean, float* moving_cov, float* Ashr, int32_t* info,
-                      cudaStream_t st) {
+                      const float* partS, const float* psum, const float* pivot, double M, cudaStream_t st) {
   if (!rec || !peers || !state || !moving_mean || !moving_cov || !Ashr || rank < 0 || rank >= world || world > XCH_MAXR) return WC_E_ARG;
   const XchLayout L = xch_layout(C, g, world);
   XchParams p{};
   p.peers = reinterpret_cast<char* const*>(peers); p.state = reinterpret_cast<uint32_t*>(state);
   p.rank = rank; p.R = world; p.dir = 0; p.data_off = L.fwd_off; p.slot_floats = L.fwd_floats;
   p.n = C + C * g + 1; p.has_tail = 1; p.tail = count_local;
-  p.info = info; p.timeout_ns = xch_timeout_ns();
+  p.info = info; p.timeout_ns = wc_xch_timeout_ns(); p.dbg = wc_debug_buf(); p.dbg_flags = wc_debug_flags();
   FwdMerge m{C, g, eps, extra_eps, momentum, moving_mean, moving_cov, rec, Ashr};
-  WC_CUDA(wc_launch(stats_exchange_kernel, XCH_CTAS, XCH_THREADS, 0, st, p, m));
+  FinalizeSrc fin{partS, psum, pivot, M};
+  WC_CUDA(wc_launch(stats_exchange_kernel, XCH_CTAS, XCH_THREADS, 0, st, p, m, fin));
   WC_CHECK_LAUNCH();
   return 0;
 }
@@ -228,7 +233,7 @@ int wc_adjoint_exchange(float* red, int C, int g, void* const* peers, void* stat
   p.peers = reinterpret_cast<char* const*>(peers); p.state = reinterpret_cast<uint32_t*>(state) + 2;
   p.rank = rank; p.R = world; p.dir = 1; p.data_off = L.bwd_off; p.slot_floats = L.bwd_floats;
   p.n = C * g + C;
-  p.info = info; p.timeout_ns = xch_timeout_ns();
+  p.info = info; p.timeout_ns = wc_xch_timeout_ns();
   WC_CUDA(wc_launch(adjoint_exchange_kernel, XCH_CTAS, XCH_THREADS, 0, st, p, red));
   WC_CHECK_LAUNCH();
   return 0;

@@ -374,15 +374,19 @@ extern "C" size_t wc_stats_workspace_bytes(int64_t M, int C, int g) {
 
 extern "C" int wc_stats_fwd(const float* x, int64_t M, int C, int g, float* workspace, size_t workspace_bytes,
                             float* mean, float* S, wc_stream_t stream) {
-  return wc_stats_fwd_impl(x, M, C, g, workspace, workspace_bytes, mean, S, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+  return wc_stats_fwd_impl(x, M, C, g, workspace, workspace_bytes, mean, S, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 // fuse (nullable): also run the prep step of wc_factor_fwd when the tensor-core path is taken; *fused reports whether
 // that happened (the caller then tells wc_factor_fwd_impl to skip its own prep launch)
 int wc_stats_fwd_impl(const float* x, int64_t M, int C, int g, float* workspace, size_t workspace_bytes,
-                      float* mean, float* S, const WcPrepFuse* fuse, int* fused, unsigned** zeroed_out, cudaStream_t stream) {
+                      float* mean, float* S, const WcPrepFuse* fuse, int* fused, unsigned** zeroed_out, WcRawStats* raw_out,
+                      cudaStream_t stream) {
+  // raw_out (nullable): on the tensor-core path, do NOT launch the finalize kernel; report where the raw accumulators are
+  // (raw_out->partS != NULL) and let the caller's next kernel finalize.  Otherwise raw_out->partS is NULL.
   if (fused) *fused = 0;
   if (zeroed_out) *zeroed_out = nullptr;
+  if (raw_out) *raw_out = WcRawStats{nullptr, nullptr, nullptr};
   if (!x || !workspace || !mean || !S || M <= 0 || C <= 0 || g <= 0 || C % g) return WC_E_ARG;
   if (M > (int64_t)INT32_MAX) return WC_E_UNSUPPORTED;
   StatsPlan pl = plan_stats(M, C, g);
@@ -402,6 +406,7 @@ int wc_stats_fwd_impl(const float* x, int64_t M, int C, int g, float* workspace,
     int rc = wc_tc_gram_self(x, M, C, g, pivot, pS, psum, st);
     if (rc) return rc;
     long long tot = (long long)C * g;
+    if (raw_out) { *raw_out = WcRawStats{pS, psum, pivot}; return 0; }
     if (fuse) {
       WC_CUDA(wc_launch(stats_finalize_prep_kernel, wc_cdiv(tot, 256), 256, 0, st, pS, psum, C, g, (double)M, pivot, mean, S, *fuse));
       WC_CHECK_LAUNCH();

@@ -131,6 +131,7 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
 
   int prep_done = 0;
   unsigned* fwd_barrier = nullptr;       // zeroed by K1's accumulator memset: grid-barrier counter of the K2b chain launch
+  WcRawStats raw{nullptr, nullptr, nullptr};   // peer-memory exchange: K1's finalize step runs inside the exchange kernel
   if ((c.phases & WC_PHASE_STATS) && train_w) {
     // single process, no renorm: the finalize kernel of the statistics also scales / shrinks the covariance and
     // updates the moving averages (K2's prep step), one launch less on the serial path
@@ -138,7 +139,8 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
     WcPrepFuse f{c.eps, c.decomposition == WC_DECOMP_ZCA ? c.eps : 0.f, c.momentum, c.moving_mean, c.moving_cov,
                  at<float>(c.workspace, W.factor)};
     rc = wc_stats_fwd_impl(c.x, M, c.Cin, c.g, at<float>(c.workspace, W.stats), W.stats_bytes, at<float>(c.saved, L.mean),
-                           at<float>(c.saved, L.S), can_fuse ? &f : nullptr, &prep_done, &fwd_barrier, (cudaStream_t)stream);
+                           at<float>(c.saved, L.S), can_fuse ? &f : nullptr, &prep_done, &fwd_barrier, xchg_fwd(c) ? &raw : nullptr,
+                           (cudaStream_t)stream);
     if (rc) return rc;
   }
   if (!(c.phases & WC_PHASE_APPLY)) return 0;
@@ -148,7 +150,8 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
     // shard record -> every rank; Chan merge + prep from the complete set; saved mean | S | count become global
     rc = wc_stats_exchange(at<float>(c.saved, L.rec), (float)c.count, c.Cin, c.g, c.xchg_peers, c.xchg_state, c.xchg_rank,
                            c.xchg_world, c.eps, c.decomposition == WC_DECOMP_ZCA ? c.eps : 0.f, c.momentum, c.moving_mean,
-                           c.moving_cov, at<float>(c.workspace, W.factor), c.info, (cudaStream_t)stream);
+                           c.moving_cov, at<float>(c.workspace, W.factor), c.info, raw.partS, raw.psum, raw.pivot, (double)M,
+                           (cudaStream_t)stream);
     if (rc) return rc;
     prep_done = 1;
     count_dev = at<float>(c.saved, L.rec_count);
@@ -214,11 +217,12 @@ extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
   const float* count_dev = c.count_dev;
   const bool xb = stats_grad && xchg_bwd(c);
   if (xb) count_dev = at<float>(c.saved, L.rec_count);       // global row count, left there by the forward exchange
-  auto chain = [&](int lo, int hi) {
+  auto chain = [&](int lo, int hi, bool exchange) {
     return wc_bwd_chain(P, s, at<float>(c.saved, L.Weff), Wk, c.Cin, c.Cout, g, c.K, c.dWu, c.dbu, c.dWc, c.dbc, c.triangular,
                         c.class_matrix, at<float>(c.saved, L.ehat), c.D, c.E, c.dD, c.dclass_matrix, c.dbf, c.red, A, cvec,
                         count_dev, c.count, c.eps, at<void>(c.saved, L.Tp_bwd), c.K, at<float>(c.workspace, W.color),
-                        at<float>(c.workspace, W.factor), barrier, lo, hi, (cudaStream_t)stream);
+                        at<float>(c.workspace, W.factor), barrier, lo, hi, exchange ? c.xchg_peers : nullptr,
+                        exchange ? c.xchg_state : nullptr, c.xchg_rank, c.xchg_world, c.info, (cudaStream_t)stream);
   };
   bool chained = false, all_done = false;
   if (c.phases & WC_PHASE_REDUCE) {
@@ -226,11 +230,12 @@ extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
                             W.reduce_bytes, CHAIN_TAIL, (cudaStream_t)stream);
     if (rc) return rc;
     if (chain_ok) {
-      const bool whole = (c.phases & WC_PHASE_DX) && c.dx && !xb;
-      rc = chain(0, whole ? 4 : 1);
-      if (rc == 0) chained = true;
-      else if (rc != WC_E_UNSUPPORTED) return rc;
-      all_done = chained && whole;
+      // one launch for the whole chain; with the adjoint exchanged over peer memory, the all-reduce is a stage of it
+      const bool whole = (c.phases & WC_PHASE_DX) && c.dx;
+      rc = chain(0, whole ? 4 : 1, whole && xb);
+      if (rc == WC_E_UNSUPPORTED && whole && xb) { rc = chain(0, 1, false); if (rc == 0) { chained = true; } }
+      else if (rc == 0) { chained = true; all_done = whole; }
+      if (rc && rc != WC_E_UNSUPPORTED) return rc;
     }
     if (!chained) {
       rc = wc_color_bwd(P, s, at<float>(c.saved, L.Weff), Wk, c.Cin, c.Cout, g, c.K, c.dWu, c.dbu, c.dWc,
@@ -248,7 +253,7 @@ extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
   if (stats_grad && !all_done) {
     rc = WC_E_UNSUPPORTED;
     // (the barrier counter is still zero here: a one-stage launch never touches it)
-    if (chain_ok && (chained || !(c.phases & WC_PHASE_REDUCE))) rc = chain(1, 4);
+    if (chain_ok && (chained || !(c.phases & WC_PHASE_REDUCE))) rc = chain(1, 4, false);
     if (rc == WC_E_UNSUPPORTED)
       rc = wc_factor_bwd_impl(c.red, c.red + gg, at<float>(c.saved, L.Weff), at<float>(c.saved, L.Wm), at<float>(c.saved, L.R),
                               at<float>(c.saved, L.U), at<float>(c.saved, L.lam), count_dev, c.count, c.Cin, g, c.eps,

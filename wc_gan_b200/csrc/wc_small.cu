@@ -5,6 +5,7 @@
 // averages, shrinkage, renorm, test path), generator.py:41-78 + conditional_layers.py:811-819,
 // :993-1005 (per-class kernels), and TF autodiff of all of them.
 #include "wc_common.cuh"
+#include "wc_xch.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <stddef.h>
@@ -324,6 +325,15 @@ struct BuildJob {
   float *ehat, *Wk, *b;
   int Cin, Cout, K, E, triangular, identity;
 };
+// synchronised batch: the adjoint {dWeff, gbar} is all-reduced over peer memory BEFORE stage `stage` of the launch, inside
+// the kernel (same slots, flags and epochs as adjoint_exchange_kernel in wc_exchange.cu, so the two can alternate)
+struct ChainXch {
+  char* const* peers; uint32_t* state;     // device array of R exchange buffers; this rank's {epoch, ticket} of the direction
+  float* red; int n;                       // the floats to sum over ranks (in place)
+  int32_t* info; unsigned long long timeout_ns;
+  size_t data_off, slot_floats;
+  int rank, R, stage;                      // R <= 1: no exchange
+};
 struct ChainEnt { short type, idx, stage, pad; int v0, n; };
 // one tiled product of the chain, everything the tile routine needs in 32-bit form (all strides in elements)
 struct TJob {
@@ -339,7 +349,7 @@ struct TJob {
   float alpha;
 };
 struct ChainProgram {
-  TJob smm[CH_MAXSMM]; VecJob vec[CH_MAXVEC]; EltJob elt[CH_MAXELT]; BuildJob build;
+  TJob smm[CH_MAXSMM]; VecJob vec[CH_MAXVEC]; EltJob elt[CH_MAXELT]; BuildJob build; ChainXch xch;
   ChainEnt ent[CH_MAXSMM + CH_MAXVEC + CH_MAXELT];
   int nent, nstages;
   int prewait;                       // stages [0, prewait) read nothing the preceding kernel writes: they run before the dependency wait
@@ -675,10 +685,47 @@ __global__ void __launch_bounds__(SMM_THREADS, 1) chain_kernel(const __grid_cons
     if (v == 0x7fffffff) s_sink = v;       // never true for a pointer / count word in practice; keeps the load alive
   }
   bool waited = false;
+  unsigned nbar = 0;
   for (int s = 0; s < pr.nstages; ++s) {
     if (s > 0) {
       if (threadIdx.x == 0 && s < 4) wc_mark(pr.dbg, 7 + 2 * s);      // own jobs of stage s-1 done
-      chain_grid_barrier(pr.barrier, (unsigned)s * gridDim.x);
+      chain_grid_barrier(pr.barrier, ++nbar * gridDim.x);
+      if (pr.xch.R > 1 && s == pr.xch.stage) {
+        // ---- all-reduce of `red` over the ranks of the node: push my slices into slot [epoch & 1][rank] of every peer ...
+        const ChainXch& x = pr.xch;
+        const uint32_t e = *reinterpret_cast<volatile uint32_t*>(x.state), slot = e & 1u;
+        const size_t rec_off = x.data_off + ((size_t)slot * x.R + x.rank) * x.slot_floats * 4;
+        const int n4 = x.n >> 2;                       // n is a multiple of 4 (C and g are multiples of 32 on this path)
+        for (int q = 0; q < x.R; ++q) {
+          const int r = (x.rank + 1 + q) % x.R;        // start with the neighbour: spreads the NVLink traffic
+          float4* dst = reinterpret_cast<float4*>(x.peers[r] + rec_off);
+          for (int i = blockIdx.x * SMM_THREADS + threadIdx.x; i < n4; i += gridDim.x * SMM_THREADS)
+            dst[i] = __ldcg(reinterpret_cast<const float4*>(x.red) + i);
+        }
+        __threadfence_system();                        // my peer stores are performed before anyone signals for this rank
+        chain_grid_barrier(pr.barrier, ++nbar * gridDim.x);
+        // ... one CTA signals for the whole grid (as XCH_CTAS arrivals: the stand-alone kernel's protocol), everyone waits ...
+        const size_t flag_off = ((size_t)1 * 2 + slot) * XCH_MAXR * 4;
+        if (blockIdx.x == 0 && threadIdx.x < x.R)
+          red_release_sys_add(reinterpret_cast<uint32_t*>(x.peers[threadIdx.x] + flag_off) + x.rank, (uint32_t)XCH_CTAS);
+        if (threadIdx.x < x.R) {
+          const uint32_t* f = reinterpret_cast<const uint32_t*>(x.peers[x.rank] + flag_off) + threadIdx.x;
+          if (!xch_spin(f, (uint32_t)XCH_CTAS * (e / 2u + 1u), x.timeout_ns) && x.info) atomicMax(&x.info[WC_INFO_XCHG_TIMEOUT], 1 + (int)threadIdx.x);
+        }
+        __syncthreads();
+        // ... and sums the R slots in rank order (bit-identical on every rank), in place
+        const float* base = reinterpret_cast<const float*>(x.peers[x.rank] + x.data_off + (size_t)slot * x.R * x.slot_floats * 4);
+        for (int i = blockIdx.x * SMM_THREADS + threadIdx.x; i < n4; i += gridDim.x * SMM_THREADS) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int r = 0; r < x.R; ++r) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(base + (size_t)r * x.slot_floats) + i);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+          }
+          reinterpret_cast<float4*>(x.red)[i] = a;
+        }
+        chain_grid_barrier(pr.barrier, ++nbar * gridDim.x);
+        if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(x.state) = e + 1;   // every CTA read it above
+      }
       if (threadIdx.x == 0 && s < 4) wc_mark(pr.dbg, 8 + 2 * s);      // barrier passed
     }
     if (!waited && s >= pr.prewait) {
@@ -1624,7 +1671,8 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
                  float* dWu, float* dbu, float* dWc, float* dbc, int triangular, const float* class_matrix, const float* ehat,
                  const float* D, int E, float* dD, float* dclass_matrix, float* dbf, float* red, float* A, float* cvec,
                  const float* count_dev, double count_host, float eps, void* Tp_bwd, int pack_K, float* ws_color,
-                 float* ws_factor, unsigned* barrier, int stage_lo, int stage_hi, cudaStream_t st) {
+                 float* ws_factor, unsigned* barrier, int stage_lo, int stage_hi, void* const* xchg_peers, void* xchg_state,
+                 int xchg_rank, int xchg_world, int32_t* info, cudaStream_t st) {
   if (!P || !s || !Weff || !Wk || !red || !barrier || Cin != Cout || g <= 0 || Cin % g) return WC_E_UNSUPPORTED;
   if (triangular && dWc) return WC_E_UNSUPPORTED;
   if ((dD || dclass_matrix) && (!class_matrix || !ehat || !D || E <= 0)) return WC_E_ARG;
@@ -1642,6 +1690,15 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
   if (dWc) Qdst = dWc; else if (K == 1 && dWu) Qdst = dWu;
   ChainBuilder cb;
   cb.pr.count_dev = count_dev; cb.pr.count_host = ch;
+  if (xchg_peers && xchg_state && xchg_world > 1) {
+    // the adjoint is all-reduced between stage 0 and stage 1 inside the launch (needs both in this launch)
+    if (!(stage_lo == 0 && stage_hi > 1) || xchg_world > XCH_MAXR || ((C * g + C) & 3)) return WC_E_UNSUPPORTED;
+    const XchLayout XL = xch_layout(C, g, xchg_world);
+    ChainXch& x = cb.pr.xch;
+    x.peers = reinterpret_cast<char* const*>(xchg_peers); x.state = reinterpret_cast<uint32_t*>(xchg_state) + 2;
+    x.red = red; x.n = C * g + C; x.info = info; x.timeout_ns = wc_xch_timeout_ns();
+    x.data_off = XL.bwd_off; x.slot_floats = XL.bwd_floats; x.rank = xchg_rank; x.R = xchg_world; x.stage = 1;
+  }
   auto in = [&](int stage) { return stage >= stage_lo && stage < stage_hi; };
   const int base = stage_lo;     // stages are renumbered from 0 inside the launch
   if (in(0)) {

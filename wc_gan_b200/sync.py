@@ -73,7 +73,12 @@ class PeerExchange:
 
     def __init__(self, buf, handle, state, rank, world):
         self.buf, self.handle, self.state, self.rank, self.world = buf, handle, state, rank, world
-        self.peers_dev = int(handle.buffer_ptrs_dev)      # device array of `world` buffer pointers, rank order
+        # device array of `world` buffer pointers, rank order.  A copy in ordinary device memory: the kernels read it on
+        # their serial path, and the allocator's own table (handle.buffer_ptrs_dev) measured ~17 us per exchange to read
+        # (scratch/xchtime.py: "pushed" 23 us after the kernel start with or without remote stores)
+        ptrs = [int(p) for p in handle.buffer_ptrs]
+        self.peer_table = torch.tensor(ptrs, dtype=torch.int64, device=buf.device)
+        self.peers_dev = self.peer_table.data_ptr()
 
 
 _EXCHANGES = {}      # (process group object, C, g, device index) -> PeerExchange | None

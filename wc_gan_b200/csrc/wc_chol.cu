@@ -529,10 +529,10 @@ __device__ void warp_potrf32_bc(float* T, float* rdiag, uint64_t* colbar, int la
   float dg = T[lane * TP + lane];
   __syncwarp();                                   // every lane holds its row before columns are overwritten
   float piv = __shfl_sync(FULL, dg, 0);
+  if (!(piv > 0.f)) { if (!bad) bad = 1; piv = 1e-30f; }
+  float rs = rsqrt_approx(piv);
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
-    if (!(piv > 0.f)) { if (!bad) bad = k + 1; piv = 1e-30f; }
-    const float rs = rsqrt_approx(piv);
     const float lk = (lane == k) ? piv * rs : a[k] * rs;
     if (lane == k) rdiag[k] = rs;
     T[k * TP + lane] = (lane >= k) ? lk : 0.f;    // final column k (zero above the diagonal)
@@ -541,6 +541,10 @@ __device__ void warp_potrf32_bc(float* T, float* rdiag, uint64_t* colbar, int la
       piv = __shfl_sync(FULL, dg, k + 1);                  // lane k+1's diagonal is final after column k
       const float lnext = __shfl_sync(FULL, lk, k + 1);    // L[k+1][k]
       a[k + 1] = fmaf(-lk, lnext, a[k + 1]);
+      // the reciprocal square root of the NEXT pivot is started here, so that its latency (the longest link of the
+      // per-column chain) runs under the trailing update below instead of at the top of the next column
+      if (!(piv > 0.f)) { if (!bad) bad = k + 2; piv = 1e-30f; }
+      rs = rsqrt_approx(piv);
     }
     __syncwarp();
     if (colbar && lane == 0) cta_mbar_arrive(&colbar[k]);

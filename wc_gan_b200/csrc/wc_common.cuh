@@ -171,6 +171,10 @@ int wc_adjoint_exchange(float* red, int C, int g, void* const* peers, void* stat
 int wc_make_f32_map3(void* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
 
+// Jacobi eigensolvers of the ZCA path (wc_jacobi.cu)
+size_t wc_jacobi_sync_bytes(int C, int g);
+int wc_jacobi_launch(const float* L, int C, int g, float* Bm, float* U, float* lam, unsigned* sync, int32_t* info, cudaStream_t st);
+
 // tiled Cholesky + inverse (wc_chol.cu)
 size_t wc_chol_pad_floats(int C, int g);
 int wc_chol_inv_launch(const float* Ain, int C, int g, float* Lout, float* Xout, float* Xpad, int32_t* info, cudaStream_t st);

@@ -1197,20 +1197,23 @@ extern "C" size_t wc_factor_workspace_bytes(int C, int g, int decomposition, int
   size_t n = 2;
   if (decomposition == WC_DECOMP_ZCA) n += 2;
   if (renorm) n += 4;
-  return n * gg_bytes(C, g) + wc_align_up(wc_chol_pad_floats(C, g) * 4, 256);
+  return n * gg_bytes(C, g) + wc_align_up(wc_chol_pad_floats(C, g) * 4, 256) + wc_align_up(wc_jacobi_sync_bytes(C, g), 256);
 }
 
 namespace {
 // factor one (G,g,g) SPD matrix `Ashr` -> Wm (inverse square root), optional sqrt factor, optional U/lam
 int factor_matrix(const float* Ashr, int C, int g, int decomposition, float* Wm, float* sqrt_out, float* U, float* lam,
-                  float* L /*scratch or output*/, float* Bm, float* Us, float* Xpad, int32_t* info, cudaStream_t st) {
+                  float* L /*scratch or output*/, float* Bm, float* Us, float* Xpad, unsigned* jsync, int32_t* info, cudaStream_t st) {
   const int G = C / g;
   long long total = (long long)C * g;
   if (decomposition == WC_DECOMP_CHOLESKY) return wc_chol_inv_launch(Ashr, C, g, sqrt_out, Wm, Xpad, info, st);   // L only on request
   int rcc = wc_chol_inv_launch(Ashr, C, g, L, nullptr, Xpad, info, st);
   if (rcc) return rcc;
-  WC_CUDA(wc_launch(jacobi_kernel, G, 1024, 0, st, L, g, Bm, U, lam, info));
-  WC_CHECK_LAUNCH();
+  int rcj = wc_jacobi_launch(L, C, g, Bm, U, lam, jsync, info, st);     // shared-memory / multi-CTA block Jacobi (wc_jacobi.cu)
+  if (rcj == WC_E_UNSUPPORTED) {                                          // 64 < g < 128, g not a multiple of 32: one-CTA kernel
+    WC_CUDA(wc_launch(jacobi_kernel, G, 1024, 0, st, L, g, Bm, U, lam, info));
+    WC_CHECK_LAUNCH();
+  } else if (rcj) return rcj;
   WC_CUDA(wc_launch(scale_cols_kernel, wc_cdiv(total, 256), 256, 0, st, U, lam, C, g, -0.25f, Us));
   WC_CHECK_LAUNCH();
   int rc = smm(smm_gg(Us, false, Us, true, Wm, g, G), st);
@@ -1258,6 +1261,7 @@ int wc_factor_fwd_impl(const float* mean, const float* S, const float* count_dev
   const bool zca = decomposition == WC_DECOMP_ZCA;
   if (zca) { Bm = reinterpret_cast<float*>(ws + off); Us = reinterpret_cast<float*>(ws + off + gb); off += 2 * gb; }
   float* Xpad = reinterpret_cast<float*>(ws + ((zca ? 4 : 2) + ((renorm && training) ? 4 : 0)) * gb);
+  unsigned* jsync = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(Xpad) + wc_align_up(wc_chol_pad_floats(C, g) * 4, 256));
   const float extra = zca ? eps : 0.f;   // conditional_layers.py:671 adds eps*I again on top of :691
   long long total = (long long)C * g;
   int rc;
@@ -1267,7 +1271,7 @@ int wc_factor_fwd_impl(const float* mean, const float* S, const float* count_dev
                                                             moving_mean, moving_cov, Ashr));
     WC_CHECK_LAUNCH();
     if (zca && (!U || !lam)) return WC_E_ARG;   // eigenvector / eigenvalue scratch is required in every phase
-    return factor_matrix(Ashr, C, g, decomposition, Weff, nullptr, U, lam, L, Bm, Us, Xpad, info, st);
+    return factor_matrix(Ashr, C, g, decomposition, Weff, nullptr, U, lam, L, Bm, Us, Xpad, jsync, info, st);
   }
   float *Amov = nullptr, *Wmov = nullptr, *Lb = nullptr, *Umov = nullptr;
   if (renorm) {
@@ -1278,7 +1282,7 @@ int wc_factor_fwd_impl(const float* mean, const float* S, const float* count_dev
                                                             moving_mean, moving_cov, Amov));
     WC_CHECK_LAUNCH();
     // lam scratch for the moving factor: reuse R's first C floats (R is written afterwards)
-    rc = factor_matrix(Amov, C, g, decomposition, Wmov, nullptr, Umov, R, L, Bm, Us, Xpad, info, st);
+    rc = factor_matrix(Amov, C, g, decomposition, Wmov, nullptr, Umov, R, L, Bm, Us, Xpad, jsync, info, st);
     if (rc) return rc;
   }
   if (!prep_done) {
@@ -1286,7 +1290,7 @@ int wc_factor_fwd_impl(const float* mean, const float* S, const float* count_dev
                                                             moving_mean, moving_cov, Ashr));
     WC_CHECK_LAUNCH();
   }
-  rc = factor_matrix(Ashr, C, g, decomposition, Wm, renorm ? Lb : nullptr, U, lam, L, Bm, Us, Xpad, info, st);
+  rc = factor_matrix(Ashr, C, g, decomposition, Wm, renorm ? Lb : nullptr, U, lam, L, Bm, Us, Xpad, jsync, info, st);
   if (rc) return rc;
   if (renorm) {
     rc = smm(smm_gg(Wmov, false, Lb, false, R, g, G), st);           // R = l_mov_inverse . stop_gradient(l)   (:697-698)

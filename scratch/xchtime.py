@@ -22,7 +22,7 @@ for i in range(3): step(i)          # back to back: the steady-state skew betwee
 torch.cuda.synchronize()
 buf = (ctypes.c_ulonglong * (160 * 32))()
 lib.wc_debug_marks(buf); lib.wc_debug_set(0)
-rows = [[buf[b * 32 + k] for k in range(28, 32)] for b in range(32) if buf[b * 32 + 28]]
+rows = [[buf[b * 32 + k] for k in range(28, 32)] for b in range(128) if buf[b * 32 + 28]]
 t0 = min(r[0] for r in rows)
 names = ['start', 'finalized', 'pushed', 'peers in']
 for r_ in range(world):

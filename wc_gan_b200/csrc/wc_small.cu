@@ -331,7 +331,7 @@ struct ChainXch {
   char* const* peers; uint32_t* state;     // device array of R exchange buffers; this rank's {epoch, ticket} of the direction
   float* red; int n;                       // the floats to sum over ranks (in place)
   int32_t* info; unsigned long long timeout_ns;
-  size_t data_off, slot_floats;
+  size_t data_off, slot_words;             // wc_xch.cuh: byte offset of the direction's slots, 8-byte words per (slot, rank)
   int rank, R, stage;                      // R <= 1: no exchange
 };
 struct ChainEnt { short type, idx, stage, pad; int v0, n; };
@@ -691,38 +691,34 @@ __global__ void __launch_bounds__(SMM_THREADS, 1) chain_kernel(const __grid_cons
       if (threadIdx.x == 0 && s < 4) wc_mark(pr.dbg, 7 + 2 * s);      // own jobs of stage s-1 done
       chain_grid_barrier(pr.barrier, ++nbar * gridDim.x);
       if (pr.xch.R > 1 && s == pr.xch.stage) {
-        // ---- all-reduce of `red` over the ranks of the node: push my slices into slot [epoch & 1][rank] of every peer ...
+        // ---- all-reduce of `red` over the ranks of the node (wc_xch.cuh): every thread pushes its elements, tagged, into
+        //      slot [epoch & 1][rank] of every rank's buffer and then sums the R words of the same elements from its own
+        //      buffer as they arrive, in rank order (bit-identical on every rank).  No flag, no fence, no extra grid barrier.
         const ChainXch& x = pr.xch;
-        const uint32_t e = *reinterpret_cast<volatile uint32_t*>(x.state), slot = e & 1u;
-        const size_t rec_off = x.data_off + ((size_t)slot * x.R + x.rank) * x.slot_floats * 4;
-        const int n4 = x.n >> 2;                       // n is a multiple of 4 (C and g are multiples of 32 on this path)
-        for (int q = 0; q < x.R; ++q) {
-          const int r = (x.rank + 1 + q) % x.R;        // start with the neighbour: spreads the NVLink traffic
-          float4* dst = reinterpret_cast<float4*>(x.peers[r] + rec_off);
-          for (int i = blockIdx.x * SMM_THREADS + threadIdx.x; i < n4; i += gridDim.x * SMM_THREADS)
-            dst[i] = __ldcg(reinterpret_cast<const float4*>(x.red) + i);
+        const uint32_t e = *reinterpret_cast<volatile uint32_t*>(x.state), slot = e & 1u, tag = e + 1u;
+        bool ok = true;
+        auto slot_of = [&](int buffer_of, int sender) {
+          return reinterpret_cast<unsigned long long*>(x.peers[buffer_of] + x.data_off) + ((size_t)slot * x.R + sender) * x.slot_words;
+        };
+        for (int i = blockIdx.x * SMM_THREADS + threadIdx.x; i < x.n; i += gridDim.x * SMM_THREADS) {
+          const float v = __ldcg(x.red + i);
+          for (int q = 0; q < x.R; ++q) ll_store(slot_of((x.rank + 1 + q) % x.R, x.rank) + i, v, tag);
         }
-        __threadfence_system();                        // my peer stores are performed before anyone signals for this rank
-        chain_grid_barrier(pr.barrier, ++nbar * gridDim.x);
-        // ... one CTA signals for the whole grid (as XCH_CTAS arrivals: the stand-alone kernel's protocol), everyone waits ...
-        const size_t flag_off = ((size_t)1 * 2 + slot) * XCH_MAXR * 4;
-        if (blockIdx.x == 0 && threadIdx.x < x.R)
-          red_release_sys_add(reinterpret_cast<uint32_t*>(x.peers[threadIdx.x] + flag_off) + x.rank, (uint32_t)XCH_CTAS);
-        if (threadIdx.x < x.R) {
-          const uint32_t* f = reinterpret_cast<const uint32_t*>(x.peers[x.rank] + flag_off) + threadIdx.x;
-          if (!xch_spin(f, (uint32_t)XCH_CTAS * (e / 2u + 1u), x.timeout_ns) && x.info) atomicMax(&x.info[WC_INFO_XCHG_TIMEOUT], 1 + (int)threadIdx.x);
-        }
-        __syncthreads();
-        // ... and sums the R slots in rank order (bit-identical on every rank), in place
-        const float* base = reinterpret_cast<const float*>(x.peers[x.rank] + x.data_off + (size_t)slot * x.R * x.slot_floats * 4);
-        for (int i = blockIdx.x * SMM_THREADS + threadIdx.x; i < n4; i += gridDim.x * SMM_THREADS) {
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int r = 0; r < x.R; ++r) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(base + (size_t)r * x.slot_floats) + i);
-            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        const unsigned long long* mine = slot_of(x.rank, 0);
+        for (int i = blockIdx.x * SMM_THREADS + threadIdx.x; i < x.n; i += gridDim.x * SMM_THREADS) {
+          float a = 0.f;
+          for (int r0 = 0; r0 < x.R; r0 += 4) {          // rank order, 4 words in flight
+            const unsigned long long* src[4]; float v[4];
+            const int cnt4 = min(4, x.R - r0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) src[k] = mine + (size_t)min(r0 + k, x.R - 1) * x.slot_words + i;
+            ll_load_many<4>(src, v, cnt4, tag, x.timeout_ns, &ok);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (k < cnt4) a += v[k];
           }
-          reinterpret_cast<float4*>(x.red)[i] = a;
+          x.red[i] = a;
         }
+        if (!ok && x.info) atomicMax(&x.info[WC_INFO_XCHG_TIMEOUT], 1);
         chain_grid_barrier(pr.barrier, ++nbar * gridDim.x);
         if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(x.state) = e + 1;   // every CTA read it above
       }
@@ -1696,12 +1692,12 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
   cb.pr.count_dev = count_dev; cb.pr.count_host = ch;
   if (xchg_peers && xchg_state && xchg_world > 1) {
     // the adjoint is all-reduced between stage 0 and stage 1 inside the launch (needs both in this launch)
-    if (!(stage_lo == 0 && stage_hi > 1) || xchg_world > XCH_MAXR || ((C * g + C) & 3)) return WC_E_UNSUPPORTED;
+    if (!(stage_lo == 0 && stage_hi > 1) || xchg_world > XCH_MAXR) return WC_E_UNSUPPORTED;
     const XchLayout XL = xch_layout(C, g, xchg_world);
     ChainXch& x = cb.pr.xch;
     x.peers = reinterpret_cast<char* const*>(xchg_peers); x.state = reinterpret_cast<uint32_t*>(xchg_state) + 2;
     x.red = red; x.n = C * g + C; x.info = info; x.timeout_ns = wc_xch_timeout_ns();
-    x.data_off = XL.bwd_off; x.slot_floats = XL.bwd_floats; x.rank = xchg_rank; x.R = xchg_world; x.stage = 1;
+    x.data_off = XL.bwd_off; x.slot_words = XL.bwd_words; x.rank = xchg_rank; x.R = xchg_world; x.stage = 1;
   }
   auto in = [&](int stage) { return stage >= stage_lo && stage < stage_hi; };
   const int base = stage_lo;     // stages are renumbered from 0 inside the launch

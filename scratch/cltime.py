@@ -12,9 +12,9 @@ torch.cuda.synchronize()
 buf = (ctypes.c_ulonglong * (8 * 32))()
 lib.wc_debug_chol_cluster_timing.argtypes = [ctypes.c_void_p]
 print('rc', lib.wc_debug_chol_cluster_timing(buf))
-ts = [[buf[r * 32 + i] for i in range(16)] for r in range(8)]
+ts = [[buf[r * 32 + i] for i in range(17)] for r in range(8)]
 base = min(t[0] for t in ts if t[0])
-names = ['start', 'loaded', 'waitB', 'gotB', 'trsm', 'rowdone', 'potrf0', 'potrf1', 'pubL', 'pubD', 'diagdone', 'waitA7', 'S7', 'gotD7', 'end', 'exit']
+names = ['start', 'loaded', 'waitB', 'gotB', 'trsm', 'rowdone', 'potrf0', 'potrf1', 'pubL', 'pubD', 'diagdone', 'waitA7', 'S7', 'gotD7', 'end', 'exit', 'invdone']
 print('      ' + ' '.join(f'{n:>8s}' for n in names))
 for r in range(8):
     print(f'cta {r} ' + ' '.join(f'{(t - base) if t else -1:8d}' for t in ts[r]))

@@ -444,6 +444,7 @@ constexpr int CLN = 8;                 // CTAs per cluster = maximum number of b
 constexpr int CLW = 8;                 // warps per CTA
 constexpr int GT = TB * TB;            // floats per published tile (column-major, pitch 32)
 __device__ unsigned long long g_cl_ts[CLN][32];
+#define CL_MARKW(i) do { if (dbg) { if (lane == 0 && grp == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); g_cl_ts[r][i] = t__; } __syncwarp(); } } while (0)
 #define CL_MARK(i) do { if (dbg) { if (lane == 0 && warp == 0 && grp == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); g_cl_ts[r][i] = t__; } __syncwarp(); } } while (0)
 
 __device__ __forceinline__ uint32_t cl_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -517,6 +518,11 @@ __device__ __forceinline__ void cta_mbar_wait0(uint64_t* bar) {     // one-shot 
       "CB_DONE:\n\t}" ::"r"(a) : "memory");
 }
 
+// Columns are announced to the follower in groups of four, singly for the last four: a wait per column made the follower
+// slower per step than the factorisation it follows (it fell 0.65 us behind by column 31); with a wait per group it runs
+// ahead of the announcements and ends about one column behind.
+__device__ __forceinline__ constexpr bool colbar_signalled(int k) { return (k & 3) == 3 || k >= 28; }
+
 // in-place lower Cholesky of a 32x32 tile by one warp (lane = row).  Column k of the factor is written to the tile as
 // soon as it is final -- it is at once the broadcast buffer for the trailing update of this warp (128-bit broadcast loads)
 // and, announced on colbar[k], the input of the warp that builds the inverse one column behind (warp_inverse_follow).
@@ -547,7 +553,7 @@ __device__ void warp_potrf32_bc(float* T, float* rdiag, uint64_t* colbar, int la
       rs = rsqrt_approx(piv);
     }
     __syncwarp();
-    if (colbar && lane == 0) cta_mbar_arrive(&colbar[k]);
+    if (colbar && lane == 0 && colbar_signalled(k)) cta_mbar_arrive(&colbar[k]);
     if (k < 30) {
       const float* b = T + k * TP;
 #pragma unroll
@@ -569,7 +575,9 @@ __device__ void warp_inverse_follow(float (&x)[32], const float* T, const float*
   for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.f : 0.f;
 #pragma unroll
   for (int m = 0; m < 32; ++m) {
-    if (colbar) cta_mbar_wait0(&colbar[m]);
+    // a group is consumed once its LAST column is announced
+    if (colbar && m < 28 && (m & 3) == 0) cta_mbar_wait0(&colbar[m + 3]);
+    if (colbar && m >= 28) cta_mbar_wait0(&colbar[m]);
     x[m] *= rdiag[m];
     const float xm = x[m];
 #pragma unroll
@@ -610,7 +618,7 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
                         float* __restrict__ Lout, float* __restrict__ Xout, int32_t* info, int dbg) {
   wc_pdl_wait();
   extern __shared__ __align__(16) float sm[];
-  __shared__ uint64_t flagA[CLN], flagA2[CLN], flagB[CLN], colbar[TB];
+  __shared__ uint64_t flagA[CLN], flagA2[CLN], flagB[CLN], colbar[TB], flagN, flagT;
   __shared__ __align__(16) float rd_own[TB], rd_warm[2 * TB];
   const int NB = g / TB;
   const int grp = blockIdx.x / CLN;
@@ -624,6 +632,7 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
   float* stg = stile + TS;               // CLN staged tiles of another block row
   float* dinv = stg + CLN * TS;          // inv(L_rr), column-major: what the rows below multiply their tiles with
   float* dnext = dinv + TS;              // inv(L_{r-1,r-1}), pushed here by CTA r-1 (the hand-over on the critical path)
+  float* lnext = dnext + TS;             // L_{r-1,r-2}, pushed here by CTA r-1: the last tile our row's products wait for
   const float* Ag = Ain + (long long)grp * g * g;
   float* gs = scratch + (long long)grp * scratch_stride;
   float* Lg = Lout ? Lout + (long long)grp * g * g : nullptr;
@@ -641,7 +650,15 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
     }
     for (int j = 0; j < TB; ++j)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&colbar[j])) : "memory");
+    // flagN: the inverse of the previous CTA's diagonal tile arrives as asynchronous stores that count their bytes on this
+    // barrier (32 x 32 floats); armed here, before the cluster barrier that precedes any push
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&flagN)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&flagN)), "r"(TB * TB * 4) : "memory");
+    // flagT: the same for tile (r-1, r-2) of L
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&flagT)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&flagT)), "r"(TB * TB * 4) : "memory");
   }
   // load block row r: column c of the column-major tile (r,J) is a contiguous piece of ROW J*32+c of the symmetric input
   if (r < NB) {
@@ -678,35 +695,51 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
     // ------------------------------------------------------------------ block row r of L
     for (int J = 0; J < r; ++J) {
       float* T = own + J * TS;
-      if (J > 0) {
-        // T -= sum_{K<J} L_rK L_JK^T  (row J's tiles come from the scratch; this runs while CTA J factors its diagonal tile).
-        // Row J is announced in two parts: its tiles 0..J-2 one block step early (flagA2), the last one (J,J-1) with
-        // flagA -- only that one fetch and one tile product sit between CTA J's last panel and our turn.
-        float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-        if (J > 1) {
-          cl_wait(&flagA2[J]);
-          cta_fetch_tiles(gtile(J, 0), J - 1, stg, t);
-          __syncthreads();
-          for (int K = 0; K < J - 1; ++K) cta_tile_mac(acc, own + K * TS, stg + K * TS, tr, tc);
-        }
-        cl_wait(&flagA[J]);
-        cta_fetch_tiles(gtile(J, J - 1), 1, stg + (J - 1) * TS, t);
-        __syncthreads();
-        cta_tile_mac(acc, own + (J - 1) * TS, stg + (J - 1) * TS, tr, tc);
+      // T_rJ -= sum_{K<J} L_rK L_JK^T, row J's tiles coming from the scratch.  Row J is announced in two parts: its tiles
+      // 0..J-2 one block step early (flagA2), the last one (J,J-1) with flagA.  The early part of the NEXT column's sum is
+      // taken here too, before this column's wait for inv(L_JJ): the CTA would idle there, and afterwards the same products
+      // would sit between CTA J's factorisation and ours (for the CTA next to the diagonal they were the critical path).
+      auto subtract = [&](float* Tt, const float (&acc)[2][2]) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          float2* p = reinterpret_cast<float2*>(T + (2 * tc + j) * TP + 2 * tr);
+          float2* p = reinterpret_cast<float2*>(Tt + (2 * tc + j) * TP + 2 * tr);
           float2 v = *p;
           v.x -= acc[0][j]; v.y -= acc[1][j];
           *p = v;
         }
         __syncthreads();
+      };
+      if (J > 0) {
+        float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        if (J == r - 1) {
+          // our predecessor pushed this tile into our shared memory the moment it had it: no scratch round trip, no fence
+          cl_wait(&flagT);
+          cta_tile_mac(acc, own + (J - 1) * TS, lnext, tr, tc);
+        } else {
+          cl_wait(&flagA[J]);
+          cta_fetch_tiles(gtile(J, J - 1), 1, stg + (J - 1) * TS, t);
+          __syncthreads();
+          cta_tile_mac(acc, own + (J - 1) * TS, stg + (J - 1) * TS, tr, tc);
+        }
+        subtract(T, acc);
+      }
+      if (J >= 1 && J + 1 < r) {
+        const int Jn = J + 1;               // tiles (Jn, 0..Jn-2) x our tiles (r, 0..Jn-2), all final since column J-1
+        float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        cl_wait(&flagA2[Jn]);
+        cta_fetch_tiles(gtile(Jn, 0), Jn - 1, stg, t);
+        __syncthreads();
+        for (int K = 0; K < Jn - 1; ++K) cta_tile_mac(acc, own + K * TS, stg + K * TS, tr, tc);
+        subtract(own + Jn * TS, acc);
       }
       {
         // L_rJ = T inv(L_JJ)^T as a tile product by the whole CTA; inv(L_JJ) comes straight out of CTA J's shared memory
         // (it was built one column behind J's factorisation, so it is there as soon as L_JJ is)
         if (J == r - 1) CL_MARK(2);
-        cl_wait(&flagB[J]);
+        // the inverse of the predecessor's diagonal tile is the hand-over on the critical path: it comes as st.async stores
+        // that complete on flagN -- data and signal in one operation; plain remote stores followed by a release-arrive
+        // took 0.45 us on the sender (the release waits for the stores) and 0.3 us more to wake us
+        if (J == r - 1) cl_wait(&flagN); else cl_wait(&flagB[J]);
         if (J == r - 1) CL_MARK(3);
         const float* Dj = dnext;                 // J == r-1: CTA J pushed its inverse into our shared memory
         if (J < r - 1) {
@@ -721,6 +754,14 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
         cta_tile_mac(acc, T, Dj, tr, tc);        // (row 2tr+i, col 2tc+j) = sum_k T(row,k) inv(L_JJ)(col,k)
         __syncthreads();                         // everyone has read T
         float* gt = gtile(r, J);
+        if (J == r - 1 && r + 1 < NB) {
+          const uint32_t rn = cl_map((uint32_t)__cvta_generic_to_shared(lnext), (uint32_t)(r + 1));
+          const uint32_t rb = cl_map((uint32_t)__cvta_generic_to_shared(&flagT), (uint32_t)(r + 1));
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1,%2}, [%3];" ::"r"(
+                             rn + (uint32_t)(((2 * tc + j) * TP + 2 * tr) * 4)), "f"(acc[0][j]), "f"(acc[1][j]), "r"(rb) : "memory");
+        }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const float2 v = make_float2(acc[0][j], acc[1][j]);
@@ -775,25 +816,28 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
       float x[32];
       warp_inverse_follow(x, phase ? Tt : stg + TS, phase ? rdv : rd_warm + TB, cb, lane);
       if (phase) {
+      CL_MARKW(16);
       // dinv: element (row c, col lane).  The next CTA gets its copy pushed (it needs it first, on the critical path).
       if (r + 1 < NB) {
         const uint32_t rn = cl_map((uint32_t)__cvta_generic_to_shared(dnext), (uint32_t)(r + 1)) + (uint32_t)(lane * TP * 4);
+        const uint32_t rb = cl_map((uint32_t)__cvta_generic_to_shared(&flagN), (uint32_t)(r + 1));
 #pragma unroll
         for (int c = 0; c < 32; c += 4)
-          asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rn + c * 4), "f"(x[c]), "f"(x[c + 1]), "f"(x[c + 2]), "f"(x[c + 3]) : "memory");
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(rn + c * 4),
+                       "f"(x[c]), "f"(x[c + 1]), "f"(x[c + 2]), "f"(x[c + 3]), "r"(rb) : "memory");
       }
 #pragma unroll
       for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(dinv + lane * TP + c) = make_float4(x[c], x[c + 1], x[c + 2], x[c + 3]);
       // the arrivals are release operations at cluster scope and cumulative over what __syncwarp ordered before them:
       // no separate fence on this (critical) hand-over
       __syncwarp();
-      if (lane < NB && lane != r) cl_arrive_remote(&flagB[r], lane);
-      CL_MARK(8);
+      if (lane < NB && lane != r && lane != r + 1) cl_arrive_remote(&flagB[r], lane);
+      CL_MARKW(8);
       float* Xr = xcol + r * TS;              // row-major
 #pragma unroll
       for (int c = 0; c < 32; ++c) Xr[c * TP + lane] = x[c];
       __syncwarp();
-      CL_MARK(9);
+      CL_MARKW(9);
       store_tile_rowmajor(dinv, Xg + (long long)(r * TB) * g + r * TB, g, lane);
       } else {
         float acc = 0.f;
@@ -882,7 +926,7 @@ int wc_chol_inv_launch(const float* Ain, int C, int g, float* Lout, float* Xout,
   const int NB = (g + TB - 1) / TB;
   if (chol_cluster_ok(g, Xout) && !(wc_debug_flags() & 2048)) {
     if (!Xpad) return WC_E_ARG;
-    const size_t csm = (size_t)(2 * CLN + 4 + CLW) * TS * sizeof(float);
+    const size_t csm = (size_t)(2 * CLN + 5 + CLW) * TS * sizeof(float);
     static bool cattr = false;
     if (!cattr) {
       WC_CUDA(cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));

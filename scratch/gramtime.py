@@ -30,7 +30,7 @@ def timeit(fn, n=20):
     return e0.elapsed_time(e1) / n * 1e3
 k1 = lambda i: lib.wc_stats_fwd(ptr(xs[i % 3]), M, C, C, ptr(ws), nb, ptr(mean), ptr(S), st)
 k4 = lambda i: lib.wc_reduce_bwd(ptr(xs[i % 3]), ptr(dys[i % 3]), N, HW, C, C, ptr(mean), None, 1, ptr(P), ptr(s), None, 0, st)
-for flags in (1, 17, 3):
+for flags in (1, 5, 9, 13, 3):
     lib.wc_debug_set(flags)
     print('flags', flags, 'K1 stage us', round(timeit(k1), 1), 'K4 stage us', round(timeit(k4), 1))
     if flags & 1:

@@ -1770,7 +1770,7 @@ void wc_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" long long wc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // ---- debug-only instrumentation ------------------------------------------------------------------------
-static int g_dbg_flags = 0;
+static int g_dbg_flags = [] { const char* e = getenv("WC_B200_DEBUG"); return e ? atoi(e) & ~1 : 0; }();   // experiment switches (A/B runs)
 static unsigned long long* g_dbg_buf = nullptr;
 int wc_debug_flags() { return g_dbg_flags; }
 int wc_l2_mode() {

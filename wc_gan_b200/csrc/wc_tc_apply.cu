@@ -703,12 +703,14 @@ int launch_tc_apply(TcApplyParams& p, const float* a0, const float* a1, float* o
     if (rc) return rc;
     return launch_tc_apply2<C>(p, tm_a0, tm_a1, tm_out, st);
   }
-  // Wave quantisation: 128-row tiles of a 65536-row tensor are 512 tiles = 3.46 rounds on 148 CTAs, i.e. the step takes the
-  // time of 4 full rounds.  When all rows form one run (unconditional layer), the tile height is lowered so that the last
-  // round is full as well: 4 rounds of 112-row tiles move 12.5 % less data per CTA than 4 rounds of 128-row tiles.  (The MMA
-  // still runs M = 128; the rows beyond tile_rows hold stale operands and are never stored.)
+  // Wave quantisation: 128-row tiles of a 65536-row tensor are 512 tiles = 3.46 rounds on 148 CTAs.  Experiment (debug bit
+  // 4194304, off by default): when all rows form one run (unconditional layer), lower the tile height so that the last
+  // round is full as well (4 rounds of 112-row tiles; the MMA still runs M = 128, the rows beyond tile_rows hold stale
+  // operands and are never stored).  Measured: K6 54.7 us instead of 52.4 us stand-alone, whole step +0.4 us -- the CTAs
+  // do not run in lock-step rounds (the tile loop is a dynamic queue on HBM bandwidth), so there is no idle tail to
+  // fill, and shorter tiles only add per-tile overhead.
   p.tile_rows = TILE_M;
-  if (!cond && !(p.dbg_flags & 4194304)) {
+  if (!cond && (p.dbg_flags & 4194304)) {
     const long long rounds = (wc_cdiv(HW, TILE_M) + WC_NUM_SMS - 1) / WC_NUM_SMS;
     const long long r = ((long long)HW + rounds * WC_NUM_SMS - 1) / (rounds * WC_NUM_SMS);
     const int r8 = (int)((r + 7) / 8 * 8);

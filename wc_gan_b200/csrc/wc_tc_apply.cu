@@ -707,8 +707,9 @@ int launch_tc_apply(TcApplyParams& p, const float* a0, const float* a1, float* o
   // 4194304, off by default): when all rows form one run (unconditional layer), lower the tile height so that the last
   // round is full as well (4 rounds of 112-row tiles; the MMA still runs M = 128, the rows beyond tile_rows hold stale
   // operands and are never stored).  Measured: K6 54.7 us instead of 52.4 us stand-alone, whole step +0.4 us -- the CTAs
-  // do not run in lock-step rounds (the tile loop is a dynamic queue on HBM bandwidth), so there is no idle tail to
-  // fill, and shorter tiles only add per-tile overhead.
+  // share HBM bandwidth rather than run in lock-step rounds (while 68 CTAs work on their fourth tile they get the
+  // bandwidth the 80 finished ones no longer use), so the idle tail is much smaller than the round count suggests, and
+  // shorter tiles add per-tile overhead.
   p.tile_rows = TILE_M;
   if (!cond && (p.dbg_flags & 4194304)) {
     const long long rounds = (wc_cdiv(HW, TILE_M) + WC_NUM_SMS - 1) / WC_NUM_SMS;

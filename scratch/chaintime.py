@@ -8,9 +8,11 @@ lib.wc_debug_set.argtypes = [ctypes.c_int]; lib.wc_debug_marks.argtypes = [ctype
 dev = torch.device('cuda', 0)
 import os
 EXTRA = int(os.environ.get('WC_DBG', '0'))
-for shape, an, K in ((bench.SHAPE, 'uconv', None), ((64, 16, 16, 128), 'ufconv', 10)):
+CASES = ((bench.SHAPE, 'uconv', None, 4), ((64, 16, 16, 128), 'ufconv', 10, 4))
+if os.environ.get('WC_CFG5'): CASES = (((256, 4, 4, 128), 'ufconv', 200, 15),)
+for shape, an, K, EE in CASES:
     xs, dys = bench.make_inputs(torch, shape, 2, dev, 1)
-    stack = bench.build_stack(W, torch, 'd', an, shape[-1], dev, K=K, E=4)
+    stack = bench.build_stack(W, torch, 'd', an, shape[-1], dev, K=K, E=EE)
     params = list(stack.parameters())
     cls = torch.randint(0, K, (shape[0], 1), dtype=torch.int32, device=dev) if K else None
     def step(i):

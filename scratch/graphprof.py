@@ -15,13 +15,15 @@ torch.cuda.set_device(dev)
 group = None
 if world > 1:
     dist.init_process_group('nccl', device_id=dev); group = dist.group.WORLD
-shape = bench.SHAPE
+shape = tuple(int(v) for v in os.environ['WC_SHAPE'].split('x')) if os.environ.get('WC_SHAPE') else bench.SHAPE
+AN, KK, EE = os.environ.get('WC_AN', 'uconv'), int(os.environ.get('WC_K', 0)) or None, int(os.environ.get('WC_E', 10))
 xs, dys = bench.make_inputs(torch, shape, 2, dev, 1 + rank)
-stack = bench.build_stack(W, torch, 'd', 'uconv', shape[-1], dev, group=group)
+stack = bench.build_stack(W, torch, 'd', AN, shape[-1], dev, group=group, K=KK, E=EE)
+cls = torch.randint(0, KK, (shape[0], 1), device=dev, dtype=torch.int32) if KK else None
 params = list(stack.parameters())
 def step(i):
     x = xs[i % 2].requires_grad_(True)
-    y = stack(x)
+    y = stack(x, cls) if KK else stack(x)
     return torch.autograd.grad(y, [x] + params, dys[i % 2])
 s = torch.cuda.Stream()
 with torch.cuda.stream(s):

@@ -191,6 +191,13 @@ def test_cfg3_full_size_vs_oracle(dist):
     run_case('d', 'uconv', (256, 16, 16, 256), dist=dist)
 
 
+@pytest.mark.parametrize('g', [64, None])
+def test_cfg3_full_size_zca_vs_oracle(g):
+    """ZCA whitening at the FULL 256x16x16x256 batch (BASELINE cfg3 is the ZCA group sweep): g = 64 runs the shared-memory
+    Jacobi kernel, g = C = 256 the multi-CTA block Jacobi."""
+    run_case('d', 'uconv', (256, 16, 16, 256), dec='zca', g=g)
+
+
 def test_cfg2_full_size_conditional_vs_oracle():
     """cfg4's largest generator layer shape (256 x 32 x 32 x 128, K = 10, E = 4, ufconv) against the fp64 oracle."""
     run_case('d', 'ufconv', (256, 32, 32, 128), K=10, E=4)

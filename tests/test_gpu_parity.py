@@ -191,6 +191,19 @@ def test_cfg3_full_size_vs_oracle(dist):
     run_case('d', 'uconv', (256, 16, 16, 256), dist=dist)
 
 
+@pytest.mark.parametrize('after_norm,shape,K,E,dec', [('ufconv', (64, 4, 4, 128), 200, 15, 'cholesky'),
+                                                       ('fconv', (48, 4, 4, 64), 40, 4, 'cholesky'),
+                                                       ('ufconv', (40, 6, 6, 64), 16, 4, 'cholesky'),
+                                                       ('ufconv', (256, 8, 8, 128), 200, 15, 'cholesky'),
+                                                       ('ufconv', (40, 6, 6, 64), 16, 4, 'zca'),
+                                                       ('fconv', (64, 4, 4, 128), 40, 4, 'zca')])
+def test_factorised_many_classes(after_norm, shape, K, E, dec):
+    """fconv / ufconv with K >= 3E + 4 classes (cfg5: K = 200, E = 15): the library forms T_k and every parameter gradient
+    from the E + 1 basis products instead of K per-class products (wc_bwd_factorised_ok); same oracle, same tolerances.
+    With ZCA the backward takes the launch-per-product path, which first rebuilds the W_k the forward did not form."""
+    run_case('d', after_norm, shape, K=K, E=E, dec=dec)
+
+
 @pytest.mark.parametrize('g', [64, None])
 def test_cfg3_full_size_zca_vs_oracle(g):
     """ZCA whitening at the FULL 256x16x16x256 batch (BASELINE cfg3 is the ZCA group sweep): g = 64 runs the shared-memory

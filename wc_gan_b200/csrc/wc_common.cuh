@@ -139,7 +139,8 @@ int wc_factor_fwd_impl(const float* mean, const float* S, const float* count_dev
 int wc_compose_fwd_impl(const float* Weff, int Cin, int Cout, int g, int K, const float* Wu, const float* bu,
                         const float* Wc, const float* bc, int triangular, const float* class_matrix,
                         const float* D, int E, const float* bf, float* ehat, float* Wk, float* T, float* b,
-                        void* Tp_fwd, void* Tp_bwd, const float* Wk_ready, unsigned* barrier, cudaStream_t st);
+                        void* Tp_fwd, void* Tp_bwd, const float* Wk_ready, unsigned* barrier, float* fact_ws, cudaStream_t st);
+size_t wc_compose_fact_workspace_bytes(int C, int K, int E, bool has_class_matrix, bool has_wc);
 int wc_factor_bwd_impl(const float* dWeff, const float* gbar, const float* Weff, const float* Wm, const float* R,
                        const float* U, const float* lam, const float* count_dev, double count_host, int C, int g,
                        float eps, int decomposition, int renorm, float* A, float* cvec, float* workspace,
@@ -150,12 +151,14 @@ int wc_reduce_bwd_impl(const float* x, const float* dy, int N, int HW, int Cin, 
                        cudaStream_t stream);
 
 // K5a + K5b as one persistent multi-stage launch (wc_small.cu); WC_E_UNSUPPORTED: use the per-product launches
-int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float* Wk, int Cin, int Cout, int g, int K,
+bool wc_bwd_factorised_ok(int C, int K, int E, bool has_class_matrix, bool has_wc);
+int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float* Wk, const float* Wu, int Cin, int Cout, int g, int K,
                  float* dWu, float* dbu, float* dWc, float* dbc, int triangular, const float* class_matrix, const float* ehat,
                  const float* D, int E, float* dD, float* dclass_matrix, float* dbf, float* red, float* A, float* cvec,
                  const float* count_dev, double count_host, float eps, void* Tp_bwd, int pack_K, float* ws_color,
                  float* ws_factor, unsigned* barrier, int stage_lo, int stage_hi, void* const* xchg_peers, void* xchg_state,
-                 int xchg_rank, int xchg_world, int32_t* info, cudaStream_t st);
+                 int xchg_rank, int xchg_world, int32_t* info, int wk_missing, cudaStream_t st);
+int wc_rebuild_wk(int Cin, int Cout, int K, const float* Wu, const float* class_matrix, const float* D, int E, float* Wk, cudaStream_t st);
 
 int wc_apply_fwd_impl(const float* x, int N, int HW, int Cin, int Cout, const float* mean, const float* T, const void* T_packed,
                       const float* b, const int32_t* cls, int K, int band, float* y, int32_t* info, int relu, cudaStream_t stream);

@@ -72,11 +72,16 @@ void layout(const WcLayerCall& c, WcSavedLayout& L) {
   L.total = cv.off;
 }
 
-struct FwdWs { size_t stats, stats_bytes, factor, factor_bytes, total; };
+struct FwdWs { size_t stats, stats_bytes, factor, factor_bytes, compose, total; };
 FwdWs fwd_ws(const WcLayerCall& c) {
   Carver cv; FwdWs w{};
   if (c.whiten && c.training) { w.stats_bytes = wc_stats_workspace_bytes((int64_t)c.N * c.HW, c.Cin, c.g); w.stats = cv.take(w.stats_bytes); }
   if (c.whiten) { w.factor_bytes = wc_factor_workspace_bytes(c.Cin, c.g, c.decomposition, c.renorm && c.training); w.factor = cv.take(w.factor_bytes); }
+  w.compose = NONE;
+  if (c.whiten && c.Cin == c.Cout) {
+    const size_t nb = wc_compose_fact_workspace_bytes(c.Cin, c.K, c.E, c.class_matrix != nullptr, c.Wc != nullptr);
+    if (nb) w.compose = cv.take(nb);
+  }
   w.total = cv.off ? cv.off : 256;
   return w;
 }
@@ -180,7 +185,8 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
   rc = wc_compose_fwd_impl(at<float>(c.saved, L.Weff), c.Cin, c.Cout, c.whiten ? c.g : c.Cin, c.K, c.Wu, c.bu, c.Wc, c.bc,
                            c.triangular, c.class_matrix, c.D, c.E, c.bf, at<float>(c.saved, L.ehat), at<float>(c.saved, L.Wk),
                            at<float>(c.saved, L.T), at<float>(c.saved, L.b), Tp, Tp ? at<void>(c.saved, L.Tp_bwd) : nullptr,
-                           plain_u(c) ? c.Wu : nullptr, fwd_barrier, (cudaStream_t)stream);
+                           plain_u(c) ? c.Wu : nullptr, fwd_barrier, c.workspace ? at<float>(c.workspace, W.compose) : nullptr,
+                           (cudaStream_t)stream);
   if (rc) return rc;
   const int band = (c.whiten && !has_coloring(c) && c.g < c.Cin) ? c.g : 0;
   return wc_apply_fwd_impl(c.x, c.N, c.HW, c.Cin, c.Cout, mean, at<float>(c.saved, L.T), Tp, plain_u(c) ? c.bu : at<float>(c.saved, L.b),
@@ -217,12 +223,15 @@ extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
   const float* count_dev = c.count_dev;
   const bool xb = stats_grad && xchg_bwd(c);
   if (xb) count_dev = at<float>(c.saved, L.rec_count);       // global row count, left there by the forward exchange
+  // the factorised forward (many classes, fconv / ufconv) does not form W_k: whoever reads it below rebuilds it first
+  const int wk_missing = stats_grad && !plain_u(c) && c.Cin == c.Cout && !c.bc &&
+                         wc_bwd_factorised_ok(c.Cin, c.K, c.E, c.class_matrix != nullptr, c.Wc != nullptr);
   auto chain = [&](int lo, int hi, bool exchange) {
-    return wc_bwd_chain(P, s, at<float>(c.saved, L.Weff), Wk, c.Cin, c.Cout, g, c.K, c.dWu, c.dbu, c.dWc, c.dbc, c.triangular,
+    return wc_bwd_chain(P, s, at<float>(c.saved, L.Weff), Wk, c.Wu, c.Cin, c.Cout, g, c.K, c.dWu, c.dbu, c.dWc, c.dbc, c.triangular,
                         c.class_matrix, at<float>(c.saved, L.ehat), c.D, c.E, c.dD, c.dclass_matrix, c.dbf, c.red, A, cvec,
                         count_dev, c.count, c.eps, at<void>(c.saved, L.Tp_bwd), c.K, at<float>(c.workspace, W.color),
                         at<float>(c.workspace, W.factor), barrier, lo, hi, exchange ? c.xchg_peers : nullptr,
-                        exchange ? c.xchg_state : nullptr, c.xchg_rank, c.xchg_world, c.info, (cudaStream_t)stream);
+                        exchange ? c.xchg_state : nullptr, c.xchg_rank, c.xchg_world, c.info, wk_missing, (cudaStream_t)stream);
   };
   bool chained = false, all_done = false;
   if (c.phases & WC_PHASE_REDUCE) {
@@ -238,6 +247,7 @@ extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
       if (rc && rc != WC_E_UNSUPPORTED) return rc;
     }
     if (!chained) {
+      if (wk_missing) { rc = wc_rebuild_wk(c.Cin, c.Cout, c.K, c.Wu, c.class_matrix, c.D, c.E, at<float>(c.saved, L.Wk), (cudaStream_t)stream); if (rc) return rc; }
       rc = wc_color_bwd(P, s, at<float>(c.saved, L.Weff), Wk, c.Cin, c.Cout, g, c.K, c.dWu, c.dbu, c.dWc,
                         c.dbc, c.triangular, c.class_matrix, at<float>(c.saved, L.ehat), c.D, c.E, c.dD, c.dclass_matrix, c.dbf,
                         stats_grad ? c.red : nullptr, stats_grad ? c.red + gg : nullptr, at<float>(c.workspace, W.color),

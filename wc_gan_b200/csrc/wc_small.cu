@@ -310,13 +310,18 @@ __global__ void __launch_bounds__(SMM_THREADS) smm_multi_kernel(const __grid_con
 //
 // Co-residency: grid <= number of SMs, one CTA fits on every SM, and nothing a chain CTA waits for depends on a kernel
 // launched after it (the dependent launch is triggered only once every CTA of this grid is running).
-enum { CJ_SMM = 0, CJ_VEC = 1, CJ_SUMK = 2, CJ_COPY = 3, CJ_WSUMK = 4, CJ_DOT = 5, CJ_L2N = 6, CJ_BUILDWK = 7 };
-constexpr int CH_MAXSMM = 5, CH_MAXVEC = 3, CH_MAXELT = 7, CH_MAXSTAGE = 6, CH_ELT_CHUNK = 2048;
+enum { CJ_SMM = 0, CJ_VEC = 1, CJ_SUMK = 2, CJ_COPY = 3, CJ_WSUMK = 4, CJ_DOT = 5, CJ_L2N = 6, CJ_BUILDWK = 7, CJ_MIXK = 8, CJ_MIXT = 9,
+       CJ_DOT2 = 10, CJ_EHATB = 11 };
+constexpr int CH_MAXSMM = 8, CH_MAXVEC = 3, CH_MAXELT = 7, CH_MAXSTAGE = 6, CH_ELT_CHUNK = 2048;
+constexpr int MIX_EPB = 128, MIX_KG = 4, MIXT_KSEG = 16, MIX_MAXB = 16, MIX_MAXK = 1024;   // CJ_MIXK / CJ_MIXT job shapes
 struct EltJob {
   const float* a; const float* b; float* out;
   long long n;                 // elements per slice
   int K, E;
   const float* cm; const float* ehat;
+  int has_u, C;                // CJ_MIXK / CJ_MIXT: basis slot 0 (the unconditional kernel) takes part; CJ_MIXT: matrix edge
+  uint8_t* pk0; uint8_t* pk1;  // CJ_MIXT: bf16 hi/lo operand images of the mixed matrices (see SmmEpi), nullable
+  int kseg, pad;               // CJ_MIXT: classes per virtual CTA (<= MIXT_KSEG)
 };
 // K2b's first half (generator.py:41-78, conditional_layers.py:811-819, :993-1005): W_k = Wu + triu?(Wc_k) + sum_e ehat[k,e] D_e,
 // b_k = bu + bc_k + bf_k, ehat = l2_normalize(class_matrix)
@@ -540,6 +545,9 @@ __device__ __noinline__ void smm_tile_rt(const TJob& jb, int bx, int by, int z, 
 }
 
 // elementwise / reduction jobs of the parameter gradients (one virtual CTA each)
+// FACT: the job types of the factorised coloring (CJ_MIXK and above) are compiled only into the kernel instance that runs
+// them: with them the common instance needed 128 registers instead of 117 and its stages were 3-4 us slower
+template <bool FACT>
 __device__ __forceinline__ void elt_job_run(int type, const EltJob& j, int cta, float* sm) {
   const int t = threadIdx.x;
   if (type == CJ_SUMK || type == CJ_COPY) {
@@ -587,11 +595,11 @@ __device__ __forceinline__ void elt_job_run(int type, const EltJob& j, int cta, 
     float s = 0.f;
     if ((j.n & 3) == 0) {
       for (long long i = 4 * t; i < j.n; i += 4 * SMM_THREADS) {
-        const float4 x = __ldcg(reinterpret_cast<const float4*>(q + i)), y = __ldg(reinterpret_cast<const float4*>(d + i));
+        const float4 x = __ldcg(reinterpret_cast<const float4*>(q + i)), y = __ldcg(reinterpret_cast<const float4*>(d + i));
         s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
       }
     } else {
-      for (long long i = t; i < j.n; i += SMM_THREADS) s = fmaf(__ldcg(q + i), d[i], s);
+      for (long long i = t; i < j.n; i += SMM_THREADS) s = fmaf(__ldcg(q + i), __ldcg(d + i), s);
     }
     s = wc_warp_sum(s);
     if ((t & 31) == 0) sm[t >> 5] = s;
@@ -613,6 +621,178 @@ __device__ __forceinline__ void elt_job_run(int type, const EltJob& j, int cta, 
         j.out[k * j.E + e] = clamped ? rho * de : rho * (de - j.ehat[k * j.E + e] * dot);
       }
     }
+  } else if (!FACT) {
+    return;
+  } else if (type == CJ_MIXK) {
+    // Factorised coloring (W_k = sum_j alpha[k,j] B_j with B_0 = Wu, B_e = D_e, alpha[k,0] = 1, alpha[k,e] = ehat[k,e-1]):
+    // out[j n + i] = sum_k alpha[k,j] a[k n + i] for ALL j = 0..E in one pass over a.  A virtual CTA takes MIX_EPB elements;
+    // its 512 threads are 4 k-groups (k mod 4) x 128 elements, 16 accumulators each, alpha from a shared-memory table,
+    // the k-groups summed through shared memory at the end.
+    float* al = sm;                                  // [K][MIX_MAXB]
+    float* red = sm + (size_t)j.K * MIX_MAXB;        // [MIX_KG][MIX_MAXB][MIX_EPB]
+    for (int q = t; q < j.K * MIX_MAXB; q += SMM_THREADS) {
+      const int k = q / MIX_MAXB, jj = q % MIX_MAXB;
+      al[q] = jj == 0 ? 1.f : (jj <= j.E ? __ldg(j.ehat + k * j.E + jj - 1) : 0.f);
+    }
+    __syncthreads();
+    const int el = t % MIX_EPB, kg = t / MIX_EPB;
+    const long long i = (long long)cta * MIX_EPB + el;
+    float acc[MIX_MAXB];
+#pragma unroll
+    for (int q = 0; q < MIX_MAXB; ++q) acc[q] = 0.f;
+    if (i < j.n) {
+      const float* src = j.a + i;
+      int k = kg;
+      for (; k + 7 * MIX_KG < j.K; k += 8 * MIX_KG) {          // eight loads in flight
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (long long)(k + u * MIX_KG) * j.n);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4* ar = reinterpret_cast<const float4*>(al + (k + u * MIX_KG) * MIX_MAXB);
+#pragma unroll
+          for (int q4 = 0; q4 < MIX_MAXB / 4; ++q4) {
+            const float4 w = ar[q4];
+            acc[4 * q4 + 0] = fmaf(w.x, v[u], acc[4 * q4 + 0]); acc[4 * q4 + 1] = fmaf(w.y, v[u], acc[4 * q4 + 1]);
+            acc[4 * q4 + 2] = fmaf(w.z, v[u], acc[4 * q4 + 2]); acc[4 * q4 + 3] = fmaf(w.w, v[u], acc[4 * q4 + 3]);
+          }
+        }
+      }
+      for (; k < j.K; k += MIX_KG) {
+        const float v = __ldcg(src + (long long)k * j.n);
+        const float* ar = al + k * MIX_MAXB;
+#pragma unroll
+        for (int q = 0; q < MIX_MAXB; ++q) acc[q] = fmaf(ar[q], v, acc[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < MIX_MAXB; ++q) red[(kg * MIX_MAXB + q) * MIX_EPB + el] = acc[q];
+    __syncthreads();
+    for (int q = t; q < (j.E + 1) * MIX_EPB; q += SMM_THREADS) {
+      const int jj = q / MIX_EPB, e2 = q % MIX_EPB;
+      const long long i2 = (long long)cta * MIX_EPB + e2;
+      if (i2 < j.n) {
+        float r = 0.f;
+#pragma unroll
+        for (int g2 = 0; g2 < MIX_KG; ++g2) r += red[(g2 * MIX_MAXB + jj) * MIX_EPB + e2];
+        j.out[(long long)jj * j.n + i2] = r;
+      }
+    }
+  } else if (type == CJ_MIXT) {
+    // out[k n + i] = sum_j alpha[k,j] a[j n + i]  (W_k from the basis, T_k from the E + 1 products Weff^T B_j); four
+    // elements per thread, MIXT_KSEG classes per virtual CTA; ehat and a were written earlier in this launch (ld.cg).
+    // With pk0 / pk1 the matrices also leave as the bf16 hi/lo operand images of K3 / K6 (layout: see SmmEpi): image 1
+    // holds 8 consecutive columns of a row per 16-byte chunk (two neighbouring lanes), image 0 holds 8 consecutive rows of
+    // a column (through a shared-memory transpose of the CTA's 2048-element slab = 2048 / C whole rows).
+    const int nchunk = (int)((j.n + CH_ELT_CHUNK - 1) / CH_ELT_CHUNK);
+    const int k0 = (cta / nchunk) * j.kseg;
+    const long long i = (long long)(cta % nchunk) * CH_ELT_CHUNK + 4 * t;
+    const bool live = i + 3 < j.n;
+    float4 tb[MIX_MAXB];
+#pragma unroll
+    for (int q = 0; q < MIX_MAXB; ++q)
+      tb[q] = (live && q <= j.E && (q > 0 || j.has_u)) ? __ldcg(reinterpret_cast<const float4*>(j.a + (long long)q * j.n + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int C = j.C;
+    const int row = (int)(i / C), col = (int)(i - (long long)row * C);       // (with images: n = C * C, slab = whole rows)
+    const long long b_img = (long long)C * 64;
+    const int lane = t & 31;
+    float* al = sm + 16 * (256 + 4) + 64;            // alpha of this CTA's classes, behind the transpose slab
+    if (t < j.kseg * MIX_MAXB) {
+      const int k = k0 + t / MIX_MAXB, q = t % MIX_MAXB;
+      al[t] = (k < j.K && q >= 1 && q <= j.E) ? __ldcg(j.ehat + k * j.E + q - 1) : 0.f;
+    }
+    __syncthreads();
+    for (int k = k0; k < min(k0 + j.kseg, j.K); ++k) {
+      float4 acc = tb[0];
+      const float* ak = al + (k - k0) * MIX_MAXB;
+#pragma unroll
+      for (int q = 1; q < MIX_MAXB; ++q) {
+        if (q <= j.E) {
+          const float w = ak[q];
+          acc.x = fmaf(w, tb[q].x, acc.x); acc.y = fmaf(w, tb[q].y, acc.y); acc.z = fmaf(w, tb[q].z, acc.z); acc.w = fmaf(w, tb[q].w, acc.w);
+        }
+      }
+      if (live) *reinterpret_cast<float4*>(j.out + (long long)k * j.n + i) = acc;
+      if (j.pk1) {
+        uint32_t h0, l0, h1, l1;
+        smm_split2(acc.x, acc.y, h0, l0);
+        smm_split2(acc.z, acc.w, h1, l1);
+        const bool odd = lane & 1;
+        const uint32_t rx = __shfl_xor_sync(0xffffffffu, odd ? h0 : l0, 1), ry = __shfl_xor_sync(0xffffffffu, odd ? h1 : l1, 1);
+        if (live) {
+          const int c8 = col & ~7;
+          uint8_t* dst = j.pk1 + (long long)k * j.n * 4 + (long long)(c8 >> 5) * (2 * b_img) + smm_kmajor32_off(row, (c8 & 31) >> 3);
+          if (!odd) *reinterpret_cast<uint4*>(dst) = make_uint4(h0, h1, rx, ry);
+          else *reinterpret_cast<uint4*>(dst + b_img) = make_uint4(rx, ry, l0, l1);
+        }
+      }
+      if (j.pk0) {
+        const int pitch = C + 4, R = CH_ELT_CHUNK / C;         // R = 16 (C = 128) or 8 (C = 256) whole rows
+        const int lr = (4 * t) / C;
+        __syncthreads();                                       // the previous class has been read out
+        *reinterpret_cast<float4*>(sm + lr * pitch + col) = acc;
+        __syncthreads();
+        const int nq = (R / 8) * C;                            // 16-byte chunks of this slab: 256
+        if (t < nq && live) {
+          const int rg = t / C, cc = t - rg * C;
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) smm_split2(sm[(rg * 8 + 2 * q) * pitch + cc], sm[(rg * 8 + 2 * q + 1) * pitch + cc], hi[q], lo[q]);
+          const int gi = (int)(((long long)(cta % nchunk) * CH_ELT_CHUNK) / C) + rg * 8;
+          uint8_t* dst = j.pk0 + (long long)k * j.n * 4 + (long long)(gi >> 5) * (2 * b_img) + smm_kmajor32_off(cc, (gi & 31) >> 3);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(dst + b_img) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+    }
+  } else if (type == CJ_DOT2) {
+    // out[k E + e] = <a_k, b_e> for TWO classes and all e per virtual CTA: the classes' elements stay in registers while
+    // the E basis matrices stream by once (the per-(k,e) form re-reads both operands K E times)
+    const int kA = 2 * cta, kB = min(2 * cta + 1, j.K - 1);
+    constexpr int NV = 8;                                      // float4 per thread and class: n <= 512 * 32
+    float4 pa[NV], pb[NV];
+    const int nv = (int)(j.n / 4);
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int q = t + u * SMM_THREADS;
+      pa[u] = q < nv ? __ldcg(reinterpret_cast<const float4*>(j.a + (long long)kA * j.n) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      pb[u] = q < nv ? __ldcg(reinterpret_cast<const float4*>(j.a + (long long)kB * j.n) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int e = 0; e < j.E; ++e) {
+      const float4* d = reinterpret_cast<const float4*>(j.b + (long long)e * j.n);
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        const int q = t + u * SMM_THREADS;
+        if (q < nv) {
+          const float4 y = __ldcg(d + q);
+          sa = fmaf(pa[u].x, y.x, sa); sa = fmaf(pa[u].y, y.y, sa); sa = fmaf(pa[u].z, y.z, sa); sa = fmaf(pa[u].w, y.w, sa);
+          sb = fmaf(pb[u].x, y.x, sb); sb = fmaf(pb[u].y, y.y, sb); sb = fmaf(pb[u].z, y.z, sb); sb = fmaf(pb[u].w, y.w, sb);
+        }
+      }
+      sa = wc_warp_sum(sa); sb = wc_warp_sum(sb);
+      if ((t & 31) == 0) { sm[(2 * e) * 16 + (t >> 5)] = sa; sm[(2 * e + 1) * 16 + (t >> 5)] = sb; }
+    }
+    __syncthreads();
+    if (t < 2 * j.E) {
+      float r = 0.f;
+#pragma unroll
+      for (int w = 0; w < SMM_THREADS / 32; ++w) r += sm[t * 16 + w];
+      const int e = t >> 1, k = (t & 1) ? kB : kA;
+      if (!(t & 1) || kB != kA) j.out[k * j.E + e] = r;
+    }
+  } else if (type == CJ_EHATB) {
+    // ehat = l2_normalize(class_matrix) (conditional_layers.py:994) and b_k = bu + bc_k + bf_k without forming W_k
+    // (a = bu, b = bf, cm = class matrix; out = b_k (nullable); ehat written through the const pointer's buffer)
+    float* eh = const_cast<float*>(j.ehat);
+    for (int k = t; k < j.K; k += SMM_THREADS) {
+      float sq = 0.f;
+      for (int e = 0; e < j.E; ++e) { const float v = j.cm[k * j.E + e]; sq = fmaf(v, v, sq); }
+      const float rho = rsqrtf(fmaxf(sq, 1e-12f));
+      for (int e = 0; e < j.E; ++e) eh[k * j.E + e] = j.cm[k * j.E + e] * rho;
+    }
+    if (j.out)
+      for (int q = t; q < j.K * j.C; q += SMM_THREADS) j.out[q] = (j.a ? j.a[q % j.C] : 0.f) + (j.b ? j.b[q] : 0.f);
   }
 }
 
@@ -668,6 +848,7 @@ __device__ __forceinline__ void chain_grid_barrier(unsigned* ctr, unsigned targe
   __syncthreads();
 }
 
+template <bool FACT>
 __global__ void __launch_bounds__(SMM_THREADS, 1) chain_kernel(const __grid_constant__ ChainParams kp) {
   const ChainProgram& pr = kp.pr;
   extern __shared__ __align__(16) float smm_sm[];
@@ -751,7 +932,7 @@ __global__ void __launch_bounds__(SMM_THREADS, 1) chain_kernel(const __grid_cons
         } else if (en.type == CJ_BUILDWK) {
           build_job_run(pr.build, l);
         } else {
-          elt_job_run(en.type, pr.elt[en.idx], l, smm_sm);
+          elt_job_run<FACT>(en.type, pr.elt[en.idx], l, smm_sm);
         }
       }
       __syncthreads();   // shared memory is reused by the next job of this CTA
@@ -1115,7 +1296,7 @@ __global__ void build_wk_kernel(int Cin, int Cout, int K, const float* __restric
     for (int e = 0; e < E; ++e) {
       float eh = cm[k * E + e] * rho;
       w = fmaf(eh, D[(long long)e * per + ij], w);
-      if (ij == 0) ehat[k * E + e] = eh;
+      if (ij == 0 && ehat) ehat[k * E + e] = eh;
     }
   }
   Wk[idx] = w;
@@ -1357,11 +1538,15 @@ struct ChainBuilder {
     pr.barrier = barrier; pr.dbg = wc_debug_buf(); pr.dbg_flags = wc_debug_flags();
     static bool attr_set = false;
     if (!attr_set) {
-      WC_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
+      WC_CUDA(cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
+      WC_CUDA(cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
       attr_set = true;
     }
+    bool fact = false;
+    for (int e = 0; e < pr.nent; ++e) fact = fact || pr.ent[e].type >= CJ_MIXK;
     ChainParams kp; kp.pr = pr;
-    WC_CUDA(wc_launch(chain_kernel, std::min(mx, WC_NUM_SMS), SMM_THREADS, CHAIN_SMEM, st, kp));
+    if (fact) WC_CUDA(wc_launch(chain_kernel<true>, std::min(mx, WC_NUM_SMS), SMM_THREADS, CHAIN_SMEM, st, kp));
+    else WC_CUDA(wc_launch(chain_kernel<false>, std::min(mx, WC_NUM_SMS), SMM_THREADS, CHAIN_SMEM, st, kp));
     WC_CHECK_LAUNCH();
     return 0;
   }
@@ -1375,7 +1560,7 @@ inline int elt_chunks(long long n) { return (int)((n + CH_ELT_CHUNK - 1) / CH_EL
 int wc_compose_fwd_impl(const float* Weff, int Cin, int Cout, int g, int K, const float* Wu, const float* bu,
                         const float* Wc, const float* bc, int triangular, const float* class_matrix,
                         const float* D, int E, const float* bf, float* ehat, float* Wk, float* T, float* b,
-                        void* Tp_fwd, void* Tp_bwd, const float* Wk_ready, unsigned* barrier, cudaStream_t st) {
+                        void* Tp_fwd, void* Tp_bwd, const float* Wk_ready, unsigned* barrier, float* fact_ws, cudaStream_t st) {
   // barrier (nullable): one zeroed u32 for the chain launch (without it only single-stage programs take that path)
   // Wk_ready (nullable): the per-class matrix already exists (K == 1 with only the unconditional kernel: it IS Wu, and the
   // bias is bu); nothing is built and `Wk` / `b` are not written
@@ -1387,6 +1572,43 @@ int wc_compose_fwd_impl(const float* Weff, int Cin, int Cout, int g, int K, cons
   // One persistent launch (chain kernel): stage 0 builds W_k, b_k, ehat -- it reads only parameters, so it runs BEFORE the
   // dependency wait, under the factorisation -- and stage 1 forms T_k = Weff^T W_k on the tensor-core tile, leaving it as
   // fp32 and as the bf16 operand images of K3 / K6.
+  // Factorised coloring with many classes: T_k = sum_j alpha[k,j] (Weff^T B_j) from E + 1 products and one mixing pass
+  // (wc_bwd_chain has the matching backward).  fact_ws: wc_compose_fact_workspace_bytes.
+  if (fact_ws && barrier && Weff && Cin == Cout && (Cin % 32) == 0 && (g % 32) == 0 && !Wk_ready &&
+      wc_bwd_factorised_ok(Cin, K, E, class_matrix != nullptr, Wc != nullptr) && !bc && !(wc_debug_flags() & 262144)) {
+    const bool has_u = Wu != nullptr;
+    const int nb = E + (has_u ? 1 : 0), j0 = has_u ? 0 : 1;
+    float* Bcat = fact_ws;
+    float* TB = fact_ws + (size_t)(E + 1) * per;
+    ChainBuilder cb;
+    // stage 0 (parameters only: runs before the dependency wait): ehat, b_k, the basis [Wu; D] in one buffer
+    { EltJob j{}; j.a = bu; j.b = bf; j.cm = class_matrix; j.ehat = ehat; j.out = b; j.K = K; j.E = E; j.C = Cout; cb.elt(0, CJ_EHATB, j, 1); }
+    if (has_u) { EltJob j{}; j.a = Wu; j.out = Bcat; j.n = per; j.K = 1; cb.elt(0, CJ_COPY, j, elt_chunks(per)); }
+    { EltJob j{}; j.a = D; j.out = Bcat + per; j.n = (long long)E * per; j.K = 1; cb.elt(0, CJ_COPY, j, elt_chunks(j.n)); }
+    cb.pr.prewait = 1;
+    // stage 1: the E + 1 products.  W_k itself is NOT formed: only the launch-per-product backward paths read it, and they
+    // rebuild it on demand (wc_rebuild_wk)
+    cb.smm(1, smm_blockdiag_left(Weff, true, Bcat + (size_t)j0 * per, TB + (size_t)j0 * per, g, Cin / g, Cout, Cout, nb, per));
+    // classes per virtual CTA: one round of CTAs when that is possible with <= MIXT_KSEG classes each
+    int kseg = 1;
+    while (kseg < MIXT_KSEG && (long long)((K + kseg - 1) / kseg) * elt_chunks(per) > WC_NUM_SMS) ++kseg;
+    const int mixt_ctas = ((K + kseg - 1) / kseg) * elt_chunks(per);
+    // stage 2: T_k, as fp32 and as the operand images of K3 / K6
+    const bool images = (Tp_fwd || Tp_bwd) && (CH_ELT_CHUNK % Cin) == 0 && (CH_ELT_CHUNK / Cin) % 8 == 0 && (Cin % 32) == 0;
+    { EltJob j{}; j.a = TB; j.out = T; j.n = per; j.K = K; j.E = E; j.ehat = ehat; j.has_u = has_u; j.C = Cout;
+      if (images) { j.pk0 = (uint8_t*)Tp_fwd; j.pk1 = (uint8_t*)Tp_bwd; }
+      j.kseg = kseg;
+      cb.elt(2, CJ_MIXT, j, mixt_ctas); }
+    int rcc = cb.launch(barrier, st);
+    if (rcc == 0) {
+      if (!images) {
+        if (Tp_fwd) { rcc = wc_pack_fwd(T, Cin, K, Tp_fwd, (wc_stream_t)st); if (rcc) return rcc; }
+        if (Tp_bwd) { rcc = wc_pack_bwd(T, nullptr, Cin, g, K, Tp_bwd, (wc_stream_t)st); if (rcc) return rcc; }
+      }
+      return 0;
+    }
+    if (rcc != WC_E_UNSUPPORTED) return rcc;
+  }
   if (Weff && Cin == Cout && (Cin % 32) == 0 && (g % 32) == 0 && !(wc_debug_flags() & 262144)) {
     ChainBuilder cb;
     int st_t = 0;
@@ -1442,7 +1664,10 @@ extern "C" int wc_compose_fwd(const float* Weff, int Cin, int Cout, int g, int K
                               const float* D, int E, const float* bf, float* ehat, float* Wk, float* T, float* b,
                               wc_stream_t stream) {
   return wc_compose_fwd_impl(Weff, Cin, Cout, g, K, Wu, bu, Wc, bc, triangular, class_matrix, D, E, bf, ehat, Wk, T, b,
-                             nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+                             nullptr, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+size_t wc_compose_fact_workspace_bytes(int C, int K, int E, bool has_class_matrix, bool has_wc) {
+  return wc_bwd_factorised_ok(C, K, E, has_class_matrix, has_wc) ? (size_t)2 * (E + 1) * C * C * sizeof(float) : 0;
 }
 
 // =============================================================================================
@@ -1657,6 +1882,22 @@ int wc_factor_bwd_impl(const float* dWeff, const float* gbar, const float* Weff,
   return 0;
 }
 
+// The factorised forms need (3E + 2) C^2 + (E + 1) C floats of scratch, taken from the K C^2 floats the per-class Q would
+// occupy, and pay one more grid barrier: worth it from K >= 3E + 4.
+bool wc_bwd_factorised_ok(int C, int K, int E, bool has_class_matrix, bool has_wc) {
+  return has_class_matrix && !has_wc && E > 0 && E + 1 <= MIX_MAXB && K >= 3 * E + 4 && K <= MIX_MAXK && (C % 4) == 0 &&
+         !(wc_debug_flags() & 8388608);
+}
+
+// The factorised forward never forms W_k; a backward path that reads it calls this first.
+int wc_rebuild_wk(int Cin, int Cout, int K, const float* Wu, const float* class_matrix, const float* D, int E, float* Wk, cudaStream_t st) {
+  const long long per = (long long)Cin * Cout;
+  WC_CUDA(wc_launch(build_wk_kernel, wc_cdiv(per * K, 256), 256, 0, st, Cin, Cout, K, Wu, (const float*)nullptr, (const float*)nullptr,
+                    (const float*)nullptr, 0, class_matrix, D, E, (const float*)nullptr, (float*)nullptr, Wk, (float*)nullptr, 0));
+  WC_CHECK_LAUNCH();
+  return 0;
+}
+
 // =============================================================================================
 // K5a + K5b as one persistent launch (Cholesky whitening, no renorm, tile-aligned shapes)
 // =============================================================================================
@@ -1665,14 +1906,20 @@ int wc_factor_bwd_impl(const float* dWeff, const float* gbar, const float* Weff,
 //   1: Psi from Z = dWeff Wm^T, cvec = Weff^T gbar / count, dWu = sum_k Q_k, dD = ehat^T Q, de = <Q_k, D_e>
 //   2: Y^T = (Psi Wm)^T, dclass_matrix = l2_normalize'(de)
 //   3: A = (1-eps)/(count-1) Wm^T Y  (+ its bf16 operand image for K6)
+// Factorised coloring with many classes (fconv / ufconv, K >= 3 E + 4, whole chain in one launch): W_k = sum_j alpha[k,j] B_j
+// over the E + 1 basis matrices B_0 = Wu, B_e = D_e, so stage 0 is replaced by two stages that never form a per-class
+// product (wc_bwd_factorised_ok):
+//   0a: G_j = sum_k alpha[k,j] P_k, gs_j = sum_k alpha[k,j] s_k, Bcat = [Wu; D], TB_e = Weff^T D_e, dbu, dbf
+//   0b: dWeff = sum_j B_j G_j^T, gbar = sum_j B_j gs_j, dWu = Weff G_0, dD_e = Weff G_e, de[k,e] = <P_k, TB_e>
+// (E + 1 products where the direct form has K: 16 instead of 200 for the Tiny-ImageNet generator.)
 // A synchronised-batch layer runs [0,1), all-reduces red = {dWeff, gbar}, then [1,4).  Returns WC_E_UNSUPPORTED when a
 // shape does not fit the tile routine (the caller then takes the launch-per-product path).  `barrier`: one zeroed u32.
-int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float* Wk, int Cin, int Cout, int g, int K,
+int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float* Wk, const float* Wu, int Cin, int Cout, int g, int K,
                  float* dWu, float* dbu, float* dWc, float* dbc, int triangular, const float* class_matrix, const float* ehat,
                  const float* D, int E, float* dD, float* dclass_matrix, float* dbf, float* red, float* A, float* cvec,
                  const float* count_dev, double count_host, float eps, void* Tp_bwd, int pack_K, float* ws_color,
                  float* ws_factor, unsigned* barrier, int stage_lo, int stage_hi, void* const* xchg_peers, void* xchg_state,
-                 int xchg_rank, int xchg_world, int32_t* info, cudaStream_t st) {
+                 int xchg_rank, int xchg_world, int32_t* info, int wk_missing, cudaStream_t st) {
   if (!P || !s || !Weff || !Wk || !red || !barrier || Cin != Cout || g <= 0 || Cin % g) return WC_E_UNSUPPORTED;
   if (triangular && dWc) return WC_E_UNSUPPORTED;
   if ((dD || dclass_matrix) && (!class_matrix || !ehat || !D || E <= 0)) return WC_E_ARG;
@@ -1700,8 +1947,52 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
     x.data_off = XL.bwd_off; x.slot_words = XL.bwd_words; x.rank = xchg_rank; x.R = xchg_world; x.stage = 1;
   }
   auto in = [&](int stage) { return stage >= stage_lo && stage < stage_hi; };
-  const int base = stage_lo;     // stages are renumbered from 0 inside the launch
-  if (in(0)) {
+  int base = stage_lo;           // stages are renumbered from 0 inside the launch
+  const bool fact = wc_bwd_factorised_ok(C, K, E, class_matrix != nullptr, dWc != nullptr) && D && stage_lo == 0 && stage_hi == 4 &&
+                    (!dWu || Wu) && !dbc;
+  if (fact) {
+    const bool has_u = Wu != nullptr;
+    const int nb = E + (has_u ? 1 : 0), j0 = has_u ? 0 : 1;       // basis slots [j0, E]
+    float* Gm = Qws;                                   // (E+1) x per
+    float* Bcat = Gm + (size_t)(E + 1) * per;          // (E+1) x per
+    float* TB = Bcat + (size_t)(E + 1) * per;          // E x per
+    float* gs = TB + (size_t)E * per;                  // (E+1) x C
+    // ---- 0a
+    { EltJob j{}; j.a = P; j.out = Gm; j.n = per; j.K = K; j.E = E; j.ehat = ehat; j.has_u = has_u;
+      cb.elt(0, CJ_MIXK, j, (int)((per + MIX_EPB - 1) / MIX_EPB)); }
+    { EltJob j{}; j.a = s; j.out = gs; j.n = C; j.K = K; j.E = E; j.ehat = ehat; j.has_u = has_u;
+      cb.elt(0, CJ_MIXK, j, (C + MIX_EPB - 1) / MIX_EPB); }
+    if (has_u) { EltJob j{}; j.a = Wu; j.out = Bcat; j.n = per; j.K = 1; cb.elt(0, CJ_COPY, j, elt_chunks(per)); }
+    { EltJob j{}; j.a = D; j.out = Bcat + per; j.n = (long long)E * per; j.K = 1; cb.elt(0, CJ_COPY, j, elt_chunks(j.n)); }
+    if (dclass_matrix) cb.smm(0, smm_blockdiag_left(Weff, true, D, TB, g, G, C, C, E, per));
+    if (dbu) {
+      VecJob u{};
+      u.A = s; u.x = nullptr; u.out = dbu; u.M = C; u.K = K; u.rsA = 1; u.csA = C;
+      u.nsum = 1; u.nb = 1; u.alpha = 1.f;
+      cb.vec(0, u);
+    }
+    if (dbf) { EltJob j{}; j.a = s; j.out = dbf; j.n = (long long)K * C; j.K = 1; cb.elt(0, CJ_COPY, j, elt_chunks(j.n)); }
+    // ---- 0b (the long jobs first: a CTA takes virtual CTAs round-robin)
+    if (dclass_matrix) {
+      EltJob j{}; j.a = P; j.b = TB; j.out = de; j.n = per; j.K = K; j.E = E;
+      if (per <= 32 * SMM_THREADS) cb.elt(1, CJ_DOT2, j, (K + 1) / 2); else cb.elt(1, CJ_DOT, j, K * E);
+    }
+    WcSmm pw = smm_init();
+    pw.A = Bcat + (size_t)j0 * per; pw.B = Gm + (size_t)j0 * per; pw.C = dWeff; pw.M = g; pw.N = g; pw.K = C;
+    pw.rsA = C; pw.csA = 1; pw.rsB = 1; pw.csB = C; pw.rsC = g; pw.csC = 1;
+    pw.nb1 = 1; pw.nb2 = G; pw.bA2 = (long long)g * C; pw.bB2 = (long long)g * C; pw.bC2 = (long long)g * g;
+    pw.nsum = nb; pw.sA = per; pw.sB = per;
+    cb.smm(1, pw);
+    VecJob v{};
+    v.A = Bcat + (size_t)j0 * per; v.x = gs + (size_t)j0 * C; v.out = gbar; v.M = C; v.K = C; v.rsA = C; v.csA = 1;
+    v.nsum = nb; v.sA = per; v.sx = C; v.nb = 1; v.alpha = 1.f;
+    cb.vec(1, v);
+    if (dWu) cb.smm(1, smm_blockdiag_left(Weff, false, Gm, dWu, g, G, C, C, 1, per));
+    if (dD) cb.smm(1, smm_blockdiag_left(Weff, false, Gm + per, dD, g, G, C, C, E, per));
+    base = -1;                                         // the remaining stages move up by one
+    if (cb.pr.xch.R > 1) cb.pr.xch.stage = 2;
+  } else if (in(0)) {
+    if (wk_missing) { const int rcw = wc_rebuild_wk(C, C, K, Wu, class_matrix, D, E, const_cast<float*>(Wk), st); if (rcw) return rcw; }
     if (need_q) cb.smm(0 - base, smm_blockdiag_left(Weff, false, P, Qdst, g, G, C, C, K, per));
     WcSmm pw = smm_init();
     pw.A = Wk; pw.B = P; pw.C = dWeff; pw.M = g; pw.N = g; pw.K = C;
@@ -1730,9 +2021,11 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
     vc.nsum = 1; vc.nb = G; vc.bA = (long long)g * g; vc.bx = g; vc.bo = g;
     vc.count_dev = count_dev; vc.count_host = ch; vc.count_mode = 1; vc.alpha = 1.f;
     cb.vec(1 - base, vc);
-    if (dWu && Qdst != dWu) { EltJob j{}; j.a = Qdst; j.out = dWu; j.n = per; j.K = K; cb.elt(1 - base, CJ_SUMK, j, elt_chunks(per)); }
-    if (dD) { EltJob j{}; j.a = Qdst; j.out = dD; j.n = per; j.K = K; j.E = E; j.ehat = ehat; cb.elt(1 - base, CJ_WSUMK, j, E * elt_chunks(per)); }
-    if (dclass_matrix) { EltJob j{}; j.a = Qdst; j.b = D; j.out = de; j.n = per; j.K = K; j.E = E; cb.elt(1 - base, CJ_DOT, j, K * E); }
+    if (!fact) {
+      if (dWu && Qdst != dWu) { EltJob j{}; j.a = Qdst; j.out = dWu; j.n = per; j.K = K; cb.elt(1 - base, CJ_SUMK, j, elt_chunks(per)); }
+      if (dD) { EltJob j{}; j.a = Qdst; j.out = dD; j.n = per; j.K = K; j.E = E; j.ehat = ehat; cb.elt(1 - base, CJ_WSUMK, j, E * elt_chunks(per)); }
+      if (dclass_matrix) { EltJob j{}; j.a = Qdst; j.b = D; j.out = de; j.n = per; j.K = K; j.E = E; cb.elt(1 - base, CJ_DOT, j, K * E); }
+    }
   }
   if (in(2)) {
     WcSmm py = smm_gg(W0, false, Weff, false, W1, g, G);

@@ -271,3 +271,27 @@ def cluster_cholesky_inverse(A: Tensor, tb: int = 32):
                 S += blk(L, I, K) @ blk(X, K, r)
             blk(X, I, r).copy_(-Dinv[I] @ S)
     return L, X
+
+
+def factorised_coloring(Weff: Tensor, Wu: Optional[Tensor], D: Tensor, ehat: Tensor, P: Tensor, s: Tensor):
+    """The factorised forms the chain kernel uses for fconv / ufconv with many classes (wc_small.cu, wc_bwd_chain /
+    wc_compose_fwd_impl): with W_k = sum_j alpha[k,j] B_j over the E + 1 basis matrices B_0 = Wu, B_e = D_e
+    (alpha[k,0] = 1, alpha[k,e] = ehat[k,e-1]; generator.py:45-48,74-76, conditional_layers.py:993-1005), no per-class
+    product is ever formed:
+        T_k   = sum_j alpha[k,j] (Weff^T B_j)                   G_j = sum_k alpha[k,j] P_k,  gs_j = sum_k alpha[k,j] s_k
+        dWeff = sum_j B_j G_j^T     gbar = sum_j B_j gs_j       dB_j = Weff G_j  (dWu, dD)   de[k,e] = <P_k, Weff^T D_e>
+    Weff (C,C) dense (block-diagonal matrices are a special case), Wu (C,C) or None, D (E,C,C), ehat (K,E), P (K,C,C) with
+    P_k = sum_{n in k} xc_n^T dy_n, s (K,C).  Returns dict(T, dWeff, gbar, dWu, dD, de)."""
+    K, E = ehat.shape
+    one = torch.ones(K, 1, dtype=ehat.dtype) if Wu is not None else torch.zeros(K, 1, dtype=ehat.dtype)
+    alpha = torch.cat([one, ehat], dim=1)                                   # (K, E+1)
+    B = torch.cat([(Wu if Wu is not None else torch.zeros_like(D[0]))[None], D], dim=0)     # (E+1, C, C)
+    TB = Weff.transpose(0, 1) @ B                                           # E + 1 products
+    T = torch.einsum('kj,jab->kab', alpha, TB)
+    G = torch.einsum('kj,kab->jab', alpha, P)
+    gs = alpha.transpose(0, 1) @ s
+    dWeff = torch.einsum('jab,jcb->ac', B, G)
+    gbar = torch.einsum('jab,jb->a', B, gs)
+    dB = Weff @ G
+    de = torch.einsum('kab,eab->ke', P, TB[1:])
+    return dict(T=T, dWeff=dWeff, gbar=gbar, dWu=dB[0] if Wu is not None else None, dD=dB[1:], de=de)

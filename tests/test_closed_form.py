@@ -137,3 +137,25 @@ def test_cluster_cholesky_schedule(n):
     assert float((L - Lr).abs().max()) < 1e-10 * float(Lr.abs().max())
     assert float((X @ Lr - torch.eye(n, dtype=torch.float64)).abs().max()) < 1e-8
     assert float(torch.triu(X, 1).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('has_u', [True, False])
+def test_factorised_coloring_forms(has_u):
+    """fconv / ufconv with many classes: the E + 1 basis products + mixing passes of the chain kernel equal the direct
+    per-class forms (T_k = Weff^T W_k, dWeff = sum_k W_k P_k^T, gbar = sum_k W_k s_k, dW_k = Weff P_k reduced to dWu / dD /
+    de) that the rest of the library -- and autograd over the oracle -- use."""
+    torch.manual_seed(2)
+    C, K, E = 12, 17, 3
+    f = lambda *sh: torch.randn(*sh, dtype=torch.float64)
+    Weff, Wu, D, P, s = f(C, C), (f(C, C) if has_u else None), f(E, C, C), f(K, C, C), f(K, C)
+    ehat = torch.nn.functional.normalize(f(K, E), dim=1)
+    got = CF.factorised_coloring(Weff, Wu, D, ehat, P, s)
+    Wk = torch.einsum('ke,eab->kab', ehat, D) + (Wu if has_u else 0.0)
+    Q = Weff @ P                                                            # dW_k
+    ref = dict(T=Weff.t() @ Wk, dWeff=torch.einsum('kab,kcb->ac', Wk, P), gbar=torch.einsum('kab,kb->a', Wk, s),
+               dWu=Q.sum(0) if has_u else None, dD=torch.einsum('ke,kab->eab', ehat, Q), de=torch.einsum('kab,eab->ke', Q, D))
+    for name, r in ref.items():
+        if r is None:
+            assert got[name] is None
+            continue
+        assert float((got[name] - r).abs().max()) < 1e-12 * float(r.abs().max()) + 1e-14, name

@@ -49,15 +49,17 @@ def _worker(rank, world, port, q, shape, after_norm, K, E, transport):
 
 
 @pytest.mark.parametrize('transport', ['peer', 'nccl'])
-@pytest.mark.parametrize('shape,after_norm', [((8, 8, 8, 128), 'ufconv'), ((4, 16, 16, 256), 'uconv'), ((6, 4, 4, 24), 'ucconv')])
-def test_sharded_equals_single(shape, after_norm, transport):
+@pytest.mark.parametrize('shape,after_norm,K,E', [((8, 8, 8, 128), 'ufconv', 5, 3), ((4, 16, 16, 256), 'uconv', 5, 3),
+                                                   ((6, 4, 4, 24), 'ucconv', 5, 3), ((16, 4, 4, 128), 'ufconv', 40, 4)])
+def test_sharded_equals_single(shape, after_norm, K, E, transport):
     """transport 'peer': statistics and adjoint exchanged inside the library's kernels over symmetric peer memory
     (wc_exchange.cu); 'nccl': host-issued all-gather / all-reduce between the phases."""
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     import wc_gan_b200 as W
     from oracle import wc_oracle as O
-    K, E = 5, 3
+    # (K = 40, E = 4: the factorised coloring forms; with the peer transport the adjoint all-reduce is a stage of that
+    # chain launch, with NCCL the split-phase backward rebuilds the W_k the forward did not form)
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()

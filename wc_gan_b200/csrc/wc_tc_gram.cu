@@ -54,6 +54,12 @@ struct TcGramParams {
 // operand stages are half as large.  The column-sum scratch and the
 // 4 KB boxes of the flush alias a ring that is idle when they are used: the operand ring (every MMA has been committed)
 // or, in self mode -- which only ever flushes once, at the end -- the staging ring.
+#ifndef WC_GRAM_NOPS_SELF
+#define WC_GRAM_NOPS_SELF 3
+#endif
+#ifndef WC_GRAM_NOPS_CROSS
+#define WC_GRAM_NOPS_CROSS 3
+#endif
 template <int C, bool SELF>
 struct GCfg {
   static constexpr int SLOT = KR * C * 4;                  // one fp32 staging slab: 16 KB (C=256)
@@ -62,7 +68,8 @@ struct GCfg {
   static constexpr int TMEM_COLS = MH * C;                 // 512 (C=256) / 128
   static constexpr int OPSTAGE = (SELF ? 2 : 4) * IMG;
   static constexpr int FLUSH_BYTES = NCONV_WARPS * 4096 + NCONV_WARPS * C * 4;     // boxes + column sums
-  static constexpr int NOPS = SELF ? 3 : (FLUSH_BYTES + OPSTAGE - 1) / OPSTAGE;    // cross: the flush scratch fits the ring
+  static constexpr int NOPS_X = (FLUSH_BYTES + OPSTAGE - 1) / OPSTAGE;             // cross: the flush scratch fits the ring
+  static constexpr int NOPS = SELF ? WC_GRAM_NOPS_SELF : (NOPS_X > WC_GRAM_NOPS_CROSS ? NOPS_X : WC_GRAM_NOPS_CROSS);
   static constexpr int BUDGET = 231424 - 1024 - 1024;      // 226 KB per CTA minus alignment slack and static barriers
   static constexpr int NSLOTS_FIT = (BUDGET - NOPS * OPSTAGE) / SLOT;
   // measured: K4 gains 4 us from 8 slabs instead of 6; K1 LOSES 2 us with 11 (its main loop is not bound by the bytes in

@@ -12,8 +12,8 @@
 // 1/sqrt(M); the dropped lo.lo term biases the diagonal by ~1e-6 relative ("Accuracy").
 //
 // One persistent CTA per SM (576 threads) owns a contiguous range of row units.  Three pipelines:
-//   warp  16   producer (one thread): 1-D cp.async.bulk of 16-row slabs (rows are contiguous in NHWC) into the
-//              fp32 staging ring (8 slabs for K4, 6 for K1 at C=256: 128 / 96 KB in flight per SM)
+//   warp  16   producer (one thread): 1-D cp.async.bulk of the rows of a step (contiguous in NHWC) into the
+//              fp32 staging ring (128 KB in flight per SM)
 //   warps 0-15 converters: ld.shared fp32 -> shift -> bf16 hi/lo -> MN-major SWIZZLE_128B operand tiles,
 //              column sums on the fly; at a slot change they drain the accumulator (tcgen05.ld -> red.global.add)
 //   warp  17   MMA issuer (one thread), owns TMEM
@@ -62,20 +62,24 @@ struct TcGramParams {
 #endif
 template <int C, bool SELF>
 struct GCfg {
-  static constexpr int SLOT = KR * C * 4;                  // one fp32 staging slab: 16 KB (C=256)
-  static constexpr int IMG = KR * C * 2;                   // one bf16 split of one operand: 8 KB (C=256)
+  // A pipeline step (one trip through the producer / converter / MMA hand-shakes) costs ~0.4 us of mbarrier round trips
+  // whatever its size, so a step carries NSUB sixteen-row MMA slices: 32 KB of rows where shared memory allows it
+  // (measured at C = 128, 16-row steps: K1 2.5 TB/s, K4 4.0 TB/s while the apply kernels run at 5.6-6.2 TB/s).
+  static constexpr int NSUB = SELF ? (C == 128 ? 4 : 2) : (C == 128 ? 2 : 1);
+  static constexpr int RS = KR * NSUB;                     // rows per step
+  static constexpr int SLOT = RS * C * 4;                  // one fp32 staging slab
+  static constexpr int IMG = KR * C * 2;                   // one bf16 split of one operand, 16 rows: 8 KB (C=256)
   static constexpr int MH = C / 128;                       // M halves
   static constexpr int TMEM_COLS = MH * C;                 // 512 (C=256) / 128
-  static constexpr int OPSTAGE = (SELF ? 2 : 4) * IMG;
+  static constexpr int SUBSTAGE = (SELF ? 2 : 4) * IMG;    // operand images of one 16-row slice
+  static constexpr int OPSTAGE = NSUB * SUBSTAGE;
+  static_assert(UNIT_ROWS % RS == 0, "a unit is a whole number of steps");
   static constexpr int FLUSH_BYTES = NCONV_WARPS * 4096 + NCONV_WARPS * C * 4;     // boxes + column sums
   static constexpr int NOPS_X = (FLUSH_BYTES + OPSTAGE - 1) / OPSTAGE;             // cross: the flush scratch fits the ring
   static constexpr int NOPS = SELF ? WC_GRAM_NOPS_SELF : (NOPS_X > WC_GRAM_NOPS_CROSS ? NOPS_X : WC_GRAM_NOPS_CROSS);
   static constexpr int BUDGET = 231424 - 1024 - 1024;      // 226 KB per CTA minus alignment slack and static barriers
   static constexpr int NSLOTS_FIT = (BUDGET - NOPS * OPSTAGE) / SLOT;
-  // measured: K4 gains 4 us from 8 slabs instead of 6; K1 LOSES 2 us with 11 (its main loop is not bound by the bytes in
-  // flight), so self mode keeps 6
-  static constexpr int NSLOTS_SELF = (FLUSH_BYTES + SLOT - 1) / SLOT > 6 ? (FLUSH_BYTES + SLOT - 1) / SLOT : 6;
-  static constexpr int NSLOTS = SELF ? NSLOTS_SELF : (NSLOTS_FIT > 16 ? 16 : NSLOTS_FIT);
+  static constexpr int NSLOTS = NSLOTS_FIT > 16 ? 16 : NSLOTS_FIT;
   static constexpr int SMEM = NSLOTS * SLOT + NOPS * OPSTAGE + 1024;
   static constexpr int CQ = C / 4, RG = NCONV / CQ;        // pivot: threads per row, row groups
   static_assert(NOPS >= 3, "operand ring too shallow");
@@ -88,8 +92,8 @@ struct Step { int sample, row0, nrows, slot; bool flush_before; bool valid; };
 struct StepIter {
   const TcGramParams& p;
   long long units_left;
-  int sidx, sub, r_in_unit, cur_slot, sample, slot;
-  __device__ StepIter(const TcGramParams& p_, long long ub, long long ue) : p(p_), units_left(ue - ub), r_in_unit(0), cur_slot(-1) {
+  int sidx, sub, r_in_unit, cur_slot, sample, slot, rs;        // rs: rows per step (a multiple of KR that divides UNIT_ROWS)
+  __device__ StepIter(const TcGramParams& p_, long long ub, long long ue, int rs_) : p(p_), units_left(ue - ub), r_in_unit(0), cur_slot(-1), rs(rs_) {
     sidx = (int)(ub / p.ups); sub = (int)(ub % p.ups);    // the only division: next() advances incrementally
     load_sample();
   }
@@ -104,12 +108,12 @@ struct StepIter {
     const int unrows = min(UNIT_ROWS, p.HW - urow0);
     s.sample = sample;
     s.row0 = urow0 + r_in_unit;
-    s.nrows = min(KR, unrows - r_in_unit);
+    s.nrows = min(rs, unrows - r_in_unit);
     s.slot = slot;
     s.flush_before = (cur_slot >= 0 && s.slot != cur_slot);
     s.valid = true;
     cur_slot = s.slot;
-    r_in_unit += KR;
+    r_in_unit += rs;
     if (r_in_unit >= unrows) {
       r_in_unit = 0; --units_left;
       if (++sub == p.ups) { sub = 0; ++sidx; if (units_left > 0) load_sample(); }
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
   if (warp == NCONV_WARPS) {
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
-      StepIter iter(p, ub, ue);
+      StepIter iter(p, ub, ue, cfg::RS);
       uint32_t pi = 0;
       const uint64_t pol = l2_policy(p.l2_load);
       for (Step st = iter.next(); st.valid; st = iter.next()) {
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
       const uint32_t idesc_full = make_idesc_bf16(128, C, 1, 1);
       // self mode, first M half: only the columns j < 128 are ever read back (the scatter is symmetric)
       const uint32_t idesc_half = make_idesc_bf16(128, 128, 1, 1);
-      StepIter iter(p, ub, ue);
+      StepIter iter(p, ub, ue, cfg::RS);
       uint32_t acc = 0, nflush = 0;
       int it = 0;
       for (Step st = iter.next(); st.valid; st = iter.next(), ++it) {
@@ -194,25 +198,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
         const int s = it % cfg::NOPS;
         mbar_wait(&op_full[s], (it / cfg::NOPS) & 1);
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(ops + s * cfg::OPSTAGE);
-        const uint32_t a_lo = a_hi + cfg::IMG;
-        const uint32_t b_hi = SELF ? a_hi : a_hi + 2 * cfg::IMG;
-        const uint32_t b_lo = b_hi + cfg::IMG;
-        const uint64_t dbh = make_desc(b_hi, KR * 128, 1024, LAYOUT_SW128);
-        const uint64_t dbl = make_desc(b_lo, KR * 128, 1024, LAYOUT_SW128);
 #pragma unroll
-        for (int mh = 0; mh < cfg::MH; ++mh) {
-          const uint32_t aoff = mh * 2 * (KR * 128);   // M half = two 64-channel blocks
-          const uint64_t dah = make_desc(a_hi + aoff, KR * 128, 1024, LAYOUT_SW128);
-          const uint64_t dal = make_desc(a_lo + aoff, KR * 128, 1024, LAYOUT_SW128);
-          const uint32_t tdm = td + mh * C;
-          const uint32_t idesc = (SELF && cfg::MH == 2 && mh == 0) ? idesc_half : idesc_full;
-          if (p.dbg_flags & 4) continue;
-          umma_bf16(tdm, dah, dbh, idesc, acc);
-          umma_bf16(tdm, dah, dbl, idesc, 1);
-          umma_bf16(tdm, dal, dbh, idesc, 1);
+        for (int sub = 0; sub < cfg::NSUB; ++sub) {
+          if (sub * KR >= st.nrows) break;             // a short step (end of a unit): the remaining slices hold no rows
+          const uint32_t a_hi = smem_u32(ops + s * cfg::OPSTAGE + sub * cfg::SUBSTAGE);
+          const uint32_t a_lo = a_hi + cfg::IMG;
+          const uint32_t b_hi = SELF ? a_hi : a_hi + 2 * cfg::IMG;
+          const uint32_t b_lo = b_hi + cfg::IMG;
+          const uint64_t dbh = make_desc(b_hi, KR * 128, 1024, LAYOUT_SW128);
+          const uint64_t dbl = make_desc(b_lo, KR * 128, 1024, LAYOUT_SW128);
+#pragma unroll
+          for (int mh = 0; mh < cfg::MH; ++mh) {
+            const uint32_t aoff = mh * 2 * (KR * 128);   // M half = two 64-channel blocks
+            const uint64_t dah = make_desc(a_hi + aoff, KR * 128, 1024, LAYOUT_SW128);
+            const uint64_t dal = make_desc(a_lo + aoff, KR * 128, 1024, LAYOUT_SW128);
+            const uint32_t tdm = td + mh * C;
+            const uint32_t idesc = (SELF && cfg::MH == 2 && mh == 0) ? idesc_half : idesc_full;
+            if (p.dbg_flags & 4) continue;
+            umma_bf16(tdm, dah, dbh, idesc, acc);
+            umma_bf16(tdm, dah, dbl, idesc, 1);
+            umma_bf16(tdm, dal, dbh, idesc, 1);
+          }
+          acc = 1;
         }
-        acc = 1;
         umma_commit(&op_empty[s]);
       }
       umma_commit(&acc_full);
@@ -358,7 +366,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
       }
     };
 
-    StepIter iter(p, ub, ue);
+    StepIter iter(p, ub, ue, cfg::RS);
     uint32_t nflush = 0;
     int it = 0, cur_slot = -1;
     for (Step st = iter.next(); st.valid; st = iter.next(), ++it) {
@@ -369,42 +377,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
       const uint32_t pi = SELF ? (uint32_t)it : 2u * it + grp;
       const int sl = pi % cfg::NSLOTS;
       mbar_wait(&stg_full[sl], (pi / cfg::NSLOTS) & 1);
-      uint32_t hi[2][QPR][2], lo[2][QPR][2];
-      if (!(p.dbg_flags & 8)) {
-        const uint32_t src = stg_u32 + sl * cfg::SLOT + ld_off;
-        float4 v[2][QPR];
+      // (the operand stage is claimed before the rows are read: the words of a sixteen-row slice then go straight from the
+      // conversion into the tile, and a step of several slices needs no more registers than one)
+      mbar_wait(&op_empty[s], ((it / cfg::NOPS) & 1) ^ 1);
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr)
+      for (int sub = 0; sub < cfg::NSUB; ++sub) {
+        if (sub * KR >= st.nrows) break;               // warp-uniform: nothing to convert, the MMA issuer skips the slice too
+        uint32_t hi[2][QPR][2], lo[2][QPR][2];
+        if (!(p.dbg_flags & 8)) {
+          const uint32_t src = stg_u32 + sl * cfg::SLOT + sub * (KR * C * 4) + ld_off;
+          float4 v[2][QPR];
 #pragma unroll
-          for (int j = 0; j < QPR; ++j) v[rr][j] = lds128(src + rr * (C * 4) + j * 512);
+          for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          const bool ok = (r0 + rr) < st.nrows;      // rows past the slab end: stale staging, contribute zero
+            for (int j = 0; j < QPR; ++j) v[rr][j] = lds128(src + rr * (C * 4) + j * 512);
 #pragma unroll
-          for (int j = 0; j < QPR; ++j) {
-            float4 a = v[rr][j];
-            a.x -= mean[j].x; a.y -= mean[j].y; a.z -= mean[j].z; a.w -= mean[j].w;
-            if (!ok) a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (want) { sum[j][0] += a.x; sum[j][1] += a.y; sum[j][2] += a.z; sum[j][3] += a.w; }
-            split2(a.x, a.y, hi[rr][j][0], lo[rr][j][0]);
-            split2(a.z, a.w, hi[rr][j][1], lo[rr][j][1]);
+          for (int rr = 0; rr < 2; ++rr) {
+            const bool ok = (sub * KR + r0 + rr) < st.nrows;      // rows past the end of the step: stale staging, contribute zero
+#pragma unroll
+            for (int j = 0; j < QPR; ++j) {
+              float4 a = v[rr][j];
+              a.x -= mean[j].x; a.y -= mean[j].y; a.z -= mean[j].z; a.w -= mean[j].w;
+              if (!ok) a = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (want) { sum[j][0] += a.x; sum[j][1] += a.y; sum[j][2] += a.z; sum[j][3] += a.w; }
+              split2(a.x, a.y, hi[rr][j][0], lo[rr][j][0]);
+              split2(a.z, a.w, hi[rr][j][1], lo[rr][j][1]);
+            }
           }
+          const uint32_t dst = ops_u32 + s * cfg::OPSTAGE + sub * cfg::SUBSTAGE + my_op * 2 * cfg::IMG;
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+            for (int j = 0; j < QPR; ++j) {
+              sts64(dst + st_off[rr] + j * 2 * (KR * 128), hi[rr][j][0], hi[rr][j][1]);
+              sts64(dst + cfg::IMG + st_off[rr] + j * 2 * (KR * 128), lo[rr][j][0], lo[rr][j][1]);
+            }
         }
       }
-      // the slab has been consumed into registers: hand it back to the producer
+      // the slab has been consumed: hand it back to the producer
       __syncwarp();
       if (lane == 0) mbar_arrive(&stg_empty[sl]);
-      mbar_wait(&op_empty[s], ((it / cfg::NOPS) & 1) ^ 1);
-      if (!(p.dbg_flags & 8)) {
-        const uint32_t dst = ops_u32 + s * cfg::OPSTAGE + my_op * 2 * cfg::IMG;
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-          for (int j = 0; j < QPR; ++j) {
-            sts64(dst + st_off[rr] + j * 2 * (KR * 128), hi[rr][j][0], hi[rr][j][1]);
-            sts64(dst + cfg::IMG + st_off[rr] + j * 2 * (KR * 128), lo[rr][j][0], lo[rr][j][1]);
-          }
-      }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&op_full[s]);

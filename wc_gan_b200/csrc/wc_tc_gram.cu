@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
 
   if (t == 0) {
     for (int s = 0; s < cfg::NSLOTS; ++s) { mbar_init(&stg_full[s], 1); mbar_init(&stg_empty[s], NCONV_WARPS / 2); }
-    for (int s = 0; s < cfg::NOPS; ++s) { mbar_init(&op_full[s], SELF ? NCONV_WARPS / 2 : NCONV_WARPS); mbar_init(&op_empty[s], 1); }
+    for (int s = 0; s < cfg::NOPS; ++s) { mbar_init(&op_full[s], NCONV_WARPS / 2); mbar_init(&op_empty[s], 1); }
     mbar_init(&acc_full, 1);
     mbar_init(&acc_empty, NCONV_WARPS);
     mbar_fence_init();
@@ -227,14 +227,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
     }
   } else {
     // ------------------------------------------------------------------ converters
-    // Two groups of 8 warps work on different slabs at the same time: K4: group 0 converts x (operand A), group 1
-    // dy (operand B) of the same step; K1: the groups take alternate steps.  Within a group a warp owns 2 rows of the
-    // slab; a lane owns the 4-channel quads {lane, lane+32} of a row (conflict-free ld.shared.v4 / st.shared.v2).
+    // Two groups of 8 warps take alternate steps (K4: a group converts both operands of its step), so that the hand-shake
+    // latencies of one step run under the conversion of the other.  Within a group a warp owns 2 rows of a sixteen-row
+    // slice; a lane owns the 4-channel quads {lane, lane+32} of a row (conflict-free ld.shared.v4 / st.shared.v2).
     const int grp = warp >> 3, wg = warp & 7;
     const uint32_t stg_u32 = smem_u32(stg), ops_u32 = smem_u32(ops);
     constexpr int QPR = C / 128;              // quads per lane per row
-    const int my_op = SELF ? 0 : grp;
-    const bool want = my_op == 0 ? (p.asum != nullptr) : (p.bsum != nullptr);
+    // cross mode: A is shifted by ma and has no column sums, B is not shifted and has them (what K4 needs; the launcher
+    // refuses anything else), so a thread keeps one shift and one set of sums whichever operand it converts
+    const bool want = SELF ? (p.asum != nullptr) : (p.bsum != nullptr);
     float sum[QPR][4];
     float4 mean[QPR];
 #pragma unroll
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
       for (int j = 0; j < QPR; ++j) mean[j] = *reinterpret_cast<const float4*>(&spiv[0][(lane + 32 * j) * 4]);
       asm volatile("bar.sync 1, %0;" ::"n"(NCONV));
     } else {
-      const float* m = my_op == 0 ? p.ma : p.mb;
+      const float* m = p.ma;
       if (m) {
 #pragma unroll
         for (int j = 0; j < QPR; ++j) mean[j] = *reinterpret_cast<const float4*>(m + (lane + 32 * j) * 4);
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
       for (int pass = 0; pass < 2; ++pass) {
         float* gsum = pass == 0 ? p.asum : p.bsum;
         if (!gsum || (pass == 1 && SELF)) continue;
-        const bool mine = (my_op == pass);
+        const bool mine = SELF ? (pass == 0) : (pass == 1);
         asm volatile("bar.sync 1, %0;" ::"n"(NCONV));
 #pragma unroll
         for (int j = 0; j < QPR; ++j) {
@@ -372,14 +373,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
     for (Step st = iter.next(); st.valid; st = iter.next(), ++it) {
       if (st.flush_before) { flush(cur_slot, nflush & 1); ++nflush; }
       cur_slot = st.slot;
-      if (SELF && (it & 1) != grp) continue;         // K1: the other group's step
+      if ((it & 1) != grp) continue;                 // the groups take alternate steps: two steps are in conversion at a time
       const int s = it % cfg::NOPS;
-      const uint32_t pi = SELF ? (uint32_t)it : 2u * it + grp;
-      const int sl = pi % cfg::NSLOTS;
-      mbar_wait(&stg_full[sl], (pi / cfg::NSLOTS) & 1);
       // (the operand stage is claimed before the rows are read: the words of a sixteen-row slice then go straight from the
       // conversion into the tile, and a step of several slices needs no more registers than one)
       mbar_wait(&op_empty[s], ((it / cfg::NOPS) & 1) ^ 1);
+#pragma unroll
+      for (int op = 0; op < (SELF ? 1 : 2); ++op) {
+      const bool is_b = !SELF && op == 1;
+      const uint32_t pi = SELF ? (uint32_t)it : 2u * it + op;
+      const int sl = pi % cfg::NSLOTS;
+      mbar_wait(&stg_full[sl], (pi / cfg::NSLOTS) & 1);
 #pragma unroll
       for (int sub = 0; sub < cfg::NSUB; ++sub) {
         if (sub * KR >= st.nrows) break;               // warp-uniform: nothing to convert, the MMA issuer skips the slice too
@@ -397,14 +401,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
 #pragma unroll
             for (int j = 0; j < QPR; ++j) {
               float4 a = v[rr][j];
-              a.x -= mean[j].x; a.y -= mean[j].y; a.z -= mean[j].z; a.w -= mean[j].w;
+              if (!is_b) { a.x -= mean[j].x; a.y -= mean[j].y; a.z -= mean[j].z; a.w -= mean[j].w; }
               if (!ok) a = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (want) { sum[j][0] += a.x; sum[j][1] += a.y; sum[j][2] += a.z; sum[j][3] += a.w; }
+              if (want && (SELF || is_b)) { sum[j][0] += a.x; sum[j][1] += a.y; sum[j][2] += a.z; sum[j][3] += a.w; }
               split2(a.x, a.y, hi[rr][j][0], lo[rr][j][0]);
               split2(a.z, a.w, hi[rr][j][1], lo[rr][j][1]);
             }
           }
-          const uint32_t dst = ops_u32 + s * cfg::OPSTAGE + sub * cfg::SUBSTAGE + my_op * 2 * cfg::IMG;
+          const uint32_t dst = ops_u32 + s * cfg::OPSTAGE + sub * cfg::SUBSTAGE + op * 2 * cfg::IMG;
 #pragma unroll
           for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
@@ -417,6 +421,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
       // the slab has been consumed: hand it back to the producer
       __syncwarp();
       if (lane == 0) mbar_arrive(&stg_empty[sl]);
+      }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&op_full[s]);

@@ -15,6 +15,7 @@ each direction is split in two phases around the collective (wc_gan_b200/sync.py
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -50,8 +51,18 @@ PHASE_STATS, PHASE_APPLY = 1, 2      # forward  (WC_PHASE_*)
 PHASE_REDUCE, PHASE_DX = 1, 2        # backward
 
 
+NVTX = bool(os.environ.get('WC_B200_NVTX'))     # NVTX ranges around the foreign calls (nsys / ncu --nvtx timelines)
+
+
 def _call(name: str, *args) -> None:
     fn = getattr(lib, name)
+    if NVTX:
+        torch.cuda.nvtx.range_push(name)
+        try:
+            check(fn(*args), name)
+        finally:
+            torch.cuda.nvtx.range_pop()
+        return
     if PROFILE is None:
         check(fn(*args), name)
         return

@@ -7,6 +7,7 @@
 //
 //   jacobi_smem_kernel   g <= 64: one CTA per group holds the whole g x g matrix; every round of the round-robin
 //                        tournament rotates its g/2 disjoint column pairs at once, one warp per pair.
+//   jacobi_q8_kernel     g in {16, 32, 64}: the same with eight lanes per pair (four pairs per warp), see below.
 //   jacobi_block_kernel  g >= 128 (multiple of 32): the columns are cut into blocks of 16; a block-level round-robin gives
 //                        nb/2 independent block pairs per block round, one CTA each (g = 256: 8 CTAs per group matrix).  A
 //                        CTA loads its two blocks (2 x 16 columns x g) into shared memory, rotates every cross pair (in the
@@ -140,6 +141,89 @@ __global__ void __launch_bounds__(1024) jacobi_smem_kernel(const float* __restri
   }
 }
 
+// ---- g in {16, 32, 64}: eight lanes per column pair ----------------------------------------------------------------------
+// The one-warp-per-pair kernel above is issue bound at g = 64 (32 warps x ~70 instructions per round on one SM, a 5-step
+// shuffle reduction for three 64-element dot products).  Here a pair is rotated by EIGHT lanes holding g / 8 elements of
+// each column in registers (128-bit shared-memory accesses), so a warp rotates four pairs at once: g / 8 warps per group,
+// a 3-step reduction, ~28 instructions per pair and a barrier among 256 instead of 1024 threads.
+template <int EPL>      // elements per lane: g = 8 * EPL, EPL in {2, 4, 8}
+__global__ void __launch_bounds__(256) jacobi_q8_kernel(const float* __restrict__ L, float* __restrict__ U, float* __restrict__ lam,
+                                                        int32_t* info) {
+  wc_pdl_wait();
+  constexpr int g = 8 * EPL, ld = g + 4, half = g / 2;
+  constexpr int VW = EPL >= 4 ? 4 : 2;                     // vector width of the accesses
+  constexpr int NV = EPL / VW;                             // vectors per lane and column
+  extern __shared__ __align__(16) float jsm[];            // column-major, pitch ld (16-byte aligned columns)
+  const int grp = blockIdx.x, t = threadIdx.x, nt = blockDim.x, lane = t & 31, warp = t >> 5;
+  const int l8 = lane & 7, slot = warp * 4 + (lane >> 3);  // this lane's pair of the round
+  const float* Lg = L + (long long)grp * g * g;
+  for (int idx = t; idx < g * g; idx += nt) { const int i = idx / g, j = idx % g; jsm[j * ld + i] = Lg[idx]; }
+  __syncthreads();
+  int sweep = 0;
+  for (; sweep < JMAX_SWEEPS; ++sweep) {
+    int rotated = 0;
+    for (int r = 0; r < g - 1; ++r) {
+      if (slot < half) {
+        int p, q; rr_pair(g, r, slot, p, q);
+        float* bp = jsm + p * ld + VW * l8;                // lane's elements: VW * l8 + (8 * VW) * v + 0 .. VW-1
+        float* bq = jsm + q * ld + VW * l8;
+        float x[EPL], y[EPL];
+        float al = 0.f, be = 0.f, ga = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if constexpr (VW == 4) {
+            const float4 a = *reinterpret_cast<const float4*>(bp + 32 * v), b = *reinterpret_cast<const float4*>(bq + 32 * v);
+            x[4 * v] = a.x; x[4 * v + 1] = a.y; x[4 * v + 2] = a.z; x[4 * v + 3] = a.w;
+            y[4 * v] = b.x; y[4 * v + 1] = b.y; y[4 * v + 2] = b.z; y[4 * v + 3] = b.w;
+          } else {
+            const float2 a = *reinterpret_cast<const float2*>(bp + 16 * v), b = *reinterpret_cast<const float2*>(bq + 16 * v);
+            x[2 * v] = a.x; x[2 * v + 1] = a.y; y[2 * v] = b.x; y[2 * v + 1] = b.y;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) { al = fmaf(x[e], x[e], al); be = fmaf(y[e], y[e], be); ga = fmaf(x[e], y[e], ga); }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {                  // the eight lanes of the pair
+          al += __shfl_xor_sync(FULL, al, o);
+          be += __shfl_xor_sync(FULL, be, o);
+          ga += __shfl_xor_sync(FULL, ga, o);
+        }
+        if (ga * ga > 1e-12f * al * be) {
+          rotated = 1;
+          const float zeta = __fdividef(be - al, 2.f * ga);
+          const float tt = copysignf(__frcp_rn(fabsf(zeta) + __fsqrt_rn(fmaf(zeta, zeta, 1.f))), zeta);
+          const float c = rsqrtf(fmaf(tt, tt, 1.f)), sn = c * tt;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            if constexpr (VW == 4) {
+              *reinterpret_cast<float4*>(bp + 32 * v) = make_float4(c * x[4 * v] - sn * y[4 * v], c * x[4 * v + 1] - sn * y[4 * v + 1],
+                                                                    c * x[4 * v + 2] - sn * y[4 * v + 2], c * x[4 * v + 3] - sn * y[4 * v + 3]);
+              *reinterpret_cast<float4*>(bq + 32 * v) = make_float4(sn * x[4 * v] + c * y[4 * v], sn * x[4 * v + 1] + c * y[4 * v + 1],
+                                                                    sn * x[4 * v + 2] + c * y[4 * v + 2], sn * x[4 * v + 3] + c * y[4 * v + 3]);
+            } else {
+              *reinterpret_cast<float2*>(bp + 16 * v) = make_float2(c * x[2 * v] - sn * y[2 * v], c * x[2 * v + 1] - sn * y[2 * v + 1]);
+              *reinterpret_cast<float2*>(bq + 16 * v) = make_float2(sn * x[2 * v] + c * y[2 * v], sn * x[2 * v + 1] + c * y[2 * v + 1]);
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (!__syncthreads_or(rotated)) { ++sweep; break; }
+  }
+  if (t == 0 && info) atomicMax(&info[WC_INFO_JACOBI], sweep);
+  float* Ug = U + (long long)grp * g * g;
+  for (int j = warp; j < g; j += nt >> 5) {
+    const float* bj = jsm + j * ld;
+    float nn = 0.f;
+    for (int i = lane; i < g; i += 32) nn = fmaf(bj[i], bj[i], nn);
+    nn = wc_warp_sum(nn);
+    const float inv = rsqrtf(fmaxf(nn, 1e-38f));
+    for (int i = lane; i < g; i += 32) Ug[(long long)i * g + j] = bj[i] * inv;
+    if (lane == 0) lam[grp * g + j] = nn;
+  }
+}
+
 // ---- g >= 128: blocks of 16 columns, one CTA per block pair, barriers in L2 ---------------------------------------------
 __device__ __forceinline__ void group_barrier(unsigned* ctr, unsigned target) {
   __syncthreads();
@@ -240,6 +324,14 @@ size_t wc_jacobi_sync_bytes(int C, int g) {
 // sync: wc_jacobi_sync_bytes bytes (zeroed here).  Returns WC_E_UNSUPPORTED for shapes neither kernel takes.
 int wc_jacobi_launch(const float* L, int C, int g, float* Bm, float* U, float* lam, unsigned* sync, int32_t* info, cudaStream_t st) {
   const int G = C / g;
+  if ((g == 16 || g == 32 || g == 64) && !(wc_debug_flags() & 33554432)) {
+    const size_t smem = (size_t)g * (g + 4) * sizeof(float);
+    if (g == 64) WC_CUDA(wc_launch(jacobi_q8_kernel<8>, G, 8 * 32, smem, st, L, U, lam, info));
+    else if (g == 32) WC_CUDA(wc_launch(jacobi_q8_kernel<4>, G, 4 * 32, smem, st, L, U, lam, info));
+    else WC_CUDA(wc_launch(jacobi_q8_kernel<2>, G, 2 * 32, smem, st, L, U, lam, info));
+    WC_CHECK_LAUNCH();
+    return 0;
+  }
   if (g <= 64) {
     const int warps = g <= 2 ? 1 : (g / 2 < 32 ? (g + 1) / 2 : 32);
     const size_t smem = (size_t)g * (g | 1) * sizeof(float);

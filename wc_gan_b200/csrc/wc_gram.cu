@@ -260,25 +260,29 @@ __global__ void stats_finalize_kernel(const float* __restrict__ partS, const flo
 __global__ void stats_finalize_prep_kernel(const float* __restrict__ partS, const float* __restrict__ partSum, int C, int g,
                                            double M, const float* __restrict__ pivot, float* __restrict__ mean,
                                            float* __restrict__ S, WcPrepFuse f) {
-  wc_pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)C * g;
-  if (idx >= total) return;
+  if (idx >= total) { wc_pdl_wait(); return; }
   int grp = (int)(idx / ((long long)g * g));
   int rem = (int)(idx % ((long long)g * g));
   int r = rem / g, c = rem % g;
   int i = grp * g + r, j = grp * g + c;
+  // the moving averages do not depend on the statistics kernel: their (cold, DRAM) loads are issued BEFORE the dependency
+  // wait and complete while that kernel drains
+  const float mc_old = f.moving_cov[idx];
+  const float mm_old = (r == c) ? f.moving_mean[i] : 0.f;
+  wc_pdl_wait();
   const float s = partS[(long long)max(i, j) * C + min(i, j)];
   const float di = partSum[i], dj = partSum[j];
   const double ddi = (double)di / M, ddj = (double)dj / M;
   const float sv = (float)((double)s - M * ddi * ddj);
   S[idx] = sv;
   const float cov = sv / ((float)M - 1.f);
-  f.moving_cov[idx] = f.moving_cov[idx] * f.momentum + cov * (1.f - f.momentum);        // conditional_layers.py:687-689
+  f.moving_cov[idx] = mc_old * f.momentum + cov * (1.f - f.momentum);        // conditional_layers.py:687-689
   if (r == c) {
     const float mu = (float)((double)pivot[i] + ddi);
     mean[i] = mu;
-    f.moving_mean[i] = f.moving_mean[i] * f.momentum + mu * (1.f - f.momentum);          // :684-686
+    f.moving_mean[i] = mm_old * f.momentum + mu * (1.f - f.momentum);          // :684-686
   }
   f.Ashr[idx] = (1.f - f.eps) * cov + (r == c ? f.eps + f.extra_eps : 0.f);              // :691 (+ :671 for ZCA)
 }

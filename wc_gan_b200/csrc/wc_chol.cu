@@ -616,7 +616,8 @@ __device__ __forceinline__ void cta_fetch_tiles(const float* gt, int n, float* d
 __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
     chol_cluster_kernel(const float* __restrict__ Ain, int g, float* __restrict__ scratch, long long scratch_stride,
                         float* __restrict__ Lout, float* __restrict__ Xout, int32_t* info, int dbg) {
-  wc_pdl_wait();
+  // (the dependency wait comes after the barriers are initialised, the strictly upper output tiles are zeroed and the cluster
+  // has synchronised: none of that reads what the preceding kernel writes, so it runs under that kernel's tail)
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t flagA[CLN], flagA2[CLN], flagB[CLN], colbar[TB], flagN, flagT;
   __shared__ __align__(16) float rd_own[TB], rd_warm[2 * TB];
@@ -660,17 +661,9 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&flagT)), "r"(TB * TB * 4) : "memory");
   }
-  // load block row r: column c of the column-major tile (r,J) is a contiguous piece of ROW J*32+c of the symmetric input
   if (r < NB) {
-    const int cq = lane >> 3, q8 = lane & 7;
-    for (int J = warp; J <= r; J += CLW) {
-      float4 v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = __ldg(reinterpret_cast<const float4*>(Ag + (long long)(J * TB + 4 * e + cq) * g + r * TB) + q8);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) *reinterpret_cast<float4*>(own + J * TS + (4 * e + cq) * TP + 4 * q8) = v[e];
-    }
     // strictly upper tiles of the outputs are zero
+    const int cq = lane >> 3, q8 = lane & 7;
     for (int J = r + 1 + warp; J < NB; J += CLW) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -682,6 +675,19 @@ __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(CLW * 32, 1)
   }
   __syncthreads();
   cl_sync();      // every CTA's flags are initialised before anyone can arrive on them
+  wc_pdl_wait();
+  // load block row r: column c of the column-major tile (r,J) is a contiguous piece of ROW J*32+c of the symmetric input
+  if (r < NB) {
+    const int cq = lane >> 3, q8 = lane & 7;
+    for (int J = warp; J <= r; J += CLW) {
+      float4 v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = __ldcg(reinterpret_cast<const float4*>(Ag + (long long)(J * TB + 4 * e + cq) * g + r * TB) + q8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) *reinterpret_cast<float4*>(own + J * TS + (4 * e + cq) * TP + 4 * q8) = v[e];
+    }
+  }
+  __syncthreads();
   CL_MARK(1);
 
   if (r < NB) {

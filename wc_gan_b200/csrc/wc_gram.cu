@@ -257,6 +257,31 @@ __global__ void stats_finalize_kernel(const float* __restrict__ partS, const flo
 // Tensor-core path, single process: finalize and the K2 prep step (covariance scaling, moving averages, shrinkage;
 // see factor_prep_kernel in wc_small.cu) in one launch.  The scatter is read from its lower triangle, so S and the
 // covariance are exactly symmetric.
+// Accumulator zeroing as a KERNEL instead of a memset node: a memset breaks the chain of programmatic dependent launches
+// (the kernel after it cannot be scheduled, let alone run its prologue, before the memset has finished, and the memset
+// cannot start before the kernel before it has drained).  The stores come after the dependency wait: the kernel before
+// this one may still be reading the buffer (finalize of the previous call on the same workspace).
+__global__ void __launch_bounds__(256) zero_kernel(uint4* __restrict__ p, size_t n16, uint32_t* __restrict__ tail, int ntail) {
+  wc_pdl_wait();
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p[i] = z;
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0u;
+}
+int zero_launch(void* ptr, size_t bytes, cudaStream_t st) {
+  if (!wc_aligned16(ptr) || (bytes & 3) || (wc_debug_flags() & 4096 * 65536 * 2)) {   // experiment bit 29: memset node
+    WC_CUDA(cudaMemsetAsync(ptr, 0, bytes, st));
+    return 0;
+  }
+  const size_t n16 = bytes / 16;
+  const int ntail = (int)((bytes - n16 * 16) / 4);
+  const size_t want = (n16 + 255) / 256;
+  const unsigned grid = (unsigned)(want < 1 ? 1 : (want > (size_t)WC_NUM_SMS * 4 ? (size_t)WC_NUM_SMS * 4 : want));
+  WC_CUDA(wc_launch(zero_kernel, grid, 256, 0, st, reinterpret_cast<uint4*>(ptr), n16,
+                    reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ptr) + n16 * 16), ntail));
+  WC_CHECK_LAUNCH();
+  return 0;
+}
+
 __global__ void stats_finalize_prep_kernel(const float* __restrict__ partS, const float* __restrict__ partSum, int C, int g,
                                            double M, const float* __restrict__ pivot, float* __restrict__ mean,
                                            float* __restrict__ S, WcPrepFuse f) {
@@ -405,7 +430,7 @@ int wc_stats_fwd_impl(const float* x, int64_t M, int C, int g, float* workspace,
     // tensor-core path: the full C x C scatter is accumulated with vector reductions into one zeroed buffer
     // (partial slot 0; column sums and scatter are adjacent: one memset); the kernel computes its own pivot and
     // the finalize kernel keeps the diagonal blocks when g < C.
-    WC_CUDA(cudaMemsetAsync(ws + pl.off_zero, 0, (pl.off_S - pl.off_zero) + (size_t)C * C * 4, st));
+    { const int rz = zero_launch(ws + pl.off_zero, (pl.off_S - pl.off_zero) + (size_t)C * C * 4, st); if (rz) return rz; }
     if (zeroed_out) *zeroed_out = reinterpret_cast<unsigned*>(ws + pl.off_zero);
     int rc = wc_tc_gram_self(x, M, C, g, pivot, pS, psum, st);
     if (rc) return rc;
@@ -481,7 +506,8 @@ int wc_reduce_bwd_impl(const float* x, const float* dy, int N, int HW, int Cin, 
     WC_CHECK_LAUNCH();
   }
   if (s == P + (size_t)K * Cin * Cout) {   // P | s contiguous (wc_layer_bwd's workspace): one memset
-    WC_CUDA(cudaMemsetAsync(P, 0, ((size_t)K * Cin * Cout + (size_t)K * Cout + (size_t)zero_tail_floats) * 4, st));
+    const int rz = zero_launch(P, ((size_t)K * Cin * Cout + (size_t)K * Cout + (size_t)zero_tail_floats) * 4, st);
+    if (rz) return rz;
   } else {
     if (zero_tail_floats) return WC_E_ARG;
     WC_CUDA(cudaMemsetAsync(P, 0, (size_t)K * Cin * Cout * 4, st));

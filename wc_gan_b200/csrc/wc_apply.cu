@@ -194,25 +194,26 @@ int launch_apply(ApplyParams& p, bool vec, cudaStream_t st) {
 }  // namespace
 
 int wc_tc_apply_fwd(const float* x, int N, int HW, int C, const float* mean, const void* packed, const float* b,
-                    const int32_t* cls, int K, float* y, int32_t* info, int relu, cudaStream_t st);
+                    const int32_t* cls, int K, float* y, int32_t* info, int relu, int early, cudaStream_t st);
 int wc_tc_apply_bwd(const float* x, const float* dy, int N, int HW, int C, const float* mean, const void* packed,
-                    bool has_A, const float* cvec, const int32_t* cls, int K, float* dx, cudaStream_t st);
+                    bool has_A, const float* cvec, const int32_t* cls, int K, float* dx, int early, cudaStream_t st);
 bool wc_tc_apply_ok(int Cin, int Cout);
 
 extern "C" int wc_apply_fwd(const float* x, int N, int HW, int Cin, int Cout, const float* mean, const float* T,
                             const void* T_packed, const float* b, const int32_t* cls, int K, int band, float* y,
                             int32_t* info, wc_stream_t stream) {
-  return wc_apply_fwd_impl(x, N, HW, Cin, Cout, mean, T, T_packed, b, cls, K, band, y, info, 0, (cudaStream_t)stream);
+  return wc_apply_fwd_impl(x, N, HW, Cin, Cout, mean, T, T_packed, b, cls, K, band, y, info, 0, (cudaStream_t)stream, 0);
 }
 
 // relu != 0: y = max(0, .), the Activation('relu') that follows every WC layer (gan/layer_utils.py:170,178; generator.py:155)
 int wc_apply_fwd_impl(const float* x, int N, int HW, int Cin, int Cout, const float* mean, const float* T, const void* T_packed,
-                      const float* b, const int32_t* cls, int K, int band, float* y, int32_t* info, int relu, cudaStream_t stream) {
+                      const float* b, const int32_t* cls, int K, int band, float* y, int32_t* info, int relu, cudaStream_t stream,
+                      int early) {
   if (!x || !T || !y || N <= 0 || HW <= 0 || Cin <= 0 || Cout <= 0 || K <= 0) return WC_E_ARG;
   if ((int64_t)N * HW > (int64_t)INT32_MAX) return WC_E_UNSUPPORTED;
   if (T_packed && wc_tc_apply_ok(Cin, Cout) && wc_aligned16(x) && wc_aligned16(y) && wc_aligned16(T_packed) &&
       (!mean || wc_aligned16(mean)))
-    return wc_tc_apply_fwd(x, N, HW, Cin, mean, T_packed, b, cls, K, y, info, relu, (cudaStream_t)stream);
+    return wc_tc_apply_fwd(x, N, HW, Cin, mean, T_packed, b, cls, K, y, info, relu, early, (cudaStream_t)stream);
   ApplyParams p{};
   p.t1 = Term{x, Cin, mean, T, (long long)Cin * Cout, Cout, 1, Cin, band, 0};
   p.nterms = 1;
@@ -226,12 +227,18 @@ int wc_apply_fwd_impl(const float* x, int N, int HW, int Cin, int Cout, const fl
 extern "C" int wc_apply_bwd(const float* x, const float* dy, int N, int HW, int Cin, int Cout, const float* mean,
                             const float* T, const float* A, const void* TA_packed, const float* cvec, int g,
                             const int32_t* cls, int K, float* dx, wc_stream_t stream) {
+  return wc_apply_bwd_impl(x, dy, N, HW, Cin, Cout, mean, T, A, TA_packed, cvec, g, cls, K, dx, (cudaStream_t)stream, 0);
+}
+// early: TcApplyParams::early (whole-layer calls)
+int wc_apply_bwd_impl(const float* x, const float* dy, int N, int HW, int Cin, int Cout, const float* mean,
+                      const float* T, const float* A, const void* TA_packed, const float* cvec, int g,
+                      const int32_t* cls, int K, float* dx, cudaStream_t stream, int early) {
   if (!dy || !T || !dx || N <= 0 || HW <= 0 || Cin <= 0 || Cout <= 0 || K <= 0) return WC_E_ARG;
   if (A && (!x || g <= 0 || Cin % g)) return WC_E_ARG;
   if ((int64_t)N * HW > (int64_t)INT32_MAX) return WC_E_UNSUPPORTED;
   if (TA_packed && wc_tc_apply_ok(Cin, Cout) && wc_aligned16(dy) && wc_aligned16(dx) && wc_aligned16(TA_packed) &&
       (!A || (wc_aligned16(x) && (!mean || wc_aligned16(mean)))))
-    return wc_tc_apply_bwd(x, dy, N, HW, Cin, mean, TA_packed, A != nullptr, cvec, cls, K, dx, (cudaStream_t)stream);
+    return wc_tc_apply_bwd(x, dy, N, HW, Cin, mean, TA_packed, A != nullptr, cvec, cls, K, dx, early, (cudaStream_t)stream);
   ApplyParams p{};
   // term 1: dy (rows x Cout) times T^T (Cout x Cin): element (k=jout, j=iin) = T[iin*Cout + jout]
   p.t1 = Term{dy, Cout, nullptr, T, (long long)Cin * Cout, 1, Cout, Cout, 0, 0};

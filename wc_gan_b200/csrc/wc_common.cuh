@@ -161,7 +161,10 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
 int wc_rebuild_wk(int Cin, int Cout, int K, const float* Wu, const float* class_matrix, const float* D, int E, float* Wk, cudaStream_t st);
 
 int wc_apply_fwd_impl(const float* x, int N, int HW, int Cin, int Cout, const float* mean, const float* T, const void* T_packed,
-                      const float* b, const int32_t* cls, int K, int band, float* y, int32_t* info, int relu, cudaStream_t stream);
+                      const float* b, const int32_t* cls, int K, int band, float* y, int32_t* info, int relu, cudaStream_t stream, int early = 0);
+int wc_apply_bwd_impl(const float* x, const float* dy, int N, int HW, int Cin, int Cout, const float* mean,
+                      const float* T, const float* A, const void* TA_packed, const float* cvec, int g,
+                      const int32_t* cls, int K, float* dx, cudaStream_t stream, int early);
 
 // peer-memory exchanges (wc_exchange.cu)
 int wc_stats_exchange(float* rec, float count_local, int C, int g, void* const* peers, void* state, int rank, int world, float eps,

@@ -190,7 +190,8 @@ extern "C" int wc_layer_fwd(const WcLayerCall* cp, wc_stream_t stream) {
   if (rc) return rc;
   const int band = (c.whiten && !has_coloring(c) && c.g < c.Cin) ? c.g : 0;
   return wc_apply_fwd_impl(c.x, c.N, c.HW, c.Cin, c.Cout, mean, at<float>(c.saved, L.T), Tp, plain_u(c) ? c.bu : at<float>(c.saved, L.b),
-                           conditional(c) ? c.cls : nullptr, c.K, band, c.y, c.info, c.relu, (cudaStream_t)stream);
+                           conditional(c) ? c.cls : nullptr, c.K, band, c.y, c.info, c.relu, (cudaStream_t)stream,
+                           c.whiten ? 1 : 0);      // x, mean and the labels were read by this call's own kernels before
 }
 
 extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
@@ -272,5 +273,9 @@ extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
     if (rc) return rc;
   }
   void* Tp = at<void>(c.saved, L.Tp_bwd);
-  return wc_apply_bwd(c.x, c.dy, c.N, c.HW, c.Cin, c.Cout, mean, at<float>(c.saved, L.T), A, Tp, cvec, g, cls, c.K, c.dx, stream);
+  // (x, dy, the mean and the labels went through K4 of this call; T's operand image dates from the forward pass: only A's
+  // image and c are written by the kernel right before K6)
+  const int early = (c.phases & WC_PHASE_REDUCE) ? 3 : 0;
+  return wc_apply_bwd_impl(c.x, c.dy, c.N, c.HW, c.Cin, c.Cout, mean, at<float>(c.saved, L.T), A, Tp, cvec, g, cls, c.K, c.dx,
+                           (cudaStream_t)stream, early);
 }

@@ -52,6 +52,11 @@ struct TcApplyParams {
   long long total_tiles;
   const int32_t* cls; int K; int32_t* info;
   int relu;                                 // 1: out = max(0, .) in the epilogue
+  // whole-layer calls only (the caller knows what the preceding kernel writes).  bit 0: activations, shifts and labels were
+  // final before the preceding kernel started, so the activation producer and the converters do not wait for it (only
+  // the matrix-image producer and the epilogue do: images and bias are what it writes); bit 1: the images of segment 0
+  // are older too (K6: T was packed in the forward pass; only A and c come from the backward chain)
+  int early;
   int l2_load[2], l2_store;                 // L2 eviction priority of the activation loads per segment / of the output stores (wctc::l2_policy)
   unsigned long long* dbg; int dbg_flags;   // debug marks / experiment switches (0 in normal use)
 };
@@ -119,7 +124,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
   __syncthreads();
   tc_fence_after();
   const uint32_t td = tmem_slot;
-  wc_pdl_wait();      // barriers, tensor maps and TMEM were set up while the previous kernel drained
+  const bool early = (p.early & 1) != 0;
+  if (!early) wc_pdl_wait();      // barriers, tensor maps and TMEM were set up while the previous kernel drained
   if (t == 0) wc_mark(p.dbg, 0);
 
   if (warp == W_PROD) {
@@ -146,11 +152,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
     // ------------------------------------------------------------------ matrix-image producer (L2-resident source)
     if (lane == 0) {
       uint32_t ib = 0;
+      bool waited = !early;
+      const int wait_seg = (p.early & 2) ? 1 : 0;      // first segment whose images the preceding kernel writes
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileInfo ti = tile_info(p, tile);
         for (int it = 0; it < total_kb; ++it, ++ib) {
           const int sg = it / cfg::NKB, kb = it % cfg::NKB;
           const int s = ib % NBOP;
+          if (!waited && sg >= wait_seg) { wc_pdl_wait(); waited = true; }
           const uint8_t* src = p.seg[sg].Bp + (long long)ti.slot * p.seg[sg].slot_stride + (long long)kb * (2 * cfg::B_IMG);
           mbar_wait(&bop_empty[s], ((ib / NBOP) & 1) ^ 1);
           uint8_t* dst = smem + cfg::OFF_BOP + s * 2 * cfg::B_IMG;
@@ -209,6 +218,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_apply_kernel(TcApplyParams p, 
     const int row = q * 32 + lane;         // row of the tile held by this thread
     uint32_t lt = 0, ec = 0;
     const uint64_t pol_st = l2_policy(p.l2_store);
+    if (early) wc_pdl_wait();              // the bias is the preceding kernel's; nothing to do here before the first tile anyway
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const TileInfo ti = tile_info(p, tile);
       const uint32_t ab = lt & 1;
@@ -785,8 +795,9 @@ extern "C" int wc_pack_bwd(const float* T, const float* A, int C, int g, int K, 
 
 // called from wc_apply.cu
 int wc_tc_apply_fwd(const float* x, int N, int HW, int C, const float* mean, const void* packed, const float* b,
-                    const int32_t* cls, int K, float* y, int32_t* info, int relu, cudaStream_t st) {
+                    const int32_t* cls, int K, float* y, int32_t* info, int relu, int early, cudaStream_t st) {
   TcApplyParams p{};
+  p.early = (wc_debug_flags() & 1073741824) ? 0 : early;
   p.seg[0] = TcSeg{mean, (const uint8_t*)packed, (long long)C * C * 4};
   p.nseg = 1;
   p.bias = b; p.bias_slot_stride = C; p.bias_sign = 1.f;
@@ -798,8 +809,9 @@ int wc_tc_apply_fwd(const float* x, int N, int HW, int C, const float* mean, con
 }
 
 int wc_tc_apply_bwd(const float* x, const float* dy, int N, int HW, int C, const float* mean, const void* packed,
-                    bool has_A, const float* cvec, const int32_t* cls, int K, float* dx, cudaStream_t st) {
+                    bool has_A, const float* cvec, const int32_t* cls, int K, float* dx, int early, cudaStream_t st) {
   TcApplyParams p{};
+  p.early = (wc_debug_flags() & 1073741824) ? 0 : early;
   p.seg[0] = TcSeg{nullptr, (const uint8_t*)packed, (long long)C * C * 4};
   p.nseg = 1;
   if (has_A) {

@@ -267,7 +267,10 @@ __global__ void __launch_bounds__(256) zero_kernel(uint4* __restrict__ p, size_t
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p[i] = z;
   if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0u;
 }
-int zero_launch(void* ptr, size_t bytes, cudaStream_t st) {
+// *by_kernel (nullable) = 1 when the zeroing was done by zero_kernel, i.e. by a kernel that waits for everything before it on
+// the stream before it lets its successor start (what tc_gram_kernel's late dependency wait relies on), 0 for a memset.
+int zero_launch(void* ptr, size_t bytes, cudaStream_t st, int* by_kernel = nullptr) {
+  if (by_kernel) *by_kernel = 0;
   if (!wc_aligned16(ptr) || (bytes & 3) || (wc_debug_flags() & 4096 * 65536 * 2)) {   // experiment bit 29: memset node
     WC_CUDA(cudaMemsetAsync(ptr, 0, bytes, st));
     return 0;
@@ -279,6 +282,7 @@ int zero_launch(void* ptr, size_t bytes, cudaStream_t st) {
   WC_CUDA(wc_launch(zero_kernel, grid, 256, 0, st, reinterpret_cast<uint4*>(ptr), n16,
                     reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ptr) + n16 * 16), ntail));
   WC_CHECK_LAUNCH();
+  if (by_kernel) *by_kernel = 1;
   return 0;
 }
 
@@ -389,9 +393,9 @@ StatsPlan plan_stats(int64_t M, int C, int g) {
 }  // namespace
 
 bool wc_tc_gram_ok(int Cin, int Cout);
-int wc_tc_gram_self(const float* x, long long M, int C, int g, float* pivot_out, float* Sp, float* sums, cudaStream_t st);
+int wc_tc_gram_self(const float* x, long long M, int C, int g, float* pivot_out, float* Sp, float* sums, int late_wait, cudaStream_t st);
 int wc_tc_gram_cross(const float* x, const float* dy, int N, int HW, int C, const float* mean, const int32_t* order,
-                     const int32_t* slot_of, int K, float* P, float* s, cudaStream_t st);
+                     const int32_t* slot_of, int K, float* P, float* s, int late_wait, cudaStream_t st);
 
 static bool g_use_tc_gram = true;
 extern "C" void wc_set_tensor_core_gram(int enable) { g_use_tc_gram = enable != 0; }
@@ -430,9 +434,10 @@ int wc_stats_fwd_impl(const float* x, int64_t M, int C, int g, float* workspace,
     // tensor-core path: the full C x C scatter is accumulated with vector reductions into one zeroed buffer
     // (partial slot 0; column sums and scatter are adjacent: one memset); the kernel computes its own pivot and
     // the finalize kernel keeps the diagonal blocks when g < C.
-    { const int rz = zero_launch(ws + pl.off_zero, (pl.off_S - pl.off_zero) + (size_t)C * C * 4, st); if (rz) return rz; }
+    int zk = 0;
+    { const int rz = zero_launch(ws + pl.off_zero, (pl.off_S - pl.off_zero) + (size_t)C * C * 4, st, &zk); if (rz) return rz; }
     if (zeroed_out) *zeroed_out = reinterpret_cast<unsigned*>(ws + pl.off_zero);
-    int rc = wc_tc_gram_self(x, M, C, g, pivot, pS, psum, st);
+    int rc = wc_tc_gram_self(x, M, C, g, pivot, pS, psum, zk, st);
     if (rc) return rc;
     long long tot = (long long)C * g;
     if (raw_out) { *raw_out = WcRawStats{pS, psum, pivot}; return 0; }
@@ -505,8 +510,9 @@ int wc_reduce_bwd_impl(const float* x, const float* dy, int N, int HW, int Cin, 
     WC_CUDA(wc_launch(class_order_kernel, 1, 1024, K * sizeof(int), st, cls, N, K, order, slot_of));
     WC_CHECK_LAUNCH();
   }
+  int zk = 0;
   if (s == P + (size_t)K * Cin * Cout) {   // P | s contiguous (wc_layer_bwd's workspace): one memset
-    const int rz = zero_launch(P, ((size_t)K * Cin * Cout + (size_t)K * Cout + (size_t)zero_tail_floats) * 4, st);
+    const int rz = zero_launch(P, ((size_t)K * Cin * Cout + (size_t)K * Cout + (size_t)zero_tail_floats) * 4, st, &zk);
     if (rz) return rz;
   } else {
     if (zero_tail_floats) return WC_E_ARG;
@@ -515,7 +521,7 @@ int wc_reduce_bwd_impl(const float* x, const float* dy, int N, int HW, int Cin, 
   }
   if (g_use_tc_gram && wc_tc_gram_ok(Cin, Cout) && wc_aligned16(x) && wc_aligned16(dy) && wc_aligned16(P) &&
       (!mean || wc_aligned16(mean)))
-    return wc_tc_gram_cross(x, dy, N, HW, Cin, mean, order, slot_of, cond ? K : 1, P, s, st);
+    return wc_tc_gram_cross(x, dy, N, HW, Cin, mean, order, slot_of, cond ? K : 1, P, s, zk, st);
   GramParams p{};
   p.A = x; p.B = dy; p.lda = Cin; p.ldb = Cout; p.ma = mean; p.mb = nullptr; p.nI = Cin; p.nJ = Cout;
   p.grouped = 0; p.g = Cin; p.tw = TI; p.tpg = 1;

@@ -45,6 +45,7 @@ struct TcGramParams {
   float* pivot_out;                     // self mode: the pivot every CTA used (written by CTA 0)
   int nslots;                           // number of [C][C] accumulators behind `out`
   int l2_load;                          // L2 eviction priority of the activation loads (wctc::l2_policy)
+  int late_wait;                        // 1: the predecessor on the stream is zero_kernel (see the kernel): only the flush waits
   unsigned long long* dbg; int dbg_flags;   // debug marks (nullptr in normal use)
 };
 
@@ -158,7 +159,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
   tc_fence_after();
   const uint32_t td = tmem_slot;
   constexpr int nops = SELF ? 1 : 2;
-  wc_pdl_wait();      // barriers, tensor map and TMEM were set up while the previous kernel drained
+  // The kernel right before this one is the one that zeroes the accumulators (zero_kernel; it has itself waited for
+  // whatever produced the activations before it let this grid start).  Nothing but the flush touches the accumulators,
+  // so only the flush waits for it: the whole main loop runs under the zeroing and its launch latency.  When the zeroing
+  // was a memset (unaligned workspace, fine-grained ABI with separate P and s) the wait comes first as everywhere else.
+  if (!p.late_wait) wc_pdl_wait();
   if (t == 0) wc_mark(p.dbg, 0);
 
   if (warp == NCONV_WARPS) {
@@ -288,8 +293,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gram_kernel(TcGramParams p, co
       st_off[rr] = (uint32_t)(lane >> 4) * (KR * 128) + (uint32_t)r * 128 + (uint32_t)((((lane & 15) >> 1) ^ (r & 7)) << 4) + (uint32_t)(lane & 1) * 8;
     }
 
+    bool dep_waited = !p.late_wait;
     auto flush = [&](int slot, uint32_t parity) {
       // accumulator -> global (vector reductions); column sums -> global
+      if (!dep_waited) { wc_pdl_wait(); dep_waited = true; }
       mbar_wait(&acc_full, parity);
       tc_fence_after();
       const int q = warp & 3, part = warp >> 2;            // TMEM lanes 32q..32q+31; a quarter of the columns
@@ -466,28 +473,28 @@ bool wc_tc_gram_ok(int Cin, int Cout) { return Cin == Cout && (Cin == 128 || Cin
 
 // Sp (C,C) and sums (C) must be zero on entry (the caller memsets them on the same stream).  pivot_out[C] receives
 // the shift the kernel used (mean of the first 32 rows).
-int wc_tc_gram_self(const float* x, long long M, int C, int g, float* pivot_out, float* Sp, float* sums, cudaStream_t st) {
+int wc_tc_gram_self(const float* x, long long M, int C, int g, float* pivot_out, float* Sp, float* sums, int late_wait, cudaStream_t st) {
   TcGramParams p{};
   p.A = x; p.B = x; p.ma = nullptr; p.mb = nullptr; p.self = 1; p.g = g;
   p.N = 1; p.HW = (int)M;
   p.order = nullptr; p.slot_of = nullptr;
   p.out = Sp; p.out_slot_stride = 0;
   p.asum = sums; p.bsum = nullptr; p.sum_slot_stride = 0;
-  p.pivot_out = pivot_out; p.nslots = 1;
+  p.pivot_out = pivot_out; p.nslots = 1; p.late_wait = late_wait;
   p.l2_load = (wc_l2_mode() & 1) ? 1 : 0;      // x is read again by K3 right after the factorisation: keep it in L2
   return C == 256 ? launch_tc_gram<256, true>(p, st) : launch_tc_gram<128, true>(p, st);
 }
 
 // P (K,C,C) and s (K,C) must be zero on entry.
 int wc_tc_gram_cross(const float* x, const float* dy, int N, int HW, int C, const float* mean, const int32_t* order,
-                     const int32_t* slot_of, int K, float* P, float* s, cudaStream_t st) {
+                     const int32_t* slot_of, int K, float* P, float* s, int late_wait, cudaStream_t st) {
   TcGramParams p{};
   p.A = x; p.B = dy; p.ma = mean; p.mb = nullptr; p.self = 0; p.g = C;
   p.N = N; p.HW = HW;
   p.order = order; p.slot_of = slot_of;
   p.out = P; p.out_slot_stride = (long long)C * C;
   p.asum = nullptr; p.bsum = s; p.sum_slot_stride = C;
-  p.pivot_out = nullptr; p.nslots = K;
+  p.pivot_out = nullptr; p.nslots = K; p.late_wait = late_wait;
   p.l2_load = (wc_l2_mode() & 8) ? 1 : 0;      // x and dy are read again by K6
   return C == 256 ? launch_tc_gram<256, false>(p, st) : launch_tc_gram<128, false>(p, st);
 }

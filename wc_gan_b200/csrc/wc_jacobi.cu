@@ -15,8 +15,12 @@
 //                        the other CTAs of its group at a barrier in L2 (release-add / acquire-spin on a per-group counter).
 //                        A sweep is nb-1 block rounds; the sweep loop ends when no CTA of the group rotated anything.
 //
-// A pair (p, q) is rotated when |b_p . b_q| > 1e-6 |b_p| |b_q|; sweeps are capped at 20.  info[WC_INFO_JACOBI] records
-// the number of sweeps used.
+// A pair (p, q) is rotated when |b_p . b_q| > 1e-6 |b_p| |b_q|; the sweep loop ends after the first sweep in which no
+// pair was further than 1e-4 from orthogonal (JSTOP2): every pair above 1e-6 was still rotated in that sweep, and what a
+// sweep leaves behind is far below what it met (measured on the covariances of the parity tests and on log-uniform /
+// rank-deficient spectra: a sweep that meets 2e-5 ... 4e-4 leaves 1e-6; the inverse square root is the same to all printed
+// digits as with the former rule "stop after a sweep without rotations", which cost one to two more sweeps of ten).
+// Sweeps are capped at 20.  info[WC_INFO_JACOBI] records the number of sweeps used.
 #include "wc_common.cuh"
 
 namespace {
@@ -25,6 +29,8 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int JB = 16;                  // columns per block (block kernel)
 constexpr int JBLK_THREADS = 512;       // 16 warps: one per column pair of a sub-round
 constexpr int JMAX_SWEEPS = 20;
+constexpr float JROT2 = 1e-12f;         // rotate a pair when cos^2 > JROT2
+constexpr float JSTOP2 = 1e-8f;         // another sweep is needed when some pair had cos^2 > JSTOP2
 
 // round-robin tournament of n (even) players: partner of position `i` (0 <= i < n/2) in round r (0 <= r < n-1)
 __device__ __forceinline__ void rr_pair(int n, int r, int i, int& p, int& q) {
@@ -33,7 +39,8 @@ __device__ __forceinline__ void rr_pair(int n, int r, int i, int& p, int& q) {
   else { p = r + i; if (p >= m) p -= m; q = r - i; if (q < 0) q += m; }
 }
 
-// rotate columns bp, bq (length len, lane-strided) of one pair; returns true if a rotation was applied
+// rotate columns bp, bq (length len, lane-strided) of one pair; returns true if the pair was far enough from orthogonal
+// to ask for another sweep
 template <int EPL>     // elements per lane (len <= 32 * EPL)
 __device__ __forceinline__ bool rotate_pair(float* bp, float* bq, int len, int lane) {
   float x[EPL], y[EPL];
@@ -52,7 +59,8 @@ __device__ __forceinline__ bool rotate_pair(float* bp, float* bq, int len, int l
     ga += __shfl_xor_sync(FULL, ga, o);
   }
   // |ga| > 1e-6 sqrt(al be)  <=>  ga^2 > 1e-12 al be  (no square root on the decision path)
-  if (!(ga * ga > 1e-12f * al * be)) return false;
+  if (!(ga * ga > JROT2 * al * be)) return false;
+  const bool more = ga * ga > JSTOP2 * al * be;
   // tan of the rotation angle: the smaller root of t^2 + 2 zeta t - 1 = 0; fast reciprocal / rsqrt are accurate to ~1 ulp,
   // and an error in (c, s) only makes the rotation slightly less effective (c^2 + s^2 = 1 holds by construction of s = c t)
   const float zeta = __fdividef(be - al, 2.f * ga);
@@ -64,7 +72,7 @@ __device__ __forceinline__ bool rotate_pair(float* bp, float* bq, int len, int l
     const int i = lane + 32 * e;
     if (i < len) { bp[i] = c * x[e] - s * y[e]; bq[i] = s * x[e] + c * y[e]; }
   }
-  return true;
+  return more;
 }
 
 // the same for len == 32 * EPL with EPL a multiple of 4: a lane owns elements 4*lane .. +3 of every 128 (128-bit accesses)
@@ -87,7 +95,8 @@ __device__ __forceinline__ bool rotate_pair_v4(float* bp, float* bq, int lane) {
     be += __shfl_xor_sync(FULL, be, o);
     ga += __shfl_xor_sync(FULL, ga, o);
   }
-  if (!(ga * ga > 1e-12f * al * be)) return false;
+  if (!(ga * ga > JROT2 * al * be)) return false;
+  const bool more = ga * ga > JSTOP2 * al * be;
   const float zeta = __fdividef(be - al, 2.f * ga);
   const float tt = copysignf(__frcp_rn(fabsf(zeta) + __fsqrt_rn(fmaf(zeta, zeta, 1.f))), zeta);
   const float c = rsqrtf(fmaf(tt, tt, 1.f)), s = c * tt;
@@ -96,7 +105,7 @@ __device__ __forceinline__ bool rotate_pair_v4(float* bp, float* bq, int lane) {
     *reinterpret_cast<float4*>(bp + 4 * lane + 128 * e) = make_float4(c * x[e].x - s * y[e].x, c * x[e].y - s * y[e].y, c * x[e].z - s * y[e].z, c * x[e].w - s * y[e].w);
     *reinterpret_cast<float4*>(bq + 4 * lane + 128 * e) = make_float4(s * x[e].x + c * y[e].x, s * x[e].y + c * y[e].y, s * x[e].z + c * y[e].z, s * x[e].w + c * y[e].w);
   }
-  return true;
+  return more;
 }
 template <int EPL>
 __device__ __forceinline__ bool rotate_pair_blk(float* bp, float* bq, int len, int lane) {
@@ -188,8 +197,8 @@ __global__ void __launch_bounds__(256) jacobi_q8_kernel(const float* __restrict_
           be += __shfl_xor_sync(FULL, be, o);
           ga += __shfl_xor_sync(FULL, ga, o);
         }
-        if (ga * ga > 1e-12f * al * be) {
-          rotated = 1;
+        if (ga * ga > JROT2 * al * be) {
+          if (ga * ga > JSTOP2 * al * be) rotated = 1;
           const float zeta = __fdividef(be - al, 2.f * ga);
           const float tt = copysignf(__frcp_rn(fabsf(zeta) + __fsqrt_rn(fmaf(zeta, zeta, 1.f))), zeta);
           const float c = rsqrtf(fmaf(tt, tt, 1.f)), sn = c * tt;

@@ -227,17 +227,21 @@ extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
   // the factorised forward (many classes, fconv / ufconv) does not form W_k: whoever reads it below rebuilds it first
   const int wk_missing = stats_grad && !plain_u(c) && c.Cin == c.Cout && !c.bc &&
                          wc_bwd_factorised_ok(c.Cin, c.K, c.E, c.class_matrix != nullptr, c.Wc != nullptr);
+  // the sums over classes (or basis matrices) that form dWeff are split over several CTAs which add into c.red: the kernel
+  // that zeroes P and s clears it too
+  const bool split_sum = chain_ok && (c.phases & WC_PHASE_REDUCE) && c.K > 1 && wc_aligned16(c.red) && !(wc_debug_flags() & 67108864);
   auto chain = [&](int lo, int hi, bool exchange) {
     return wc_bwd_chain(P, s, at<float>(c.saved, L.Weff), Wk, c.Wu, c.Cin, c.Cout, g, c.K, c.dWu, c.dbu, c.dWc, c.dbc, c.triangular,
                         c.class_matrix, at<float>(c.saved, L.ehat), c.D, c.E, c.dD, c.dclass_matrix, c.dbf, c.red, A, cvec,
                         count_dev, c.count, c.eps, at<void>(c.saved, L.Tp_bwd), c.K, at<float>(c.workspace, W.color),
                         at<float>(c.workspace, W.factor), barrier, lo, hi, exchange ? c.xchg_peers : nullptr,
-                        exchange ? c.xchg_state : nullptr, c.xchg_rank, c.xchg_world, c.info, wk_missing, (cudaStream_t)stream);
+                        exchange ? c.xchg_state : nullptr, c.xchg_rank, c.xchg_world, c.info, wk_missing, split_sum && lo == 0,
+                        (cudaStream_t)stream);
   };
   bool chained = false, all_done = false;
   if (c.phases & WC_PHASE_REDUCE) {
     rc = wc_reduce_bwd_impl(c.x, c.dy, c.N, c.HW, c.Cin, c.Cout, mean, cls, c.K, P, s, at<float>(c.workspace, W.reduce),
-                            W.reduce_bytes, CHAIN_TAIL, (cudaStream_t)stream);
+                            W.reduce_bytes, CHAIN_TAIL, split_sum ? c.red : nullptr, split_sum ? gg : 0, (cudaStream_t)stream);
     if (rc) return rc;
     if (chain_ok) {
       // one launch for the whole chain; with the adjoint exchanged over peer memory, the all-reduce is a stage of it

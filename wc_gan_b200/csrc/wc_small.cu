@@ -76,7 +76,8 @@ __device__ __forceinline__ void smm_store_panel(const float4 (&v)[SMM_NV], int k
 //               src(n,k) = C[k][n] (K3's T^T), image 1 src(n,k) = C[n][k] (K6's T); either may be NULL
 //   EPI_PSI     C is a lower-triangular product Z; what is stored is Psi = -(tril(Z) + tril(Z)^T - diag(Z))
 //               (both triangles; CTAs of strictly upper tiles do nothing)
-enum { EPI_NONE = 0, EPI_PACK = 1, EPI_PSI = 2 };
+//   EPI_ATOMIC  the tile is ADDED to C (red.global.add): the jobs of a split sum (chain launches only; C zeroed beforehand)
+enum { EPI_NONE = 0, EPI_PACK = 1, EPI_PSI = 2, EPI_ATOMIC = 3 };
 struct SmmEpi {
   int kind;
   uint8_t* pk0; uint8_t* pk1;      // packed images (wc_pack_* layout), NULL = skip
@@ -226,6 +227,7 @@ struct VecJob {
   int nb; long long bA, bx, bo;
   const float* count_dev; float count_host; int count_mode; float alpha;
   int cta0, nctas;
+  int narrow;                  // chain launches, rows contiguous in k: 16 outputs per CTA (one per warp) instead of 32
 };
 constexpr int SMM_MAXJOBS = 3, SMM_MAXVEC = 2;
 // lead: CTAs [0, lead) exit at once.  The tile code is ~1500 straight-line instructions per operand-layout variant and a
@@ -233,10 +235,17 @@ constexpr int SMM_MAXJOBS = 3, SMM_MAXVEC = 2;
 // consecutive launches lands on the same SM, so a launch can be shifted onto the SMs that just ran its variant.
 struct SmmMulti { SmmJob job[SMM_MAXJOBS]; int njobs; VecJob vec[SMM_MAXVEC]; int nvec; int lead; };
 
+// a / b for 0 <= a < 2^20, b >= 1: exact ((a + 0.5) / b is at least 0.5 / b away from an integer, the quotient's error is
+// below 2^-21 of its value)
+__device__ __forceinline__ int small_div(int a, int b) {
+  return __float2int_rz(__fdividef(__int2float_rn(a) + 0.5f, __int2float_rn(b)));
+}
+
 // one CTA = 32 outputs of one batch; 16 k-slices of 32 threads
 __device__ __forceinline__ void vec_job_run(const VecJob& v, int cta, float* sm) {
-  const int per_b = (v.M + 31) / 32;
-  const int b = cta / per_b, i0 = (cta % per_b) * 32;
+  const int nout = v.narrow ? 16 : 32;
+  const int per_b = (v.M + nout - 1) / nout;
+  const int b = cta / per_b, i0 = (cta % per_b) * nout;
   const int t = threadIdx.x, io = t & 31, ks = t >> 5;       // 16 slices
   const float* A = v.A + (long long)b * v.bA;
   const float* x = v.x ? v.x + (long long)b * v.bx : nullptr;
@@ -246,6 +255,7 @@ __device__ __forceinline__ void vec_job_run(const VecJob& v, int cta, float* sm)
     const int i = i0 + io;
     if (i < v.M)
       for (int q = 0; q < v.nsum; ++q)
+#pragma unroll 4
         for (int k = ks; k < v.K; k += 16) acc = fmaf(A[(long long)q * v.sA + (long long)k * v.csA + i], x ? x[(long long)q * v.sx + k] : 1.f, acc);
     sm[ks * 32 + io] = acc;
     __syncthreads();
@@ -254,20 +264,41 @@ __device__ __forceinline__ void vec_job_run(const VecJob& v, int cta, float* sm)
       for (int s2 = 1; s2 < 16; ++s2) acc += sm[s2 * 32 + io];
     }
   } else {
-    // rows of A are (near) contiguous in k: a warp walks k for two outputs
-    for (int h = 0; h < 2; ++h) {
-      const int i = i0 + ks * 2 + h;
-      float a = 0.f;
-      if (i < v.M)
-        for (int q = 0; q < v.nsum; ++q)
-          for (int k = io; k < v.K; k += 32) a = fmaf(A[(long long)q * v.sA + (long long)i * v.rsA + (long long)k * v.csA], x ? x[(long long)q * v.sx + k] : 1.f, a);
-      a = wc_warp_sum(a);
-      if (io == 0) sm[ks * 2 + h] = a;
+    // rows of A are (near) contiguous in k: a warp walks k for two outputs.  The (summed index, k block) pairs are walked
+    // as ONE flat loop, sixteen steps' loads of both outputs in flight at a time: as two nested loops the 2 x nsum x K/32
+    // loads were issued one L2 round trip after the other (gbar = sum_k W_k s_k with 10 classes: ~10 us, the longest job
+    // of its stage).
+    // With a sum over many matrices (narrow) a warp takes ONE output, so that the job is spread over twice the CTAs.
+    const int kb = (v.K + 31) >> 5, total = v.nsum * kb;
+    const int iA = v.narrow ? i0 + ks : i0 + ks * 2, iB = iA + 1;
+    const bool okA = iA < v.M, okB = !v.narrow && iB < v.M;
+    const float* rowA = A + (long long)iA * v.rsA;
+    const float* rowB = A + (long long)iB * v.rsA;
+    float a0 = 0.f, a1 = 0.f;
+    // running 32-bit offsets of the next step (64-bit index arithmetic per load made the loop issue bound: ~40
+    // instructions per element on 16 warps)
+    const int csA = (int)v.csA, sA = (int)v.sA, sx = (int)v.sx, K = v.K;
+    int q = 0, k = io, off = io * csA, xoff = io;
+    for (int it0 = 0; it0 < total; it0 += 16) {
+      float va[16], vb[16], vx[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const bool okk = it0 + u < total && k < K;
+        va[u] = (okk && okA) ? rowA[off] : 0.f;
+        vb[u] = (okk && okB) ? rowB[off] : 0.f;
+        vx[u] = okk ? (x ? x[xoff] : 1.f) : 0.f;
+        k += 32; off += 32 * csA; xoff += 32;
+        if (k - io >= kb * 32) { ++q; k = io; off = q * sA + io * csA; xoff = q * sx + io; }
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) { a0 = fmaf(va[u], vx[u], a0); a1 = fmaf(vb[u], vx[u], a1); }
     }
+    a0 = wc_warp_sum(a0); a1 = wc_warp_sum(a1);
+    if (io == 0) { if (v.narrow) sm[ks] = a0; else { sm[ks * 2] = a0; sm[ks * 2 + 1] = a1; } }
     __syncthreads();
     acc = (t < 32) ? sm[t] : 0.f;
   }
-  if (t < 32 && i0 + t < v.M) {
+  if (t < nout && i0 + t < v.M) {
     float scale = v.alpha;
     if (v.count_mode) {
       float cnt = v.count_dev ? v.count_dev[0] : v.count_host;
@@ -339,7 +370,7 @@ struct ChainXch {
   size_t data_off, slot_words;             // wc_xch.cuh: byte offset of the direction's slots, 8-byte words per (slot, rank)
   int rank, R, stage;                      // R <= 1: no exchange
 };
-struct ChainEnt { short type, idx, stage, pad; int v0, n; };
+struct ChainEnt { short type, idx, stage, l0; int v0, n; };      // virtual CTAs [v0, v0 + n) of `stage` run parts [l0, l0 + n) of job idx
 // one tiled product of the chain, everything the tile routine needs in 32-bit form (all strides in elements)
 struct TJob {
   const float* A; const float* B; float* C;
@@ -349,13 +380,14 @@ struct TJob {
   int bA1, bA2, bB1, bB2, bC1, bC2;
   int sA, sB;                      // stride of the extra summed dimension
   int K, nsum, nb2, gx, gy;
+  int ntile, sum_per;              // tiles of one pass over C; summed indices per virtual-CTA group (split sums: EPI_ATOMIC)
   int pk_slot_stride, pkC, row_per_b2;
   short ak, bk, epi, count_mode, tri, pad;
   float alpha;
 };
 struct ChainProgram {
   TJob smm[CH_MAXSMM]; VecJob vec[CH_MAXVEC]; EltJob elt[CH_MAXELT]; BuildJob build; ChainXch xch;
-  ChainEnt ent[CH_MAXSMM + CH_MAXVEC + CH_MAXELT];
+  ChainEnt ent[CH_MAXSMM + CH_MAXVEC + CH_MAXELT + 2];   // (+ 2: a product whose tiles are spread over two stages has two entries)
   int nent, nstages;
   int prewait;                       // stages [0, prewait) read nothing the preceding kernel writes: they run before the dependency wait
   const float* count_dev; float count_host;       // rows of the global batch (count_dev[0] when non-NULL)
@@ -367,7 +399,8 @@ struct ChainProgram {
 static_assert(sizeof(ChainProgram) <= 4000, "kernel parameter space");
 static_assert(sizeof(TJob) % 4 == 0 && offsetof(ChainProgram, smm) % 4 == 0, "word copy of a job");
 // the same bytes as plain words, so that a thread can touch an arbitrary line of the parameter block
-union ChainParams { ChainProgram pr; int words[(sizeof(ChainProgram) + 3) / 4]; };
+union alignas(16) ChainParams { ChainProgram pr; int words[(sizeof(ChainProgram) + 3) / 4]; };
+static_assert(sizeof(ChainParams) % 16 == 0, "128-bit copy of the program");
 
 // ---- tensor-core tile: C(32 x 32) = alpha * sum_q A_q(32 x K) B_q(K x 32) on mma.sync, "3xTF32" ----------------------------
 // Each operand chunk (32 x 64) is copied in its NATIVE layout with fully coalesced 16-byte cp.async.cg (L2 only: operands
@@ -380,7 +413,7 @@ union ChainParams { ChainProgram pr; int words[(sizeof(ChainProgram) + 3) / 4]; 
 // 2^-22 relative.  16 warps: 4 warp tiles of m16 x n16, times four quarters of every k chunk, summed through shared memory.
 constexpr int MT_NS = 4, MT_KC = 64, MT_OPF = 64 * 40, MT_STAGEF = 2 * MT_OPF;     // floats per operand / stage buffer
 constexpr int MT_PK = MT_KC + 4, MT_PM = 40;                                       // pitches: k contiguous / mn contiguous
-constexpr int MT_REDF = 3 * 4 * 32 * 8;
+constexpr int MT_REDF = 4 * 4 * 32 * 8;
 constexpr int CHAIN_SMEM = (MT_NS * MT_STAGEF + MT_REDF + 32 * 33) * 4;
 static_assert(32 * MT_PK <= MT_OPF && MT_KC * MT_PM <= MT_OPF, "operand buffer");
 
@@ -401,11 +434,11 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-__device__ __noinline__ void smm_tile_rt(const TJob& jb, int bx, int by, int z, float* smm_sm, int dflags, unsigned long long* dbg, float cnt) {
+__device__ __noinline__ void smm_tile_rt(const TJob& jb, int bx, int by, int z, int iq0, float* smm_sm, int dflags, unsigned long long* dbg, float cnt) {
   if (threadIdx.x == 0) wc_mark_clk(dbg, 16);
   if (jb.epi == EPI_PSI && by < bx) return;                // block-uniform
   const bool ak = jb.ak != 0, bk = jb.bk != 0;             // k is the contiguous index of the operand in memory
-  const int b1 = z / jb.nb2, b2 = z - b1 * jb.nb2;
+  const int b1 = small_div(z, jb.nb2), b2 = z - b1 * jb.nb2;
   const int i0 = by * SMM_T, j0 = bx * SMM_T;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int kq = warp >> 2, wt = warp & 3;                  // quarter of the k chunk, warp tile
@@ -419,8 +452,8 @@ __device__ __noinline__ void smm_tile_rt(const TJob& jb, int bx, int by, int z, 
   const int sa = ak ? r16 * MT_PK + c16 : r8 * MT_PM + c8;
   const int sb = MT_OPF + (bk ? r16 * MT_PK + c16 : r8 * MT_PM + c8);
   const int kta = ak ? c16 : r8, ktb = bk ? c16 : r8;      // k index (in the chunk) of this thread's pieces
-  const int K = jb.K, nkc = (K + MT_KC - 1) / MT_KC, nchunks = jb.nsum * nkc;
-  int iq = 0, ic = 0;                                       // (summed index, k chunk) of the next chunk to issue
+  const int K = jb.K, nkc = (K + MT_KC - 1) / MT_KC, nchunks = min(jb.sum_per, jb.nsum - iq0) * nkc;
+  int iq = iq0, ic = 0;                                     // (summed index, k chunk) of the next chunk to issue
   auto issue = [&](int c) {
     const int kval = K - ic * MT_KC;      // K is a multiple of 32: the last chunk may be half empty (zero-filled)
     float* st = smm_sm + (c % MT_NS) * MT_STAGEF;
@@ -440,6 +473,7 @@ __device__ __noinline__ void smm_tile_rt(const TJob& jb, int bx, int by, int z, 
     for (int q = 0; q < 3; ++q)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[n][q][e] = 0.f;
+  if (threadIdx.x == 0) wc_mark_clk(dbg, 31);
 #pragma unroll
   for (int c = 0; c < MT_NS - 1; ++c) { if (c < nchunks) issue(c); cp_async_commit(); }
   if (threadIdx.x == 0) wc_mark_clk(dbg, 17);
@@ -478,44 +512,49 @@ __device__ __noinline__ void smm_tile_rt(const TJob& jb, int bx, int by, int z, 
   cp_async_wait<0>();
   __syncthreads();                        // the ring is free: reduction scratch and the output tile live behind it
   if (threadIdx.x == 0) wc_mark_clk(dbg, 26);
-  float* red = smm_sm + MT_NS * MT_STAGEF;          // [3 k quarters][4 warp tiles][32 lanes][8]
+  float* red = smm_sm + MT_NS * MT_STAGEF;          // [4 k quarters][4 warp tiles][32 lanes][8]
   float* tile = red + MT_REDF;                      // [32][33]
-  float v8[8];
+  {
+    float v8[8];
 #pragma unroll
-  for (int n = 0; n < 2; ++n)
+    for (int n = 0; n < 2; ++n)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v8[n * 4 + e] = (acc[n][0][e] + acc[n][1][e]) + acc[n][2][e];
-  if (kq > 0) {
-    float* r = red + (((kq - 1) * 4 + wt) * 32 + lane) * 8;
+      for (int e = 0; e < 4; ++e) v8[n * 4 + e] = (acc[n][0][e] + acc[n][1][e]) + acc[n][2][e];
+    float* r = red + ((kq * 4 + wt) * 32 + lane) * 8;
     *reinterpret_cast<float4*>(r) = make_float4(v8[0], v8[1], v8[2], v8[3]);
     *reinterpret_cast<float4*>(r + 4) = make_float4(v8[4], v8[5], v8[6], v8[7]);
   }
   __syncthreads();
-  if (kq == 0) {
+  // Every warp finishes TWO of the eight elements a lane holds of its warp tile: warp (kq, wt) sums the four k quarters of
+  // elements 2 kq and 2 kq + 1 and stores them.  (With the k-quarter-0 warps doing all eight, the epilogue was ~250
+  // dependent instructions on one warp per scheduler: 2200 cycles per tile.)
+  {
+    float2 o = *reinterpret_cast<const float2*>(red + (wt * 32 + lane) * 8 + 2 * kq);
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const float* r = red + ((q * 4 + wt) * 32 + lane) * 8;
-      const float4 o0 = *reinterpret_cast<const float4*>(r), o1 = *reinterpret_cast<const float4*>(r + 4);
-      v8[0] += o0.x; v8[1] += o0.y; v8[2] += o0.z; v8[3] += o0.w; v8[4] += o1.x; v8[5] += o1.y; v8[6] += o1.z; v8[7] += o1.w;
+    for (int q = 1; q < 4; ++q) {
+      const float2 p2 = *reinterpret_cast<const float2*>(red + ((q * 4 + wt) * 32 + lane) * 8 + 2 * kq);
+      o.x += p2.x; o.y += p2.y;
     }
     float alpha = jb.alpha;
     if (jb.count_mode) alpha = __fdividef(alpha, jb.count_mode == 1 ? cnt : (cnt - 1.f));
     float* C = jb.C + (b1 * jb.bC1 + b2 * jb.bC2);
-    const int rsC = jb.rsC, csC = jb.csC, tri = jb.tri;
+    const int rsC = jb.rsC, csC = jb.csC, tri = jb.tri, epi = jb.epi;
+    const int li = m0 + gq + (kq & 1) * 8, i = i0 + li;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int li = m0 + gq + ((e >> 1) & 1) * 8, lj = n0 + (e >> 2) * 8 + 2 * tq + (e & 1);
-      const int i = i0 + li, j = j0 + lj;
-      if (jb.epi == EPI_PSI) {
+    for (int h = 0; h < 2; ++h) {
+      const int lj = n0 + (kq >> 1) * 8 + 2 * tq + h, j = j0 + lj;
+      const float acc1 = h ? o.y : o.x;
+      if (epi == EPI_PSI) {
         if (j > i) continue;
-        const float v = -alpha * v8[e];
+        const float v = -alpha * acc1;
         C[i * rsC + j * csC] = v;
         if (j < i) C[j * rsC + i * csC] = v;
       } else {
-        float v = alpha * v8[e];
+        float v = alpha * acc1;
         if ((tri == 1 && j > i) || (tri == 2 && j < i)) v = 0.f;
-        C[i * rsC + j * csC] = v;
-        if (jb.epi == EPI_PACK) tile[li * 33 + lj] = v;
+        if (epi == EPI_ATOMIC) atomicAdd(&C[i * rsC + j * csC], v);
+        else C[i * rsC + j * csC] = v;
+        if (epi == EPI_PACK) tile[li * 33 + lj] = v;
       }
     }
   }
@@ -850,21 +889,24 @@ __device__ __forceinline__ void chain_grid_barrier(unsigned* ctr, unsigned targe
 
 template <bool FACT>
 __global__ void __launch_bounds__(SMM_THREADS, 1) chain_kernel(const __grid_constant__ ChainParams kp) {
-  const ChainProgram& pr = kp.pr;
   extern __shared__ __align__(16) float smm_sm[];
   __shared__ float s_cnt[1];
-  __shared__ int s_sink;
-  // the tile routine takes its job descriptor from SHARED memory: reading it through a reference into the parameter
-  // block (generic loads from the parameter window, ~700 cycles each, in dependent chains) cost 2800 cycles of set-up and
-  // 2400 of epilogue per tile
-  __shared__ __align__(16) int s_job[(sizeof(TJob) + 3) / 4];
-  // The program (3.3 KB of kernel parameters) is read through the constant cache; cold, every job descriptor costs a
-  // chain of ~300-cycle misses at the start of every stage (measured: 1.5 us per tile).  Touch every line of it once
-  // here, BEFORE the dependency wait, where it overlaps the predecessor's tail.
-  if (threadIdx.x < (int)(sizeof(ChainProgram) / 64)) {
-    const int v = kp.words[threadIdx.x * 16];
-    if (v == 0x7fffffff) s_sink = v;       // never true for a pointer / count word in practice; keeps the load alive
+  // The program (3.5 KB of kernel parameters) is copied to SHARED memory once, BEFORE the dependency wait, where it overlaps
+  // the predecessor's tail.  Read in place through the constant bank, the dispatch of one tile cost ~2600 SM cycles per
+  // stage (the search through the entry table alone 1750: every word of the parameter block that misses the small
+  // first-level constant cache is a ~100-300 cycle access, in a dependent chain), and a reference into the parameter window
+  // handed to the tile routine turned every field access into a ~700 cycle generic load.
+  // The copy itself goes through GENERIC 128-bit loads from the parameter window (one ~700 cycle round trip for the whole
+  // block): indexed reads of the constant bank are replayed once per distinct address of a warp.
+  __shared__ __align__(16) int s_prog[sizeof(ChainParams) / 4];
+  __shared__ int s_found;
+  {
+    const int4* src = reinterpret_cast<const int4*>(kp.words);
+    asm volatile("" : "+l"(src));            // forget the address space: plain generic loads
+    for (int i = threadIdx.x; i < (int)(sizeof(ChainParams) / 16); i += SMM_THREADS) reinterpret_cast<int4*>(s_prog)[i] = src[i];
   }
+  __syncthreads();
+  const ChainProgram& pr = *reinterpret_cast<const ChainProgram*>(s_prog);
   bool waited = false;
   unsigned nbar = 0;
   for (int s = 0; s < pr.nstages; ++s) {
@@ -904,6 +946,7 @@ __global__ void __launch_bounds__(SMM_THREADS, 1) chain_kernel(const __grid_cons
         if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(x.state) = e + 1;   // every CTA read it above
       }
       if (threadIdx.x == 0 && s < 4) wc_mark(pr.dbg, 8 + 2 * s);      // barrier passed
+      if (threadIdx.x == 0) wc_mark_clk(pr.dbg, 28);
     }
     if (!waited && s >= pr.prewait) {
       wc_pdl_wait();
@@ -913,20 +956,24 @@ __global__ void __launch_bounds__(SMM_THREADS, 1) chain_kernel(const __grid_cons
       if (threadIdx.x == 0) wc_mark(pr.dbg, 8);
     }
     for (int v = blockIdx.x; v < pr.stage_total[s]; v += gridDim.x) {
-      int e = 0;
-      for (; e < pr.nent; ++e)
-        if (pr.ent[e].stage == s && v >= pr.ent[e].v0 && v < pr.ent[e].v0 + pr.ent[e].n) break;
-      if (e < pr.nent) {
+      // entry of virtual CTA v: every thread looks at one entry (a serial search was a chain of ~100 cycle steps)
+      if (threadIdx.x < pr.nent) {
+        const ChainEnt c = pr.ent[threadIdx.x];
+        if (c.stage == s && v >= c.v0 && v < c.v0 + c.n) s_found = threadIdx.x;
+      }
+      __syncthreads();
+      const int e = s_found;
+      {
         const ChainEnt en = pr.ent[e];
-        const int l = v - en.v0;
+        const int l = v - en.v0 + en.l0;
+        if (threadIdx.x == 0) wc_mark_clk(pr.dbg, 29);
         if (en.type == CJ_SMM) {
-          constexpr int JW = (int)(sizeof(TJob) / 4);
-          const int w0 = (int)(offsetof(ChainProgram, smm) / 4) + en.idx * JW;
-          if (threadIdx.x < JW) s_job[threadIdx.x] = kp.words[w0 + threadIdx.x];
-          __syncthreads();
-          const TJob& jb = *reinterpret_cast<const TJob*>(s_job);
-          const int gxy = jb.gx * jb.gy, zz = l / gxy, rem = l - zz * gxy, yy = rem / jb.gx;
-          smm_tile_rt(jb, rem - yy * jb.gx, yy, zz, smm_sm, pr.dbg_flags, pr.dbg, s_cnt[0]);
+          if (threadIdx.x == 0) wc_mark_clk(pr.dbg, 30);
+          const TJob& jb = pr.smm[en.idx];
+          // (integer divisions are ~35 dependent instructions each: three of them were 500 cycles of the dispatch)
+          const int sp = small_div(l, jb.ntile), lt = l - sp * jb.ntile;        // part of a split sum, tile of the pass
+          const int gxy = jb.gx * jb.gy, zz = small_div(lt, gxy), rem = lt - zz * gxy, yy = small_div(rem, jb.gx);
+          smm_tile_rt(jb, rem - yy * jb.gx, yy, zz, sp * jb.sum_per, smm_sm, pr.dbg_flags, pr.dbg, s_cnt[0]);
         } else if (en.type == CJ_VEC) {
           vec_job_run(pr.vec[en.idx], l, smm_sm);
         } else if (en.type == CJ_BUILDWK) {
@@ -1486,16 +1533,25 @@ int wc_factor_fwd_impl(const float* mean, const float* S, const float* count_dev
 namespace {
 struct ChainBuilder {
   ChainProgram pr{};
-  int nsmm = 0, nvec = 0, nelt = 0;
+  int nsmm = 0, nvec = 0, nelt = 0, nsplit2 = 0;
   bool ok = true;
-  void ent(int type, int idx, int stage, int n) {
+  void ent(int type, int idx, int stage, int n, int l0 = 0) {
     ChainEnt& e = pr.ent[pr.nent++];
-    e.type = (short)type; e.idx = (short)idx; e.stage = (short)stage; e.pad = 0;
+    e.type = (short)type; e.idx = (short)idx; e.stage = (short)stage; e.l0 = (short)l0;
     e.v0 = pr.stage_total[stage]; e.n = n;
     pr.stage_total[stage] += n;
     if (stage + 1 > pr.nstages) pr.nstages = stage + 1;
   }
-  void smm(int stage, const WcSmm& p, const SmmEpi& ep = SmmEpi{}, int count_mode = 0) {
+  // nsplit > 1: the summed dimension (p.nsum) is cut into nsplit groups of virtual CTAs that ADD their partial tiles into
+  // C (EPI_ATOMIC: C must be zero when the stage starts; plain epilogue only)
+  // stage2 >= 0: only the first `first_n` tiles run in `stage`, the rest in `stage2` (a product nothing in stage + 1 reads)
+  void smm(int stage, const WcSmm& p, const SmmEpi& ep0 = SmmEpi{}, int count_mode = 0, int nsplit = 1, int first_n = 0,
+           int stage2 = -1) {
+    SmmEpi ep = ep0;
+    nsplit = std::max(1, std::min(nsplit, p.nsum));
+    const int sum_per = (p.nsum + nsplit - 1) / nsplit;
+    nsplit = (p.nsum + sum_per - 1) / sum_per;
+    if (nsplit > 1) { if (ep.kind != EPI_NONE) { ok = false; return; } ep.kind = EPI_ATOMIC; }
     if (nsmm >= CH_MAXSMM || !smm_is_fast(p) || p.beta != 0.f || (p.K % 32)) { ok = false; return; }
     if (ep.kind == EPI_PACK && (ep.pkC % 32 || (ep.pk0 && !wc_aligned16(ep.pk0)) || (ep.pk1 && !wc_aligned16(ep.pk1)))) { ok = false; return; }
     const long long lim = 1ll << 30;
@@ -1513,12 +1569,21 @@ struct ChainBuilder {
     j.pk_slot_stride = (int)ep.pk_slot_stride; j.pkC = ep.pkC; j.row_per_b2 = ep.row_per_b2;
     j.epi = (short)ep.kind; j.count_mode = (short)count_mode; j.tri = (short)p.tri; j.pad = 0;
     j.alpha = p.alpha;
-    ent(CJ_SMM, nsmm++, stage, j.gx * j.gy * p.nb1 * p.nb2);
+    j.ntile = j.gx * j.gy * p.nb1 * p.nb2; j.sum_per = sum_per;
+    const int nv = j.ntile * nsplit;
+    if (stage2 < 0 || first_n >= nv) { ent(CJ_SMM, nsmm++, stage, nv); return; }
+    if (nv > 32767 || nsplit2 >= 2) { ok = false; return; }
+    ++nsplit2;
+    first_n = std::max(0, first_n);
+    if (first_n > 0) ent(CJ_SMM, nsmm, stage, first_n);
+    ent(CJ_SMM, nsmm++, stage2, nv - first_n, first_n);
   }
   void vec(int stage, const VecJob& v0) {
     if (nvec >= CH_MAXVEC || v0.M <= 0 || v0.nb <= 0) { ok = false; return; }
     VecJob& v = pr.vec[nvec];
-    v = v0; v.cta0 = 0; v.nctas = ((v.M + 31) / 32) * v.nb;
+    v = v0; v.cta0 = 0;
+    v.narrow = (v.rsA != 1 && v.nsum > 1) ? 1 : 0;
+    v.nctas = ((v.M + (v.narrow ? 15 : 31)) / (v.narrow ? 16 : 32)) * v.nb;
     ent(CJ_VEC, nvec++, stage, v.nctas);
   }
   void build(int stage, const BuildJob& j) {
@@ -1919,7 +1984,7 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
                  const float* D, int E, float* dD, float* dclass_matrix, float* dbf, float* red, float* A, float* cvec,
                  const float* count_dev, double count_host, float eps, void* Tp_bwd, int pack_K, float* ws_color,
                  float* ws_factor, unsigned* barrier, int stage_lo, int stage_hi, void* const* xchg_peers, void* xchg_state,
-                 int xchg_rank, int xchg_world, int32_t* info, int wk_missing, cudaStream_t st) {
+                 int xchg_rank, int xchg_world, int32_t* info, int wk_missing, int dweff_zeroed, cudaStream_t st) {
   if (!P || !s || !Weff || !Wk || !red || !barrier || Cin != Cout || g <= 0 || Cin % g) return WC_E_UNSUPPORTED;
   if (triangular && dWc) return WC_E_UNSUPPORTED;
   if ((dD || dclass_matrix) && (!class_matrix || !ehat || !D || E <= 0)) return WC_E_ARG;
@@ -1948,6 +2013,15 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
   }
   auto in = [&](int stage) { return stage >= stage_lo && stage < stage_hi; };
   int base = stage_lo;           // stages are renumbered from 0 inside the launch
+  bool qspan = false;            // Q's tiles are spread over stages 0 and 1 (below)
+  // dWeff is a sum over the K classes (or the E + 1 basis matrices) of C^3 products on only (C/32)^2 tiles: one CTA per
+  // tile walked the whole sum while the rest of the grid waited at the barrier (cfg2, K = 10, C = 128: 19.7 of the
+  // stage's 20 us).  With dWeff zeroed by the caller the sum is cut into groups that add their partial tiles, about one
+  // grid's worth of jobs in all.
+  auto sum_split = [&](int nsum) {
+    const int tiles = G * (g / SMM_T) * (g / SMM_T);
+    return (dweff_zeroed && nsum > 1) ? std::max(1, WC_NUM_SMS / std::max(1, tiles)) : 1;
+  };
   const bool fact = wc_bwd_factorised_ok(C, K, E, class_matrix != nullptr, dWc != nullptr) && D && stage_lo == 0 && stage_hi == 4 &&
                     (!dWu || Wu) && !dbc;
   if (fact) {
@@ -1982,7 +2056,7 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
     pw.rsA = C; pw.csA = 1; pw.rsB = 1; pw.csB = C; pw.rsC = g; pw.csC = 1;
     pw.nb1 = 1; pw.nb2 = G; pw.bA2 = (long long)g * C; pw.bB2 = (long long)g * C; pw.bC2 = (long long)g * g;
     pw.nsum = nb; pw.sA = per; pw.sB = per;
-    cb.smm(1, pw);
+    cb.smm(1, pw, SmmEpi{}, 0, sum_split(nb));
     VecJob v{};
     v.A = Bcat + (size_t)j0 * per; v.x = gs + (size_t)j0 * C; v.out = gbar; v.M = C; v.K = C; v.rsA = C; v.csA = 1;
     v.nsum = nb; v.sA = per; v.sx = C; v.nb = 1; v.alpha = 1.f;
@@ -1993,13 +2067,13 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
     if (cb.pr.xch.R > 1) cb.pr.xch.stage = 2;
   } else if (in(0)) {
     if (wk_missing) { const int rcw = wc_rebuild_wk(C, C, K, Wu, class_matrix, D, E, const_cast<float*>(Wk), st); if (rcw) return rcw; }
-    if (need_q) cb.smm(0 - base, smm_blockdiag_left(Weff, false, P, Qdst, g, G, C, C, K, per));
+    // (the long jobs first: a CTA takes virtual CTAs round-robin)
     WcSmm pw = smm_init();
     pw.A = Wk; pw.B = P; pw.C = dWeff; pw.M = g; pw.N = g; pw.K = C;
     pw.rsA = C; pw.csA = 1; pw.rsB = 1; pw.csB = C; pw.rsC = g; pw.csC = 1;
     pw.nb1 = 1; pw.nb2 = G; pw.bA2 = (long long)g * C; pw.bB2 = (long long)g * C; pw.bC2 = (long long)g * g;
     pw.nsum = K; pw.sA = per; pw.sB = per;
-    cb.smm(0 - base, pw);
+    cb.smm(0 - base, pw, SmmEpi{}, 0, sum_split(K));
     VecJob v{};
     v.A = Wk; v.x = s; v.out = gbar; v.M = C; v.K = C; v.rsA = C; v.csA = 1;
     v.nsum = K; v.sA = per; v.sx = C; v.nb = 1; v.alpha = 1.f;
@@ -2012,7 +2086,20 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
     }
     if (dbc) { EltJob j{}; j.a = s; j.out = dbc; j.n = (long long)K * C; j.K = 1; cb.elt(0 - base, CJ_COPY, j, elt_chunks(j.n)); }
     if (dbf) { EltJob j{}; j.a = s; j.out = dbf; j.n = (long long)K * C; j.K = 1; cb.elt(0 - base, CJ_COPY, j, elt_chunks(j.n)); }
+    if (need_q) {
+      // Q_k = Weff P_k feeds only parameter gradients: nothing on the chain dWeff -> Psi -> Y -> A reads it.  With several
+      // classes on a small matrix its K (C/32)^2 tiles made stage 0 a two-round stage while stages 1-3 keep most of the
+      // grid idle (cfg2: 10 / 16 / 16 tiles for 148 CTAs): the tiles that do not fit the first round of stage 0 run next to
+      // Psi in stage 1 when that keeps stage 1 a single round, and the jobs that read Q move one stage down.
+      const WcSmm pq = smm_blockdiag_left(Weff, false, P, Qdst, g, G, C, C, K, per);
+      const int tiles = G * (g / SMM_T) * (g / SMM_T), qtiles = (pq.M / SMM_T) * (pq.N / SMM_T) * pq.nb1 * pq.nb2;
+      const int room = std::max(0, WC_NUM_SMS - cb.pr.stage_total[0]);
+      qspan = K > 1 && stage_lo == 0 && stage_hi == 4 && qtiles > room && (qtiles - room) + tiles + G * ((g + 31) / 32) <= WC_NUM_SMS &&
+              !(wc_debug_flags() & 134217728);
+      if (qspan) cb.smm(0, pq, SmmEpi{}, 0, 1, room, 1); else cb.smm(0 - base, pq);
+    }
   }
+  const int qs = qspan ? 1 : 0;      // the readers of Q run one stage later
   if (in(1)) {
     SmmEpi e1{}; e1.kind = EPI_PSI;
     cb.smm(1 - base, smm_gg(dWeff, false, Weff, true, W0, g, G), e1);
@@ -2022,16 +2109,16 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
     vc.count_dev = count_dev; vc.count_host = ch; vc.count_mode = 1; vc.alpha = 1.f;
     cb.vec(1 - base, vc);
     if (!fact) {
-      if (dWu && Qdst != dWu) { EltJob j{}; j.a = Qdst; j.out = dWu; j.n = per; j.K = K; cb.elt(1 - base, CJ_SUMK, j, elt_chunks(per)); }
-      if (dD) { EltJob j{}; j.a = Qdst; j.out = dD; j.n = per; j.K = K; j.E = E; j.ehat = ehat; cb.elt(1 - base, CJ_WSUMK, j, E * elt_chunks(per)); }
-      if (dclass_matrix) { EltJob j{}; j.a = Qdst; j.b = D; j.out = de; j.n = per; j.K = K; j.E = E; cb.elt(1 - base, CJ_DOT, j, K * E); }
+      if (dWu && Qdst != dWu) { EltJob j{}; j.a = Qdst; j.out = dWu; j.n = per; j.K = K; cb.elt(1 + qs - base, CJ_SUMK, j, elt_chunks(per)); }
+      if (dD) { EltJob j{}; j.a = Qdst; j.out = dD; j.n = per; j.K = K; j.E = E; j.ehat = ehat; cb.elt(1 + qs - base, CJ_WSUMK, j, E * elt_chunks(per)); }
+      if (dclass_matrix) { EltJob j{}; j.a = Qdst; j.b = D; j.out = de; j.n = per; j.K = K; j.E = E; cb.elt(1 + qs - base, CJ_DOT, j, K * E); }
     }
   }
   if (in(2)) {
     WcSmm py = smm_gg(W0, false, Weff, false, W1, g, G);
     py.rsC = 1; py.csC = g;                                   // stored transposed: the next product reads row panels
     cb.smm(2 - base, py);
-    if (dclass_matrix) { EltJob j{}; j.a = de; j.out = dclass_matrix; j.K = K; j.E = E; j.cm = class_matrix; j.ehat = ehat; cb.elt(2 - base, CJ_L2N, j, 1); }
+    if (dclass_matrix) { EltJob j{}; j.a = de; j.out = dclass_matrix; j.K = K; j.E = E; j.cm = class_matrix; j.ehat = ehat; cb.elt(2 + qs - base, CJ_L2N, j, 1); }
   }
   if (in(3)) {
     WcSmm pa = smm_gg(W1, false, Weff, false, A, g, G);

@@ -10,7 +10,8 @@
 //   jacobi_q8_kernel     g in {16, 32, 64}: the same with eight lanes per pair (four pairs per warp), see below.
 //   jacobi_block_kernel  g >= 128 (multiple of 32): the columns are cut into blocks of 16; a block-level round-robin gives
 //                        nb/2 independent block pairs per block round, one CTA each (g = 256: 8 CTAs per group matrix).  A
-//                        CTA loads its two blocks (2 x 16 columns x g) into shared memory, rotates every cross pair (in the
+//                        CTA (4 warps, eight lanes per column pair) loads its two blocks (2 x 16 columns x g) into shared
+//                        memory, rotates every cross pair (in the
 //                        first block round of a sweep also the pairs inside each block), writes the blocks back and meets
 //                        the other CTAs of its group at a barrier in L2 (release-add / acquire-spin on a per-group counter).
 //                        A sweep is nb-1 block rounds; the sweep loop ends when no CTA of the group rotated anything.
@@ -27,7 +28,7 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int JB = 16;                  // columns per block (block kernel)
-constexpr int JBLK_THREADS = 512;       // 16 warps: one per column pair of a sub-round
+constexpr int JBLK_THREADS = 128;       // 4 warps x 4 column pairs (eight lanes each): the 16 pairs of a sub-round
 constexpr int JMAX_SWEEPS = 20;
 constexpr float JROT2 = 1e-12f;         // rotate a pair when cos^2 > JROT2
 constexpr float JSTOP2 = 1e-8f;         // another sweep is needed when some pair had cos^2 > JSTOP2
@@ -111,6 +112,41 @@ template <int EPL>
 __device__ __forceinline__ bool rotate_pair_blk(float* bp, float* bq, int len, int lane) {
   if constexpr (EPL % 4 == 0) return rotate_pair_v4<EPL>(bp, bq, lane);
   else return rotate_pair<EPL>(bp, bq, len, lane);
+}
+// EIGHT lanes per pair (columns of length 32 * NV, contiguous): lane l8 of the pair owns elements 4 l8 + 32 v + 0..3.  A
+// quarter-warp reads 128 contiguous bytes of one column per access, a warp rotates four pairs at once, and the three dot
+// products take a 3-step reduction among the 8 lanes (the whole-warp version: 5 steps, and 4x the warps per sub-round).
+template <int NV>
+__device__ __forceinline__ bool rotate_pair_l8(float* bp, float* bq, int l8) {
+  float4 x[NV], y[NV];
+  float al[2] = {0.f, 0.f}, be[2] = {0.f, 0.f}, ga[2] = {0.f, 0.f};       // two partial sums each: shorter FMA chains
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    x[v] = *reinterpret_cast<const float4*>(bp + 4 * l8 + 32 * v);
+    y[v] = *reinterpret_cast<const float4*>(bq + 4 * l8 + 32 * v);
+    float& a = al[v & 1]; float& b = be[v & 1]; float& c = ga[v & 1];
+    a = fmaf(x[v].x, x[v].x, a); a = fmaf(x[v].y, x[v].y, a); a = fmaf(x[v].z, x[v].z, a); a = fmaf(x[v].w, x[v].w, a);
+    b = fmaf(y[v].x, y[v].x, b); b = fmaf(y[v].y, y[v].y, b); b = fmaf(y[v].z, y[v].z, b); b = fmaf(y[v].w, y[v].w, b);
+    c = fmaf(x[v].x, y[v].x, c); c = fmaf(x[v].y, y[v].y, c); c = fmaf(x[v].z, y[v].z, c); c = fmaf(x[v].w, y[v].w, c);
+  }
+  float sa = al[0] + al[1], sb = be[0] + be[1], sg = ga[0] + ga[1];
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    sa += __shfl_xor_sync(FULL, sa, o);
+    sb += __shfl_xor_sync(FULL, sb, o);
+    sg += __shfl_xor_sync(FULL, sg, o);
+  }
+  if (!(sg * sg > JROT2 * sa * sb)) return false;
+  const bool more = sg * sg > JSTOP2 * sa * sb;
+  const float zeta = __fdividef(sb - sa, 2.f * sg);
+  const float tt = copysignf(__frcp_rn(fabsf(zeta) + __fsqrt_rn(fmaf(zeta, zeta, 1.f))), zeta);
+  const float c = rsqrtf(fmaf(tt, tt, 1.f)), s = c * tt;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    *reinterpret_cast<float4*>(bp + 4 * l8 + 32 * v) = make_float4(c * x[v].x - s * y[v].x, c * x[v].y - s * y[v].y, c * x[v].z - s * y[v].z, c * x[v].w - s * y[v].w);
+    *reinterpret_cast<float4*>(bq + 4 * l8 + 32 * v) = make_float4(s * x[v].x + c * y[v].x, s * x[v].y + c * y[v].y, s * x[v].z + c * y[v].z, s * x[v].w + c * y[v].w);
+  }
+  return more;
 }
 
 // ---- g <= 64: whole matrix in one CTA ---------------------------------------------------------------------------------
@@ -272,30 +308,42 @@ __global__ void __launch_bounds__(JBLK_THREADS, 1) jacobi_block_kernel(const flo
     for (int R = 0; R < nb - 1; ++R) {
       int bp, bq; rr_pair(nb, R, c, bp, bq);
       // load the two blocks (each JB contiguous columns of B): 128-bit, L2 only (written by other CTAs in earlier rounds)
-      for (int h = 0; h < 2; ++h) {
-        const float4* src = reinterpret_cast<const float4*>(B + (long long)(h ? bq : bp) * JB * g);
-        float4* dst = reinterpret_cast<float4*>(blk[h]);
-        for (int i = t; i < JB * g / 4; i += JBLK_THREADS) dst[i] = __ldcg(src + i);
+      // (JB * g / 4 = EPL * JBLK_THREADS vectors per block: all 2 * EPL loads of a thread are in flight together)
+      {
+        float4 tmp[2][EPL];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4* src = reinterpret_cast<const float4*>(B + (long long)(h ? bq : bp) * JB * g);
+#pragma unroll
+          for (int u = 0; u < EPL; ++u) tmp[h][u] = __ldcg(src + t + u * JBLK_THREADS);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int u = 0; u < EPL; ++u) reinterpret_cast<float4*>(blk[h])[t + u * JBLK_THREADS] = tmp[h][u];
       }
       __syncthreads();
+      const int slot = warp * 4 + (lane >> 3), l8 = lane & 7;      // this lane's pair of the sub-round
       if (R == 0) {
         // pairs inside the 2 x JB columns, all of them: a full tournament of 32 players (31 sub-rounds of 16 pairs)
         for (int r = 0; r < 2 * JB - 1; ++r) {
-          int p, q; rr_pair(2 * JB, r, warp, p, q);
-          rotated |= rotate_pair_blk<EPL>(jsm + p * g, jsm + q * g, g, lane) ? 1 : 0;
+          int p, q; rr_pair(2 * JB, r, slot, p, q);
+          rotated |= rotate_pair_l8<EPL>(jsm + p * g, jsm + q * g, l8) ? 1 : 0;
           __syncthreads();
         }
       } else {
-        // cross pairs only: column `warp` of the first block with column (warp + r) % JB of the second
+        // cross pairs only: column `slot` of the first block with column (slot + r) % JB of the second
         for (int r = 0; r < JB; ++r) {
-          rotated |= rotate_pair_blk<EPL>(blk[0] + warp * g, blk[1] + ((warp + r) & (JB - 1)) * g, g, lane) ? 1 : 0;
+          rotated |= rotate_pair_l8<EPL>(blk[0] + slot * g, blk[1] + ((slot + r) & (JB - 1)) * g, l8) ? 1 : 0;
           __syncthreads();
         }
       }
+#pragma unroll
       for (int h = 0; h < 2; ++h) {
         float4* dst = reinterpret_cast<float4*>(B + (long long)(h ? bq : bp) * JB * g);
         const float4* src = reinterpret_cast<const float4*>(blk[h]);
-        for (int i = t; i < JB * g / 4; i += JBLK_THREADS) dst[i] = src[i];
+#pragma unroll
+        for (int u = 0; u < EPL; ++u) dst[t + u * JBLK_THREADS] = src[t + u * JBLK_THREADS];
       }
       if (R == nb - 2 && __syncthreads_or(rotated) && t == 0) atomicOr(rot + sweep, 1u);
       group_barrier(bar, ++nbar * cpg);

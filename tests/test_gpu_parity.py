@@ -211,6 +211,20 @@ def test_cfg3_full_size_zca_vs_oracle(g):
     run_case('d', 'uconv', (256, 16, 16, 256), dec='zca', g=g)
 
 
+@pytest.mark.parametrize('after_norm,shape,K,E,g', [('ucconv', (32, 8, 8, 256), 10, 4, None),      # 2 class groups per tile, Q in stage 0
+                                                      ('ufconv', (32, 8, 8, 256), 6, 3, None),
+                                                      ('ucconv', (48, 8, 8, 128), 10, 4, 64),       # two whitening groups
+                                                      ('ufconv', (48, 8, 8, 128), 7, 3, 32),
+                                                      ('cconv', (40, 8, 8, 128), 12, 4, None),      # no unconditional kernel
+                                                      ('ucconv', (24, 4, 4, 64), 5, 2, None)])
+def test_split_class_sums(after_norm, shape, K, E, g):
+    """Backward chain with several classes: dWeff = sum_k W_k P_k^T is formed by groups of classes that ADD their partial
+    tiles into the zeroed adjoint buffer, and the tiles of Q_k that do not fit the first round of stage 0 run in stage 1
+    (wc_bwd_chain in csrc/wc_small.cu); shapes chosen to hit one / several classes per group, block-diagonal whitening
+    and both placements of Q."""
+    run_case('d', after_norm, shape, K=K, E=E, g=g)
+
+
 def test_cfg2_full_size_conditional_vs_oracle():
     """cfg4's largest generator layer shape (256 x 32 x 32 x 128, K = 10, E = 4, ufconv) against the fp64 oracle."""
     run_case('d', 'ufconv', (256, 32, 32, 128), K=10, E=4)

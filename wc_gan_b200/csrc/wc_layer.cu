@@ -229,6 +229,7 @@ extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
                          wc_bwd_factorised_ok(c.Cin, c.K, c.E, c.class_matrix != nullptr, c.Wc != nullptr);
   // the sums over classes (or basis matrices) that form dWeff are split over several CTAs which add into c.red: the kernel
   // that zeroes P and s clears it too
+  // (experiment bit 2^26 = 67108864: one CTA per tile walks the whole sum, as before)
   const bool split_sum = chain_ok && (c.phases & WC_PHASE_REDUCE) && c.K > 1 && wc_aligned16(c.red) && !(wc_debug_flags() & 67108864);
   auto chain = [&](int lo, int hi, bool exchange) {
     return wc_bwd_chain(P, s, at<float>(c.saved, L.Weff), Wk, c.Wu, c.Cin, c.Cout, g, c.K, c.dWu, c.dbu, c.dWc, c.dbc, c.triangular,

@@ -2091,6 +2091,7 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
       // classes on a small matrix its K (C/32)^2 tiles made stage 0 a two-round stage while stages 1-3 keep most of the
       // grid idle (cfg2: 10 / 16 / 16 tiles for 148 CTAs): the tiles that do not fit the first round of stage 0 run next to
       // Psi in stage 1 when that keeps stage 1 a single round, and the jobs that read Q move one stage down.
+      // (experiment bit 2^27 = 134217728: all of Q in stage 0)
       const WcSmm pq = smm_blockdiag_left(Weff, false, P, Qdst, g, G, C, C, K, per);
       const int tiles = G * (g / SMM_T) * (g / SMM_T), qtiles = (pq.M / SMM_T) * (pq.N / SMM_T) * pq.nb1 * pq.nb2;
       const int room = std::max(0, WC_NUM_SMS - cb.pr.stage_total[0]);

@@ -2,7 +2,8 @@
    compute-sanitizer --tool {memcheck,racecheck,synccheck} python scratch/sanitize_smoke.py
 1. __graft_entry__.smoke(): 16x8x8x256 ufconv K=5 E=3 (tcgen05 K1/K3/K4/K6, cluster Cholesky with st.async hand-overs, chain)
 2. 32x4x4x128 ufconv K=40 E=4: the factorised coloring stages (CJ_MIXK / CJ_MIXT / CJ_DOT2) of chain_kernel<true>
-3. 8x8x8x256 uconv ZCA g=256: multi-CTA block Jacobi;  g=64: shared-memory Jacobi"""
+3. 8x8x8x256 uconv ZCA g=256: multi-CTA block Jacobi;  g=64: shared-memory Jacobi
+4. 16x4x4x128 ucconv K=10: split class sums (EPI_ATOMIC) with the rider product Q spread over stages 0 / 1"""
 import sys
 sys.path.insert(0, '/root/repo')
 import torch
@@ -22,6 +23,7 @@ def run(shape, an, K, E, dec='cholesky', g=None):
     st.check_info()
     assert torch.isfinite(y).all() and torch.isfinite(x.grad).all()
 run((32, 4, 4, 128), 'ufconv', 40, 4)
+run((16, 4, 4, 128), 'ucconv', 10, 4)
 run((8, 8, 8, 256), 'uconv', None, 4, dec='zca')
 run((8, 8, 8, 256), 'uconv', None, 4, dec='zca', g=64)
 print('sanitize_smoke ok')

@@ -148,7 +148,7 @@ int wc_factor_bwd_impl(const float* dWeff, const float* gbar, const float* Weff,
 
 int wc_reduce_bwd_impl(const float* x, const float* dy, int N, int HW, int Cin, int Cout, const float* mean, const int32_t* cls,
                        int K, float* P, float* s, float* workspace, size_t workspace_bytes, int zero_tail_floats,
-                       float* zero2, size_t zero2_floats, cudaStream_t stream);
+                       float* zero2, size_t zero2_floats, float* zero3, size_t zero3_floats, cudaStream_t stream);
 
 // K5a + K5b as one persistent multi-stage launch (wc_small.cu); WC_E_UNSUPPORTED: use the per-product launches
 bool wc_bwd_factorised_ok(int C, int K, int E, bool has_class_matrix, bool has_wc);
@@ -157,7 +157,7 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
                  const float* D, int E, float* dD, float* dclass_matrix, float* dbf, float* red, float* A, float* cvec,
                  const float* count_dev, double count_host, float eps, void* Tp_bwd, int pack_K, float* ws_color,
                  float* ws_factor, unsigned* barrier, int stage_lo, int stage_hi, void* const* xchg_peers, void* xchg_state,
-                 int xchg_rank, int xchg_world, int32_t* info, int wk_missing, int dweff_zeroed, cudaStream_t st);
+                 int xchg_rank, int xchg_world, int32_t* info, int wk_missing, int dweff_zeroed, int ws_zeroed, cudaStream_t st);
 int wc_rebuild_wk(int Cin, int Cout, int K, const float* Wu, const float* class_matrix, const float* D, int E, float* Wk, cudaStream_t st);
 
 int wc_apply_fwd_impl(const float* x, int N, int HW, int Cin, int Cout, const float* mean, const float* T, const void* T_packed,

@@ -261,34 +261,39 @@ __global__ void stats_finalize_kernel(const float* __restrict__ partS, const flo
 // (the kernel after it cannot be scheduled, let alone run its prologue, before the memset has finished, and the memset
 // cannot start before the kernel before it has drained).  The stores come after the dependency wait: the kernel before
 // this one may still be reading the buffer (finalize of the previous call on the same workspace).
-// (p2, n16_2): an optional second range (the adjoint accumulator that the split class sums of the backward chain add into)
+// (p2, n16_2), (p3, n16_3): optional further ranges (the adjoint accumulator that the split class sums of the backward chain
+// add into; the scratch matrices its K-split products add into)
 __global__ void __launch_bounds__(256) zero_kernel(uint4* __restrict__ p, size_t n16, uint32_t* __restrict__ tail, int ntail,
-                                                   uint4* __restrict__ p2, size_t n16_2) {
+                                                   uint4* __restrict__ p2, size_t n16_2, uint4* __restrict__ p3, size_t n16_3) {
   wc_pdl_wait();
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p[i] = z;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16_2; i += (size_t)gridDim.x * blockDim.x) p2[i] = z;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16_3; i += (size_t)gridDim.x * blockDim.x) p3[i] = z;
   if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0u;
 }
 // *by_kernel (nullable) = 1 when the zeroing was done by zero_kernel, i.e. by a kernel that waits for everything before it on
 // the stream before it lets its successor start (what tc_gram_kernel's late dependency wait relies on), 0 for a memset.
 // (ptr2, bytes2): optional second range, a multiple of 16 bytes
-int zero_launch(void* ptr, size_t bytes, cudaStream_t st, int* by_kernel = nullptr, void* ptr2 = nullptr, size_t bytes2 = 0) {
+int zero_launch(void* ptr, size_t bytes, cudaStream_t st, int* by_kernel = nullptr, void* ptr2 = nullptr, size_t bytes2 = 0,
+                void* ptr3 = nullptr, size_t bytes3 = 0) {
   if (by_kernel) *by_kernel = 0;
   if (!ptr2) bytes2 = 0;
-  if (!wc_aligned16(ptr) || (bytes & 3) || !wc_aligned16(ptr2) || (bytes2 & 15) ||
+  if (!ptr3) bytes3 = 0;
+  if (!wc_aligned16(ptr) || (bytes & 3) || !wc_aligned16(ptr2) || (bytes2 & 15) || !wc_aligned16(ptr3) || (bytes3 & 15) ||
       (wc_debug_flags() & 4096 * 65536 * 2)) {   // experiment bit 29: memset node
     WC_CUDA(cudaMemsetAsync(ptr, 0, bytes, st));
     if (bytes2) WC_CUDA(cudaMemsetAsync(ptr2, 0, bytes2, st));
+    if (bytes3) WC_CUDA(cudaMemsetAsync(ptr3, 0, bytes3, st));
     return 0;
   }
   const size_t n16 = bytes / 16;
   const int ntail = (int)((bytes - n16 * 16) / 4);
-  const size_t want = (n16 + bytes2 / 16 + 255) / 256;
+  const size_t want = (n16 + bytes2 / 16 + bytes3 / 16 + 255) / 256;
   const unsigned grid = (unsigned)(want < 1 ? 1 : (want > (size_t)WC_NUM_SMS * 4 ? (size_t)WC_NUM_SMS * 4 : want));
   WC_CUDA(wc_launch(zero_kernel, grid, 256, 0, st, reinterpret_cast<uint4*>(ptr), n16,
                     reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ptr) + n16 * 16), ntail,
-                    reinterpret_cast<uint4*>(ptr2), bytes2 / 16));
+                    reinterpret_cast<uint4*>(ptr2), bytes2 / 16, reinterpret_cast<uint4*>(ptr3), bytes3 / 16));
   WC_CHECK_LAUNCH();
   if (by_kernel) *by_kernel = 1;
   return 0;
@@ -496,15 +501,15 @@ extern "C" size_t wc_reduce_workspace_bytes(int N, int HW, int Cin, int Cout, in
 extern "C" int wc_reduce_bwd(const float* x, const float* dy, int N, int HW, int Cin, int Cout,
                              const float* mean, const int32_t* cls, int K,
                              float* P, float* s, float* workspace, size_t workspace_bytes, wc_stream_t stream) {
-  return wc_reduce_bwd_impl(x, dy, N, HW, Cin, Cout, mean, cls, K, P, s, workspace, workspace_bytes, 0, nullptr, 0, (cudaStream_t)stream);
+  return wc_reduce_bwd_impl(x, dy, N, HW, Cin, Cout, mean, cls, K, P, s, workspace, workspace_bytes, 0, nullptr, 0, nullptr, 0, (cudaStream_t)stream);
 }
 
 // zero_tail_floats: floats after s (P | s | tail contiguous) that the accumulator memset also clears (the grid-barrier
 // counter of the chain launch that consumes P and s); (zero2, zero2_floats): one more buffer cleared by the same launch
-// (the adjoint accumulator of that chain), nullable
+// (the adjoint accumulator of that chain; its K-split scratch matrices), nullable
 int wc_reduce_bwd_impl(const float* x, const float* dy, int N, int HW, int Cin, int Cout, const float* mean, const int32_t* cls,
                        int K, float* P, float* s, float* workspace, size_t workspace_bytes, int zero_tail_floats,
-                       float* zero2, size_t zero2_floats, cudaStream_t stream) {
+                       float* zero2, size_t zero2_floats, float* zero3, size_t zero3_floats, cudaStream_t stream) {
   if (!x || !dy || !P || !s || N <= 0 || HW <= 0 || Cin <= 0 || Cout <= 0 || K <= 0) return WC_E_ARG;
   if ((int64_t)N * HW > (int64_t)INT32_MAX) return WC_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
@@ -522,10 +527,10 @@ int wc_reduce_bwd_impl(const float* x, const float* dy, int N, int HW, int Cin, 
   int zk = 0;
   if (s == P + (size_t)K * Cin * Cout) {   // P | s contiguous (wc_layer_bwd's workspace): one memset
     const int rz = zero_launch(P, ((size_t)K * Cin * Cout + (size_t)K * Cout + (size_t)zero_tail_floats) * 4, st, &zk, zero2,
-                               zero2_floats * 4);
+                               zero2_floats * 4, zero3, zero3_floats * 4);
     if (rz) return rz;
   } else {
-    if (zero_tail_floats || zero2) return WC_E_ARG;
+    if (zero_tail_floats || zero2 || zero3) return WC_E_ARG;
     WC_CUDA(cudaMemsetAsync(P, 0, (size_t)K * Cin * Cout * 4, st));
     WC_CUDA(cudaMemsetAsync(s, 0, (size_t)K * Cout * 4, st));
   }

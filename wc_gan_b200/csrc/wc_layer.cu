@@ -231,18 +231,26 @@ extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
   // that zeroes P and s clears it too
   // (experiment bit 2^26 = 67108864: one CTA per tile walks the whole sum, as before)
   const bool split_sum = chain_ok && (c.phases & WC_PHASE_REDUCE) && c.K > 1 && wc_aligned16(c.red) && !(wc_debug_flags() & 67108864);
+  // The products of stages 1 and 2 (Psi, Y) are split along K over several CTAs that add their partial tiles into the two
+  // scratch matrices at the head of the factor workspace: cleared by the same kernel, when the whole chain runs in this call.
+  // (experiment bit 2^28 = 268435456: one CTA per tile)
+  const bool whole_call = (c.phases & WC_PHASE_REDUCE) && (c.phases & WC_PHASE_DX) && c.dx;
+  const bool split_k = chain_ok && whole_call && W.factor_bytes >= 2 * wc_align_up(gg * 4, 256) &&
+                       wc_aligned16(at<float>(c.workspace, W.factor)) && !(wc_debug_flags() & 268435456);
   auto chain = [&](int lo, int hi, bool exchange) {
     return wc_bwd_chain(P, s, at<float>(c.saved, L.Weff), Wk, c.Wu, c.Cin, c.Cout, g, c.K, c.dWu, c.dbu, c.dWc, c.dbc, c.triangular,
                         c.class_matrix, at<float>(c.saved, L.ehat), c.D, c.E, c.dD, c.dclass_matrix, c.dbf, c.red, A, cvec,
                         count_dev, c.count, c.eps, at<void>(c.saved, L.Tp_bwd), c.K, at<float>(c.workspace, W.color),
                         at<float>(c.workspace, W.factor), barrier, lo, hi, exchange ? c.xchg_peers : nullptr,
                         exchange ? c.xchg_state : nullptr, c.xchg_rank, c.xchg_world, c.info, wk_missing, split_sum && lo == 0,
-                        (cudaStream_t)stream);
+                        split_k && lo == 0 && hi == 4, (cudaStream_t)stream);
   };
   bool chained = false, all_done = false;
   if (c.phases & WC_PHASE_REDUCE) {
     rc = wc_reduce_bwd_impl(c.x, c.dy, c.N, c.HW, c.Cin, c.Cout, mean, cls, c.K, P, s, at<float>(c.workspace, W.reduce),
-                            W.reduce_bytes, CHAIN_TAIL, split_sum ? c.red : nullptr, split_sum ? gg : 0, (cudaStream_t)stream);
+                            W.reduce_bytes, CHAIN_TAIL, split_sum ? c.red : nullptr, split_sum ? gg : 0,
+                            split_k ? at<float>(c.workspace, W.factor) : nullptr, split_k ? 2 * wc_align_up(gg * 4, 256) / 4 : 0,
+                            (cudaStream_t)stream);
     if (rc) return rc;
     if (chain_ok) {
       // one launch for the whole chain; with the adjoint exchanged over peer memory, the all-reduce is a stage of it

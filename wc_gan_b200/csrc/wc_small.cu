@@ -76,8 +76,9 @@ __device__ __forceinline__ void smm_store_panel(const float4 (&v)[SMM_NV], int k
 //               src(n,k) = C[k][n] (K3's T^T), image 1 src(n,k) = C[n][k] (K6's T); either may be NULL
 //   EPI_PSI     C is a lower-triangular product Z; what is stored is Psi = -(tril(Z) + tril(Z)^T - diag(Z))
 //               (both triangles; CTAs of strictly upper tiles do nothing)
-//   EPI_ATOMIC  the tile is ADDED to C (red.global.add): the jobs of a split sum (chain launches only; C zeroed beforehand)
-enum { EPI_NONE = 0, EPI_PACK = 1, EPI_PSI = 2, EPI_ATOMIC = 3 };
+// Chain launches can also ADD a tile to C (red.global.add; TJob::atomic): the parts of a split sum, C zeroed beforehand.
+// EPI_PSI is linear in Z, so its parts add into both triangles the same way.
+enum { EPI_NONE = 0, EPI_PACK = 1, EPI_PSI = 2 };
 struct SmmEpi {
   int kind;
   uint8_t* pk0; uint8_t* pk1;      // packed images (wc_pack_* layout), NULL = skip
@@ -380,9 +381,10 @@ struct TJob {
   int bA1, bA2, bB1, bB2, bC1, bC2;
   int sA, sB;                      // stride of the extra summed dimension
   int K, nsum, nb2, gx, gy;
-  int ntile, sum_per;              // tiles of one pass over C; summed indices per virtual-CTA group (split sums: EPI_ATOMIC)
+  int ntile, chunks_per;           // tiles of one pass over C; 64-wide k chunks (of the nsum x K/64 in all) per part of a split sum
+  int tri_enum;                    // EPI_PSI: the virtual CTAs enumerate the lower tiles only (gx == gy)
   int pk_slot_stride, pkC, row_per_b2;
-  short ak, bk, epi, count_mode, tri, pad;
+  short ak, bk, epi, count_mode, tri, atomic;
   float alpha;
 };
 struct ChainProgram {
@@ -434,7 +436,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-__device__ __noinline__ void smm_tile_rt(const TJob& jb, int bx, int by, int z, int iq0, float* smm_sm, int dflags, unsigned long long* dbg, float cnt) {
+__device__ __noinline__ void smm_tile_rt(const TJob& jb, int bx, int by, int z, int chunk0, float* smm_sm, int dflags, unsigned long long* dbg, float cnt) {
   if (threadIdx.x == 0) wc_mark_clk(dbg, 16);
   if (jb.epi == EPI_PSI && by < bx) return;                // block-uniform
   const bool ak = jb.ak != 0, bk = jb.bk != 0;             // k is the contiguous index of the operand in memory
@@ -452,8 +454,8 @@ __device__ __noinline__ void smm_tile_rt(const TJob& jb, int bx, int by, int z, 
   const int sa = ak ? r16 * MT_PK + c16 : r8 * MT_PM + c8;
   const int sb = MT_OPF + (bk ? r16 * MT_PK + c16 : r8 * MT_PM + c8);
   const int kta = ak ? c16 : r8, ktb = bk ? c16 : r8;      // k index (in the chunk) of this thread's pieces
-  const int K = jb.K, nkc = (K + MT_KC - 1) / MT_KC, nchunks = min(jb.sum_per, jb.nsum - iq0) * nkc;
-  int iq = iq0, ic = 0;                                     // (summed index, k chunk) of the next chunk to issue
+  const int K = jb.K, nkc = (K + MT_KC - 1) / MT_KC, nchunks = min(jb.chunks_per, jb.nsum * nkc - chunk0);
+  int iq = small_div(chunk0, nkc), ic = chunk0 - iq * nkc;   // (summed index, k chunk) of the next chunk to issue
   auto issue = [&](int c) {
     const int kval = K - ic * MT_KC;      // K is a multiple of 32: the last chunk may be half empty (zero-filled)
     float* st = smm_sm + (c % MT_NS) * MT_STAGEF;
@@ -538,7 +540,7 @@ __device__ __noinline__ void smm_tile_rt(const TJob& jb, int bx, int by, int z, 
     float alpha = jb.alpha;
     if (jb.count_mode) alpha = __fdividef(alpha, jb.count_mode == 1 ? cnt : (cnt - 1.f));
     float* C = jb.C + (b1 * jb.bC1 + b2 * jb.bC2);
-    const int rsC = jb.rsC, csC = jb.csC, tri = jb.tri, epi = jb.epi;
+    const int rsC = jb.rsC, csC = jb.csC, tri = jb.tri, epi = jb.epi, atomic = jb.atomic;
     const int li = m0 + gq + (kq & 1) * 8, i = i0 + li;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -547,12 +549,17 @@ __device__ __noinline__ void smm_tile_rt(const TJob& jb, int bx, int by, int z, 
       if (epi == EPI_PSI) {
         if (j > i) continue;
         const float v = -alpha * acc1;
-        C[i * rsC + j * csC] = v;
-        if (j < i) C[j * rsC + i * csC] = v;
+        if (atomic) {
+          atomicAdd(&C[i * rsC + j * csC], v);
+          if (j < i) atomicAdd(&C[j * rsC + i * csC], v);
+        } else {
+          C[i * rsC + j * csC] = v;
+          if (j < i) C[j * rsC + i * csC] = v;
+        }
       } else {
         float v = alpha * acc1;
         if ((tri == 1 && j > i) || (tri == 2 && j < i)) v = 0.f;
-        if (epi == EPI_ATOMIC) atomicAdd(&C[i * rsC + j * csC], v);
+        if (atomic) atomicAdd(&C[i * rsC + j * csC], v);
         else C[i * rsC + j * csC] = v;
         if (epi == EPI_PACK) tile[li * 33 + lj] = v;
       }
@@ -972,8 +979,23 @@ __global__ void __launch_bounds__(SMM_THREADS, 1) chain_kernel(const __grid_cons
           const TJob& jb = pr.smm[en.idx];
           // (integer divisions are ~35 dependent instructions each: three of them were 500 cycles of the dispatch)
           const int sp = small_div(l, jb.ntile), lt = l - sp * jb.ntile;        // part of a split sum, tile of the pass
-          const int gxy = jb.gx * jb.gy, zz = small_div(lt, gxy), rem = lt - zz * gxy, yy = small_div(rem, jb.gx);
-          smm_tile_rt(jb, rem - yy * jb.gx, yy, zz, sp * jb.sum_per, smm_sm, pr.dbg_flags, pr.dbg, s_cnt[0]);
+          int zz, yy, xx;
+          if (jb.tri_enum) {
+            // lower tiles only: lt = zz * T (T + 1) / 2 + yy (yy + 1) / 2 + xx, xx <= yy
+            const int per_z = jb.gy * (jb.gy + 1) / 2;
+            zz = small_div(lt, per_z);
+            const int r = lt - zz * per_z;
+            yy = (int)((__fsqrt_rn(8.f * (float)r + 1.f) - 1.f) * 0.5f);
+            if (yy * (yy + 1) / 2 > r) --yy;                                    // (rounding of the square root)
+            if ((yy + 1) * (yy + 2) / 2 <= r) ++yy;
+            xx = r - yy * (yy + 1) / 2;
+          } else {
+            const int gxy = jb.gx * jb.gy;
+            zz = small_div(lt, gxy);
+            const int rem = lt - zz * gxy;
+            yy = small_div(rem, jb.gx); xx = rem - yy * jb.gx;
+          }
+          smm_tile_rt(jb, xx, yy, zz, sp * jb.chunks_per, smm_sm, pr.dbg_flags, pr.dbg, s_cnt[0]);
         } else if (en.type == CJ_VEC) {
           vec_job_run(pr.vec[en.idx], l, smm_sm);
         } else if (en.type == CJ_BUILDWK) {
@@ -1542,16 +1564,17 @@ struct ChainBuilder {
     pr.stage_total[stage] += n;
     if (stage + 1 > pr.nstages) pr.nstages = stage + 1;
   }
-  // nsplit > 1: the summed dimension (p.nsum) is cut into nsplit groups of virtual CTAs that ADD their partial tiles into
-  // C (EPI_ATOMIC: C must be zero when the stage starts; plain epilogue only)
+  // nsplit > 1: the nsum x K/64 chunks of a tile are cut into nsplit groups of virtual CTAs that ADD their partial tiles
+  // into C (C must be zero when the stage starts; plain and EPI_PSI epilogues)
   // stage2 >= 0: only the first `first_n` tiles run in `stage`, the rest in `stage2` (a product nothing in stage + 1 reads)
   void smm(int stage, const WcSmm& p, const SmmEpi& ep0 = SmmEpi{}, int count_mode = 0, int nsplit = 1, int first_n = 0,
            int stage2 = -1) {
-    SmmEpi ep = ep0;
-    nsplit = std::max(1, std::min(nsplit, p.nsum));
-    const int sum_per = (p.nsum + nsplit - 1) / nsplit;
-    nsplit = (p.nsum + sum_per - 1) / sum_per;
-    if (nsplit > 1) { if (ep.kind != EPI_NONE) { ok = false; return; } ep.kind = EPI_ATOMIC; }
+    const SmmEpi& ep = ep0;
+    const int chunks = p.nsum * ((p.K + MT_KC - 1) / MT_KC);     // 64-wide k chunks of one tile
+    nsplit = std::max(1, std::min(nsplit, chunks));
+    const int chunks_per = (chunks + nsplit - 1) / nsplit;
+    nsplit = (chunks + chunks_per - 1) / chunks_per;
+    if (nsplit > 1 && ep.kind == EPI_PACK) { ok = false; return; }   // the operand image needs the whole sum
     if (nsmm >= CH_MAXSMM || !smm_is_fast(p) || p.beta != 0.f || (p.K % 32)) { ok = false; return; }
     if (ep.kind == EPI_PACK && (ep.pkC % 32 || (ep.pk0 && !wc_aligned16(ep.pk0)) || (ep.pk1 && !wc_aligned16(ep.pk1)))) { ok = false; return; }
     const long long lim = 1ll << 30;
@@ -1567,9 +1590,11 @@ struct ChainBuilder {
     j.sA = (int)p.sA; j.sB = (int)p.sB;
     j.K = p.K; j.nsum = p.nsum; j.nb2 = p.nb2; j.gx = p.N / SMM_T; j.gy = p.M / SMM_T;
     j.pk_slot_stride = (int)ep.pk_slot_stride; j.pkC = ep.pkC; j.row_per_b2 = ep.row_per_b2;
-    j.epi = (short)ep.kind; j.count_mode = (short)count_mode; j.tri = (short)p.tri; j.pad = 0;
+    j.epi = (short)ep.kind; j.count_mode = (short)count_mode; j.tri = (short)p.tri;
     j.alpha = p.alpha;
-    j.ntile = j.gx * j.gy * p.nb1 * p.nb2; j.sum_per = sum_per;
+    j.atomic = nsplit > 1 ? 1 : 0;
+    j.tri_enum = (ep.kind == EPI_PSI && nsplit > 1 && j.gx == j.gy) ? 1 : 0;
+    j.ntile = (j.tri_enum ? j.gy * (j.gy + 1) / 2 : j.gx * j.gy) * p.nb1 * p.nb2; j.chunks_per = chunks_per;
     const int nv = j.ntile * nsplit;
     if (stage2 < 0 || first_n >= nv) { ent(CJ_SMM, nsmm++, stage, nv); return; }
     if (nv > 32767 || nsplit2 >= 2) { ok = false; return; }
@@ -1984,7 +2009,7 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
                  const float* D, int E, float* dD, float* dclass_matrix, float* dbf, float* red, float* A, float* cvec,
                  const float* count_dev, double count_host, float eps, void* Tp_bwd, int pack_K, float* ws_color,
                  float* ws_factor, unsigned* barrier, int stage_lo, int stage_hi, void* const* xchg_peers, void* xchg_state,
-                 int xchg_rank, int xchg_world, int32_t* info, int wk_missing, int dweff_zeroed, cudaStream_t st) {
+                 int xchg_rank, int xchg_world, int32_t* info, int wk_missing, int dweff_zeroed, int ws_zeroed, cudaStream_t st) {
   if (!P || !s || !Weff || !Wk || !red || !barrier || Cin != Cout || g <= 0 || Cin % g) return WC_E_UNSUPPORTED;
   if (triangular && dWc) return WC_E_UNSUPPORTED;
   if ((dD || dclass_matrix) && (!class_matrix || !ehat || !D || E <= 0)) return WC_E_ARG;
@@ -2020,7 +2045,17 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
   // grid's worth of jobs in all.
   auto sum_split = [&](int nsum) {
     const int tiles = G * (g / SMM_T) * (g / SMM_T);
-    return (dweff_zeroed && nsum > 1) ? std::max(1, WC_NUM_SMS / std::max(1, tiles)) : 1;
+    if (!dweff_zeroed || nsum <= 1) return 1;
+    const int fit = std::max(1, WC_NUM_SMS / std::max(1, tiles)), per_part = (nsum + fit - 1) / fit;   // whole summed indices per part
+    return (nsum + per_part - 1) / per_part;
+  };
+  // Stage 2 has (g/32)^2 tiles per group for the whole grid (C = 256: 64 tiles of four chunks on 144 CTAs): with W1 zeroed by
+  // the caller the k range of a tile is cut so that the parts fill the grid once (Y: 5.0 -> 3.8 us).  Stage 3's tile also
+  // leaves as an operand image and needs the whole sum.
+  // A part keeps at least two chunks: a 1-chunk part pays more for its atomic epilogue than the chunk it saves (C = 128,
+  // measured).
+  auto k_split = [&](int tiles) {
+    return ws_zeroed ? std::max(1, std::min(WC_NUM_SMS / std::max(1, tiles), ((g + MT_KC - 1) / MT_KC) / 2)) : 1;
   };
   const bool fact = wc_bwd_factorised_ok(C, K, E, class_matrix != nullptr, dWc != nullptr) && D && stage_lo == 0 && stage_hi == 4 &&
                     (!dWu || Wu) && !dbc;
@@ -2095,7 +2130,9 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
       const WcSmm pq = smm_blockdiag_left(Weff, false, P, Qdst, g, G, C, C, K, per);
       const int tiles = G * (g / SMM_T) * (g / SMM_T), qtiles = (pq.M / SMM_T) * (pq.N / SMM_T) * pq.nb1 * pq.nb2;
       const int room = std::max(0, WC_NUM_SMS - cb.pr.stage_total[0]);
-      qspan = K > 1 && stage_lo == 0 && stage_hi == 4 && qtiles > room && (qtiles - room) + tiles + G * ((g + 31) / 32) <= WC_NUM_SMS &&
+      const int lower = G * (g / SMM_T) * (g / SMM_T + 1) / 2, nkc = (g + MT_KC - 1) / MT_KC;
+      const int psi_jobs = std::max(tiles, ws_zeroed ? lower * std::min(k_split(lower), nkc) : 0);   // virtual CTAs of Psi in stage 1 (upper bound)
+      qspan = K > 1 && stage_lo == 0 && stage_hi == 4 && qtiles > room && (qtiles - room) + psi_jobs + G * ((g + 31) / 32) <= WC_NUM_SMS &&
               !(wc_debug_flags() & 134217728);
       if (qspan) cb.smm(0, pq, SmmEpi{}, 0, 1, room, 1); else cb.smm(0 - base, pq);
     }
@@ -2103,6 +2140,9 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
   const int qs = qspan ? 1 : 0;      // the readers of Q run one stage later
   if (in(1)) {
     SmmEpi e1{}; e1.kind = EPI_PSI;
+    // (Psi is NOT split: measured at C = 256, four 1-chunk parts per lower tile cost 1.3 us more than one 4-chunk tile --
+    // every part pays the mirrored, uncoalesced red.global.add of both triangles.  The tile routine and the triangular
+    // enumeration support it: pass k_split(lower tiles) as the last argument.)
     cb.smm(1 - base, smm_gg(dWeff, false, Weff, true, W0, g, G), e1);
     VecJob vc{};
     vc.A = Weff; vc.x = gbar; vc.out = cvec; vc.M = g; vc.K = g; vc.rsA = 1; vc.csA = g;
@@ -2118,7 +2158,7 @@ int wc_bwd_chain(const float* P, const float* s, const float* Weff, const float*
   if (in(2)) {
     WcSmm py = smm_gg(W0, false, Weff, false, W1, g, G);
     py.rsC = 1; py.csC = g;                                   // stored transposed: the next product reads row panels
-    cb.smm(2 - base, py);
+    cb.smm(2 - base, py, SmmEpi{}, 0, k_split(G * (g / SMM_T) * (g / SMM_T)));
     if (dclass_matrix) { EltJob j{}; j.a = de; j.out = dclass_matrix; j.K = K; j.E = E; j.cm = class_matrix; j.ehat = ehat; cb.elt(2 + qs - base, CJ_L2N, j, 1); }
   }
   if (in(3)) {

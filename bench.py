@@ -444,6 +444,13 @@ def run_ours(args):
 
     def e2e_step(i):
         b = i % 2
+        # The results of the step that used this slot two steps ago are released HERE, on the compute stream, after that
+        # stream has been made to wait for their read-back: the caching allocator can then hand the same blocks to this
+        # step.  (With Tensor.record_stream instead, a block becomes reusable only once an event recorded at free time
+        # has completed; the host runs several steps ahead of the device, so every step allocated fresh 67 MB blocks
+        # with cudaMalloc -- hidden on boxes where that call is fast, 15 ms per step where it is not.)
+        cur.wait_event(ev_out[b])
+        alive[b] = None
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_comp[b])            # the step that last read this input pair has run
             xd[b].copy_(xh[b], non_blocking=True)
@@ -460,7 +467,6 @@ def run_ours(args):
             yh[b].copy_(y.detach(), non_blocking=True)
             dxh[b].copy_(gr[0], non_blocking=True)
             ev_out[b].record(s_out)
-        y.record_stream(s_out); gr[0].record_stream(s_out)
         alive[b] = (y, gr)
 
     def e2e_drain():

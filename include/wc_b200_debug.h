@@ -21,6 +21,12 @@ int wc_debug_marks(unsigned long long* host_out);
 /* per-CTA / per-phase timestamps of the last Cholesky launch (cluster kernel: [8][32] u64; one-CTA kernel: [64] i64)  */
 int wc_debug_chol_cluster_timing(unsigned long long* host_out);
 int wc_debug_chol_timing(long long* host_out);
+/* The program (stages, grid, jobs) the backward chain launch would run for a Cholesky layer with Cin = Cout = C, group size g,
+ * K classes and E embedding filters, written to out[] WITHOUT touching the device (host logic only; used by the CPU tests):
+ * out = {stages, grid, entries, stage_total[6], then per entry {type, stage, virtual CTAs, first part, chunks per part,
+ * atomic + 2 * epilogue}}.  what: 1 unconditional kernel, 2 per-class kernels, 4 factorized branch, 8 adjoint buffer zeroed
+ * by the caller (split class sums), 16 scratch matrices zeroed (K-split of stage 2).  Returns 0 or a WC_E_* code.          */
+int wc_debug_bwd_chain_plan(int C, int g, int K, int E, int what, int* out, int out_len);
 
 #ifdef __cplusplus
 }

@@ -1553,6 +1553,9 @@ int wc_factor_fwd_impl(const float* mean, const float* S, const float* count_dev
 // host side of the chain launches (forward: K2b; backward: K5a + K5b)
 // =============================================================================================
 namespace {
+// debug / test hook (wc_debug_bwd_chain_plan): when set, ChainBuilder::launch() writes the plan here instead of launching
+thread_local int* t_chain_plan_out = nullptr;
+thread_local int t_chain_plan_len = 0;
 struct ChainBuilder {
   ChainProgram pr{};
   int nsmm = 0, nvec = 0, nelt = 0, nsplit2 = 0;
@@ -1626,6 +1629,23 @@ struct ChainBuilder {
     int mx = 1;
     for (int s2 = 0; s2 < pr.nstages; ++s2) mx = std::max(mx, pr.stage_total[s2]);
     pr.barrier = barrier; pr.dbg = wc_debug_buf(); pr.dbg_flags = wc_debug_flags();
+    if (t_chain_plan_out) {
+      // {stages, grid, entries, stage_total[0 .. CH_MAXSTAGE), then per entry: type, stage, virtual CTAs, first part, and for
+      //  tile products chunks per part and the atomic flag}
+      int* o = t_chain_plan_out;
+      const int need = 3 + CH_MAXSTAGE + 6 * pr.nent;
+      if (t_chain_plan_len < need) return WC_E_WORKSPACE;
+      o[0] = pr.nstages; o[1] = std::min(mx, WC_NUM_SMS); o[2] = pr.nent;
+      for (int s2 = 0; s2 < CH_MAXSTAGE; ++s2) o[3 + s2] = pr.stage_total[s2];
+      for (int e = 0; e < pr.nent; ++e) {
+        int* q = o + 3 + CH_MAXSTAGE + 6 * e;
+        const ChainEnt& en = pr.ent[e];
+        q[0] = en.type; q[1] = en.stage; q[2] = en.n; q[3] = en.l0;
+        q[4] = en.type == CJ_SMM ? pr.smm[en.idx].chunks_per : 0;
+        q[5] = en.type == CJ_SMM ? pr.smm[en.idx].atomic + 2 * pr.smm[en.idx].epi : 0;
+      }
+      return 0;
+    }
     static bool attr_set = false;
     if (!attr_set) {
       WC_CUDA(cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
@@ -2181,6 +2201,24 @@ extern "C" int wc_factor_bwd(const float* dWeff, const float* gbar, const float*
                              size_t workspace_bytes, wc_stream_t stream) {
   return wc_factor_bwd_impl(dWeff, gbar, Weff, Wm, R, U, lam, count_dev, count_host, C, g, eps, decomposition, renorm, A, cvec,
                             workspace, workspace_bytes, nullptr, 0, (cudaStream_t)stream);
+}
+
+// Test / debug hook (include/wc_b200_debug.h): the program wc_bwd_chain would launch for a whole backward chain of a
+// Cholesky layer with Cin = Cout = C, without touching the device.  what: 1 unconditional kernel (Wu, dWu, dbu), 2 per-class
+// kernels (dWc, dbc), 4 factorized branch (class_matrix, D, dD, dclass_matrix), 8 the adjoint buffer is zeroed (split class
+// sums), 16 the scratch matrices are zeroed (K-split of stage 2).
+extern "C" int wc_debug_bwd_chain_plan(int C, int g, int K, int E, int what, int* out, int out_len) {
+  if (!out || C <= 0 || g <= 0 || C % g || K <= 0) return WC_E_ARG;
+  float* const d = reinterpret_cast<float*>(uintptr_t(4096));        // never dereferenced on the host
+  const bool u = what & 1, cc = what & 2, f = (what & 4) && E > 0;
+  unsigned* bar = reinterpret_cast<unsigned*>(uintptr_t(8192));
+  t_chain_plan_out = out; t_chain_plan_len = out_len;
+  const int rc = wc_bwd_chain(d, d, d, d, u ? d : nullptr, C, C, g, K, u ? d : nullptr, u ? d : nullptr, cc ? d : nullptr,
+                              cc ? d : nullptr, 0, f ? d : nullptr, f ? d : nullptr, f ? d : nullptr, f ? E : 0, f ? d : nullptr,
+                              f ? d : nullptr, nullptr, d, d, d, nullptr, 65536.0, 1e-3f, g == C ? d : nullptr, K, d, d, bar, 0, 4, nullptr, nullptr, 0, 1,
+                              nullptr, 0, (what & 8) != 0, (what & 16) != 0, nullptr);
+  t_chain_plan_out = nullptr; t_chain_plan_len = 0;
+  return rc;
 }
 
 extern "C" int wc_version(void) { return WC_B200_VERSION; }

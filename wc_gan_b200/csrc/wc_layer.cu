@@ -230,12 +230,15 @@ extern "C" int wc_layer_bwd(const WcLayerCall* cp, wc_stream_t stream) {
   // the sums over classes (or basis matrices) that form dWeff are split over several CTAs which add into c.red: the kernel
   // that zeroes P and s clears it too
   // (experiment bit 2^26 = 67108864: one CTA per tile walks the whole sum, as before)
-  const bool split_sum = chain_ok && (c.phases & WC_PHASE_REDUCE) && c.K > 1 && wc_aligned16(c.red) && !(wc_debug_flags() & 67108864);
+  // Only with use_tensor_cores: the FFMA path (use_tensor_cores = 0) stays deterministic, and sums added in arrival order
+  // are not.
+  const bool split_sum = chain_ok && c.use_tensor_cores && (c.phases & WC_PHASE_REDUCE) && c.K > 1 && wc_aligned16(c.red) &&
+                         !(wc_debug_flags() & 67108864);
   // The products of stages 1 and 2 (Psi, Y) are split along K over several CTAs that add their partial tiles into the two
   // scratch matrices at the head of the factor workspace: cleared by the same kernel, when the whole chain runs in this call.
   // (experiment bit 2^28 = 268435456: one CTA per tile)
   const bool whole_call = (c.phases & WC_PHASE_REDUCE) && (c.phases & WC_PHASE_DX) && c.dx;
-  const bool split_k = chain_ok && whole_call && W.factor_bytes >= 2 * wc_align_up(gg * 4, 256) &&
+  const bool split_k = chain_ok && c.use_tensor_cores && whole_call && W.factor_bytes >= 2 * wc_align_up(gg * 4, 256) &&
                        wc_aligned16(at<float>(c.workspace, W.factor)) && !(wc_debug_flags() & 268435456);
   auto chain = [&](int lo, int hi, bool exchange) {
     return wc_bwd_chain(P, s, at<float>(c.saved, L.Weff), Wk, c.Wu, c.Cin, c.Cout, g, c.K, c.dWu, c.dbu, c.dWc, c.dbc, c.triangular,
